@@ -1,0 +1,174 @@
+/*
+ * xenomapper_b200.h -- C ABI of libxenomapper_b200.so
+ *
+ * Drop-in boundary for xenomapper's read-binning hot path.  Each entry point
+ * names the piece of the reference it stands in for; all citations are into
+ * xenomapper/xenomapper.py of genomematt/xenomapper v1.0.2 ("xm.py").
+ *
+ * The library replaces, as ONE call, what the reference does with
+ *     readpairs = getReadPairs(sam1, sam2, skip_repeated_reads)     xm.py:95-118
+ *     counts    = main_single_end | main_paired_end |
+ *                 conservative_main_paired_end(readpairs, six outputs,
+ *                                min_score, tag_func)                xm.py:291-556
+ * where tag_func is get_tag (xm.py:176), get_tag_with_ZS_as_XS (xm.py:193) or
+ * get_cigarbased_AS_tag (xm.py:228).  Headers (process_headers, xm.py:133)
+ * and the summary table (output_summary, xm.py:558) stay in the Python host
+ * shim, xenomapper_b200/xenomapper.py.
+ *
+ * Plain C types only: bind with ctypes / cffi / cgo / JNI alike.  There is no
+ * CPU fallback: every classify call runs the sm_100a CUDA kernels and fails
+ * with XM_ERR_CUDA when no usable device is present.
+ */
+#ifndef XENOMAPPER_B200_H
+#define XENOMAPPER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XM_ABI_VERSION 1
+
+/* States and bins share one numbering: the order of the reference's output
+ * arguments (xm.py:291-297).  counts[] is indexed [state] for single-end and
+ * [forward_state * 6 + reverse_state] for paired walks (xm.py:330, :420). */
+enum xm_bin {
+    XM_PRIMARY_SPECIFIC = 0,
+    XM_SECONDARY_SPECIFIC = 1,
+    XM_PRIMARY_MULTI = 2,
+    XM_SECONDARY_MULTI = 3,
+    XM_UNASSIGNED = 4,
+    XM_UNRESOLVED = 5
+};
+
+enum xm_mode {
+    XM_MODE_SE = 0,              /* main_single_end, xm.py:291 */
+    XM_MODE_PE_LIBERAL = 1,      /* main_paired_end, xm.py:354 */
+    XM_MODE_PE_CONSERVATIVE = 2  /* conservative_main_paired_end, xm.py:456 */
+};
+
+enum xm_score_src {
+    XM_SCORE_AS_XS = 0,          /* tag_func = get_tag */
+    XM_SCORE_AS_ZS = 1,          /* tag_func = get_tag_with_ZS_as_XS (--use_zs) */
+    XM_SCORE_CIGAR_NM = 2        /* tag_func = get_cigarbased_AS_tag (--cigar_scores) */
+};
+
+/* Return codes.  1..4 map onto the exception the reference raises on the same
+ * input; the host shim re-raises that class. */
+enum xm_status {
+    XM_OK = 0,
+    XM_ERR_ASSERT = 1,       /* AssertionError: QNAMEs differ at a yielded index (xm.py:106) */
+    XM_ERR_VALUE = 2,        /* ValueError: duplicate tag (xm.py:190) or float()/int() rejects the value */
+    XM_ERR_RUNTIME = 3,      /* RuntimeError (xm.py:289) */
+    XM_ERR_UNICODE = 4,      /* UnicodeDecodeError from the reference's 'rt' file layer */
+    XM_ERR_UNSUPPORTED = 5,  /* valid for the reference, outside the device grammar: non-integer or
+                                >31-bit scores, non-ASCII bytes, a lone '\r' line break.  Detected and
+                                reported, never mis-scored. */
+    XM_ERR_NOMEM = 6,
+    XM_ERR_CUDA = 7,
+    XM_ERR_ARG = 8,
+    XM_ERR_IO = 9
+};
+
+typedef struct xm_opts {
+    int32_t mode;            /* enum xm_mode */
+    int32_t score_src;       /* enum xm_score_src */
+    int32_t skip_repeated;   /* getReadPairs(skip_repeated_reads=...), xm.py:110; the CLI sets it for SE (xm.py:691) */
+    uint32_t enabled_bins;   /* bit b: bin b has an output.  Disabled bins still count (xm.py:330-349) */
+    double min_score;        /* --min_score; -inf default (xm.py:298) */
+} xm_opts;
+
+typedef struct xm_result {
+    uint64_t counts[36];     /* category histogram; zero entries are categories that never occurred */
+    uint64_t n_records;      /* records the lockstep reader yielded (xm.py:107) */
+    uint64_t out_len[6];     /* bytes written to each bin (0 for disabled bins) */
+    uint64_t bytes_in[2];    /* raw bytes of the yielded primary / secondary records (roofline numerator) */
+    int32_t status;          /* enum xm_status of the first failing record, XM_OK otherwise */
+    int32_t err_stream;      /* 0 primary, 1 secondary, -1 n/a */
+    uint64_t err_record;     /* index in the yielded sequence of the failing record */
+    float ms_scan;           /* device time of the secondary-stream scan kernel */
+    float ms_classify;       /* device time of the primary-stream classify+emit kernel */
+    float ms_total;          /* device time of the whole call (CUDA events) */
+    uint32_t n_launches;     /* kernels launched by the call */
+} xm_result;
+
+typedef struct xm_ctx xm_ctx;
+
+/* ---- lifetime -------------------------------------------------------- */
+
+/* One context per process and device.  flags: 0.  NULL on failure (see
+ * xm_last_error(NULL)). */
+xm_ctx *xm_create(int device, uint32_t flags);
+void xm_destroy(xm_ctx *ctx);
+const char *xm_last_error(const xm_ctx *ctx);
+int xm_abi_version(void);
+
+/* ---- device-resident walk ------------------------------------------- */
+
+/* Inputs and outputs live in device memory (16-byte aligned, readable up to
+ * the next multiple of 16 past their length).  d_prim / d_sec are the record
+ * regions of the two SAM files: everything after the '@' header lines.
+ * d_out[b] receives bin b's lines, in input order; out_cap[b] is its
+ * capacity.  A bin that would overflow makes the call fail with XM_ERR_ARG
+ * after reporting the needed sizes in res->out_len.  Replaces xm.py:95-118
+ * + 291-556 for callers that keep SAM text on the GPU. */
+int xm_classify_device(xm_ctx *ctx, const void *d_prim, uint64_t prim_len,
+                       const void *d_sec, uint64_t sec_len, const xm_opts *opts,
+                       void *const d_out[6], const uint64_t out_cap[6], xm_result *res);
+
+/* ---- host-buffer walk ------------------------------------------------- */
+
+/* Same walk on host memory (pageable or pinned): the library stages the two
+ * record regions through pinned double buffers with cudaMemcpyAsync, runs the
+ * kernels chunk by chunk, and returns the six bins in library-owned host
+ * buffers (valid until the next classify call or xm_destroy).  This is what
+ * the ctypes shim calls for file-likes without a descriptor (xm.py tests). */
+int xm_classify_host(xm_ctx *ctx, const void *prim, uint64_t prim_len,
+                     const void *sec, uint64_t sec_len, const xm_opts *opts, xm_result *res);
+int xm_get_output(xm_ctx *ctx, int bin, const void **data, uint64_t *len);
+
+/* ---- file-descriptor walk ---------------------------------------------- */
+
+/* Streams two seekable SAM files from the given byte offsets (the first byte
+ * after each header) and appends each bin to out_fds[b] (-1 = disabled) with
+ * write(2), in record order.  The caller flushes anything it already wrote to
+ * those descriptors first (process_headers output).  Replaces the CLI's use
+ * of getReadPairs + main_* on real files (xm.py:702-740). */
+int xm_classify_fds(xm_ctx *ctx, int fd_prim, int64_t off_prim, int fd_sec, int64_t off_sec,
+                    const int out_fds[6], const xm_opts *opts, xm_result *res);
+
+/* ---- sharded walk (one process per GPU) -------------------------------- */
+
+/* Counting pass: how many records (after skip_repeated de-duplication if set)
+ * a byte range holds, where its first record starts, and whether a blank line
+ * ends the stream inside it.  Ranks exchange these 4 words (NCCL allgather in
+ * bench.py / the shim) to turn byte shards into record-index shards. */
+typedef struct xm_shard_info {
+    uint64_t n_records;      /* records that START in [begin, end) */
+    uint64_t first_start;    /* byte offset (in the whole stream) of the first of them, or end */
+    uint64_t stop_at;        /* index within this shard of the first blank line, or UINT64_MAX */
+    uint64_t reserved;
+} xm_shard_info;
+int xm_count_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repeated, xm_shard_info *info);
+
+/* ---- device memory helpers (so bindings need no CUDA of their own) ----- */
+int xm_dev_alloc(xm_ctx *ctx, uint64_t bytes, void **d_ptr);
+int xm_dev_free(xm_ctx *ctx, void *d_ptr);
+int xm_host_alloc_pinned(xm_ctx *ctx, uint64_t bytes, void **h_ptr);
+int xm_host_free_pinned(xm_ctx *ctx, void *h_ptr);
+int xm_memcpy_h2d(xm_ctx *ctx, void *d_dst, const void *h_src, uint64_t bytes);
+int xm_memcpy_d2h(xm_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes);
+int xm_memcpy_d2d(xm_ctx *ctx, void *d_dst, const void *d_src, uint64_t bytes);
+int xm_dev_mem_info(xm_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
+
+/* tuning knobs for tests: which tile geometry and parse path the kernels use */
+#define XM_DEBUG_FORCE_GENERIC 1u   /* every line through the exact byte-wise tokeniser */
+#define XM_DEBUG_SMALL_TILES   2u   /* 1 KiB tiles: exercises tile-boundary logic on small inputs */
+int xm_set_debug(xm_ctx *ctx, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XENOMAPPER_B200_H */

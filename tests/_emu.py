@@ -1,0 +1,58 @@
+"""ctypes face of the CPU emulation of the tile programs (tests/emu/xm_emu.cpp).  Test scaffolding only."""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "emu", "xm_emu.cpp")
+SO = os.path.join(HERE, "emu", "libxm_emu.so")
+DEPS = [SRC] + [os.path.join(ROOT, "xenomapper_b200", "csrc", f) for f in
+                ("xm_common.h", "xm_parse.h", "xm_tile.h", "xm_walk.h")] + [os.path.join(ROOT, "include", "xenomapper_b200.h")]
+
+
+class Opts(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("score_src", C.c_int32), ("skip_repeated", C.c_int32),
+                ("enabled_bins", C.c_uint32), ("min_score", C.c_double)]
+
+
+class Result(C.Structure):
+    _fields_ = [("counts", C.c_uint64 * 36), ("n_records", C.c_uint64), ("out_len", C.c_uint64 * 6),
+                ("bytes_in", C.c_uint64 * 2), ("status", C.c_int32), ("err_stream", C.c_int32),
+                ("err_record", C.c_uint64), ("ms_scan", C.c_float), ("ms_classify", C.c_float),
+                ("ms_total", C.c_float), ("n_launches", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
+            subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                                   "-o", SO, SRC])
+        _lib = C.CDLL(SO)
+        _lib.xm_emu_classify.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(Opts), C.c_uint32,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Result),
+                                         C.c_char_p, C.c_size_t]
+        _lib.xm_emu_classify.restype = C.c_int
+    return _lib
+
+
+def classify(prim, sec, mode=0, score_src=0, skip_repeated=False, min_score=float("-inf"), enabled_bins=0x3F,
+             debug=0, cap=None):
+    L = lib()
+    prim, sec = bytes(prim), bytes(sec)
+    if cap is None:
+        cap = 4 * (len(prim) + len(sec)) + 64     # a pair walk can emit a line twice (overlapping units)
+    bufs = [C.create_string_buffer(cap) for _ in range(6)]
+    outp = (C.c_void_p * 6)(*[C.cast(b, C.c_void_p) for b in bufs])
+    caps = (C.c_uint64 * 6)(*([cap] * 6))
+    o = Opts(mode, score_src, int(bool(skip_repeated)), enabled_bins, min_score)
+    r = Result()
+    err = C.create_string_buffer(512)
+    rc = L.xm_emu_classify(prim, len(prim), sec, len(sec), C.byref(o), debug, outp, caps, C.byref(r), err, 512)
+    outs = [bufs[b].raw[:r.out_len[b]] for b in range(6)]
+    return dict(status=rc, outputs=outs, counts=list(r.counts), n_records=r.n_records, err_record=r.err_record,
+                bytes_in=list(r.bytes_in), message=err.value.decode())

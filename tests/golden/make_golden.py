@@ -175,7 +175,7 @@ def adversarial():
     add("space_in_tags_changes_tokens", lines(rec("a", tags=("AS:i:66 XN:i:0", "MD:Z:50 YT:Z:UU"))), lines(rec("a", tags=("AS:i:66  XS:i:66",))))
     add("utf8_in_qname", lines(rec("réad")), lines(rec("réad", tags=("AS:i:1",))), gpu="unsupported")
     add("nbsp_separator", lines(rec("a").replace("\t", " ", 2)), lines(rec("a", tags=("AS:i:1",))), gpu="unsupported")
-    add("invalid_utf8", lines(rec("a")).replace(b"chr1", b"ch\xff1"), lines(rec("a")), gpu="unsupported")
+    add("invalid_utf8", lines(rec("a")).replace(b"chr1", b"ch\xff1"), lines(rec("a")))
     # single-end duplicates handling (CLI default for SE, xm.py:691)
     runs_p = [rec(q, tags=("AS:i:%d" % a,)) for q, a in (("a", 9), ("a", 8), ("b", 7), ("c", 6), ("c", 5), ("c", 4), ("d", 3))]
     runs_s = [rec(q, tags=("AS:i:%d" % a,)) for q, a in (("a", 1), ("b", 9), ("b", 8), ("b", 8), ("c", 2), ("d", 9), ("d", 1))]

@@ -1,0 +1,42 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the reference goldens and the oracle."""
+import pytest
+
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+
+ERR = {0: None, 1: "AssertionError", 2: "ValueError", 3: "RuntimeError", 4: "UnicodeDecodeError", 5: "Unsupported"}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from xenomapper_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def run_case(ctx, case, debug):
+    from xenomapper_b200 import _lib
+    ctx.set_debug(debug)
+    p, s = G.case_records(case)
+    o = case["opts"]
+    opts = _lib.Context.opts(o["mode"], o["score_src"], o["skip_repeated"], o["min_score"], o["enabled_bins"])
+    rc, res, outs = ctx.classify_host(p, s, opts)
+    e = case["expect"]
+    if case["gpu"] == "unsupported":
+        assert rc == _lib.XM_ERR_UNSUPPORTED, ctx.error()
+        return
+    assert ERR[rc] == e["error"], ctx.error()
+    assert [len(x) for x in outs] == e["records_len"]
+    assert [G.sha(x) for x in outs] == e["records_sha256"]
+    if e["error"] is None:
+        assert G.counts_dict(list(res.counts), o["mode"]) == e["counts"]
+
+
+@pytest.mark.parametrize("debug", [0, 1, 2, 3], ids=["big", "big_generic", "small", "small_generic"])
+@pytest.mark.parametrize("case", G.CASES, ids=[c["name"] for c in G.CASES])
+def test_cuda_matches_reference_golden(ctx, case, debug):
+    if debug >= 2 and case["input"]["kind"] == "synth" and case["input"]["seed"] != 1:
+        pytest.skip("covered by seed 1")
+    run_case(ctx, case, debug)

@@ -1,0 +1,221 @@
+"""ctypes binding of libxenomapper_b200.so (include/xenomapper_b200.h).
+
+The library is the only implementation of the read-binning walk in this
+package: if it is missing or no B200 is usable, loading / Context() raises.
+There is no Python or CPU fallback.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxenomapper_b200.so")
+
+BINS = ("primary_specific", "secondary_specific", "primary_multi",
+        "secondary_multi", "unassigned", "unresolved")
+MODE_SE, MODE_PE_LIBERAL, MODE_PE_CONSERVATIVE = 0, 1, 2
+SCORE_AS_XS, SCORE_AS_ZS, SCORE_CIGAR_NM = 0, 1, 2
+(XM_OK, XM_ERR_ASSERT, XM_ERR_VALUE, XM_ERR_RUNTIME, XM_ERR_UNICODE, XM_ERR_UNSUPPORTED,
+ XM_ERR_NOMEM, XM_ERR_CUDA, XM_ERR_ARG, XM_ERR_IO) = range(10)
+DEBUG_FORCE_GENERIC, DEBUG_SMALL_TILES = 1, 2
+
+EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_classify_device",
+           "xm_classify_host", "xm_get_output", "xm_classify_fds", "xm_count_device", "xm_dev_alloc",
+           "xm_dev_free", "xm_host_alloc_pinned", "xm_host_free_pinned", "xm_memcpy_h2d", "xm_memcpy_d2h",
+           "xm_memcpy_d2d", "xm_dev_mem_info", "xm_set_debug")
+
+
+class Opts(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("score_src", C.c_int32), ("skip_repeated", C.c_int32),
+                ("enabled_bins", C.c_uint32), ("min_score", C.c_double)]
+
+
+class Result(C.Structure):
+    _fields_ = [("counts", C.c_uint64 * 36), ("n_records", C.c_uint64), ("out_len", C.c_uint64 * 6),
+                ("bytes_in", C.c_uint64 * 2), ("status", C.c_int32), ("err_stream", C.c_int32),
+                ("err_record", C.c_uint64), ("ms_scan", C.c_float), ("ms_classify", C.c_float),
+                ("ms_total", C.c_float), ("n_launches", C.c_uint32)]
+
+
+class ShardInfo(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("first_start", C.c_uint64), ("stop_at", C.c_uint64),
+                ("reserved", C.c_uint64)]
+
+
+class XenomapperLibraryError(RuntimeError):
+    """CUDA / allocation / argument failures of the native library."""
+
+
+class UnsupportedInput(ValueError):
+    """Input the reference accepts but the device grammar does not (XM_ERR_UNSUPPORTED)."""
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XenomapperLibraryError(
+            "%s is missing: build it with `python -m xenomapper_b200.build` (needs nvcc). "
+            "xenomapper_b200 has no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i = C.c_void_p, C.c_uint64, C.c_int
+    L.xm_abi_version.restype = i
+    L.xm_create.argtypes = [i, C.c_uint32]
+    L.xm_create.restype = vp
+    L.xm_destroy.argtypes = [vp]
+    L.xm_destroy.restype = None
+    L.xm_last_error.argtypes = [vp]
+    L.xm_last_error.restype = C.c_char_p
+    L.xm_classify_device.argtypes = [vp, vp, u64, vp, u64, C.POINTER(Opts), C.POINTER(vp), C.POINTER(u64), C.POINTER(Result)]
+    L.xm_classify_host.argtypes = [vp, vp, u64, vp, u64, C.POINTER(Opts), C.POINTER(Result)]
+    L.xm_get_output.argtypes = [vp, i, C.POINTER(vp), C.POINTER(u64)]
+    L.xm_classify_fds.argtypes = [vp, i, C.c_int64, i, C.c_int64, C.POINTER(i), C.POINTER(Opts), C.POINTER(Result)]
+    L.xm_count_device.argtypes = [vp, vp, u64, i, C.POINTER(ShardInfo)]
+    L.xm_dev_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    L.xm_dev_free.argtypes = [vp, vp]
+    L.xm_host_alloc_pinned.argtypes = [vp, u64, C.POINTER(vp)]
+    L.xm_host_free_pinned.argtypes = [vp, vp]
+    L.xm_memcpy_h2d.argtypes = [vp, vp, vp, u64]
+    L.xm_memcpy_d2h.argtypes = [vp, vp, vp, u64]
+    L.xm_memcpy_d2d.argtypes = [vp, vp, vp, u64]
+    L.xm_dev_mem_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.xm_set_debug.argtypes = [vp, C.c_uint32]
+    for name in EXPORTS:
+        if name not in ("xm_create", "xm_destroy", "xm_last_error", "xm_abi_version"):
+            getattr(L, name).restype = i
+    _lib = L
+    return L
+
+
+def _host_ptr(buf):
+    """(address, length, keep-alive) for bytes / bytearray / memoryview / numpy uint8 arrays"""
+    if isinstance(buf, bytes):
+        return C.cast(C.c_char_p(buf), C.c_void_p), len(buf), buf
+    if isinstance(buf, (bytearray, memoryview)):
+        mv = memoryview(buf).cast("B")
+        if mv.readonly:
+            b = mv.tobytes()
+            return C.cast(C.c_char_p(b), C.c_void_p), len(b), b
+        arr = (C.c_char * len(mv)).from_buffer(mv)
+        return C.cast(arr, C.c_void_p), len(mv), arr
+    return C.c_void_p(buf.ctypes.data), buf.nbytes, buf
+
+
+class Context:
+    """One xm_ctx: a CUDA device, its streams and scratch."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self.h = self.lib.xm_create(device, 0)
+        if not self.h:
+            raise XenomapperLibraryError(self.lib.xm_last_error(None).decode() or "xm_create failed")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.xm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def error(self):
+        return self.lib.xm_last_error(self.h).decode()
+
+    def _check(self, rc, what):
+        if rc in (XM_ERR_NOMEM, XM_ERR_CUDA, XM_ERR_ARG, XM_ERR_IO):
+            raise XenomapperLibraryError("%s failed (%d): %s" % (what, rc, self.error()))
+        return rc
+
+    def set_debug(self, flags):
+        self.lib.xm_set_debug(self.h, flags)
+
+    # ---- memory -------------------------------------------------------------
+    def dev_alloc(self, n):
+        p = C.c_void_p()
+        self._check(self.lib.xm_dev_alloc(self.h, n, C.byref(p)), "xm_dev_alloc")
+        return p.value
+
+    def dev_free(self, p):
+        self.lib.xm_dev_free(self.h, p)
+
+    def pinned_alloc(self, n):
+        p = C.c_void_p()
+        self._check(self.lib.xm_host_alloc_pinned(self.h, n, C.byref(p)), "xm_host_alloc_pinned")
+        return p.value
+
+    def pinned_free(self, p):
+        self.lib.xm_host_free_pinned(self.h, p)
+
+    def h2d(self, d, host, n=None):
+        a, ln, keep = _host_ptr(host) if not isinstance(host, int) else (C.c_void_p(host), n, None)
+        self._check(self.lib.xm_memcpy_h2d(self.h, d, a, ln if n is None else n), "xm_memcpy_h2d")
+
+    def d2h(self, d, n):
+        buf = C.create_string_buffer(n) if n else C.create_string_buffer(1)
+        if n:
+            self._check(self.lib.xm_memcpy_d2h(self.h, buf, d, n), "xm_memcpy_d2h")
+        return buf.raw[:n]
+
+    def d2d(self, dst, src, n):
+        self._check(self.lib.xm_memcpy_d2d(self.h, dst, src, n), "xm_memcpy_d2d")
+
+    def mem_info(self):
+        f, t = C.c_uint64(), C.c_uint64()
+        self.lib.xm_dev_mem_info(self.h, C.byref(f), C.byref(t))
+        return f.value, t.value
+
+    # ---- walks --------------------------------------------------------------
+    @staticmethod
+    def opts(mode=MODE_SE, score_src=SCORE_AS_XS, skip_repeated=False, min_score=float("-inf"), enabled_bins=0x3F):
+        return Opts(mode, score_src, int(bool(skip_repeated)), enabled_bins, min_score)
+
+    def classify_device(self, d_prim, prim_len, d_sec, sec_len, opts, d_out, out_cap):
+        res = Result()
+        outp = (C.c_void_p * 6)(*d_out)
+        caps = (C.c_uint64 * 6)(*out_cap)
+        rc = self.lib.xm_classify_device(self.h, d_prim, prim_len, d_sec, sec_len, C.byref(opts), outp, caps, C.byref(res))
+        self._check(rc, "xm_classify_device")
+        return rc, res
+
+    def classify_host(self, prim, sec, opts, want_outputs=True):
+        """prim / sec: bytes-like record regions (or (address, length) tuples of pinned memory)."""
+        pa, pn, pk = prim + (None,) if isinstance(prim, tuple) else _host_ptr(prim)
+        sa, sn, sk = sec + (None,) if isinstance(sec, tuple) else _host_ptr(sec)
+        res = Result()
+        rc = self.lib.xm_classify_host(self.h, pa, pn, sa, sn, C.byref(opts), C.byref(res))
+        self._check(rc, "xm_classify_host")
+        outs = None
+        if want_outputs:
+            outs = []
+            for b in range(6):
+                p, n = C.c_void_p(), C.c_uint64()
+                self.lib.xm_get_output(self.h, b, C.byref(p), C.byref(n))
+                outs.append(C.string_at(p.value, n.value) if n.value else b"")
+        del pk, sk
+        return rc, res, outs
+
+    def classify_fds(self, fd_prim, off_prim, fd_sec, off_sec, out_fds, opts):
+        res = Result()
+        fds = (C.c_int * 6)(*out_fds)
+        rc = self.lib.xm_classify_fds(self.h, fd_prim, off_prim, fd_sec, off_sec, fds, C.byref(opts), C.byref(res))
+        self._check(rc, "xm_classify_fds")
+        return rc, res
+
+    def count_device(self, d_buf, n, skip_repeated=False):
+        info = ShardInfo()
+        self._check(self.lib.xm_count_device(self.h, d_buf, n, int(bool(skip_repeated)), C.byref(info)), "xm_count_device")
+        return info
+
+
+_default_ctx = None
+
+
+def default_context():
+    """Process-wide context on the device named by XENOMAPPER_DEVICE (default: LOCAL_RANK or 0)."""
+    global _default_ctx
+    if _default_ctx is None:
+        dev = int(os.environ.get("XENOMAPPER_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        _default_ctx = Context(dev)
+    return _default_ctx

@@ -1,0 +1,417 @@
+/*
+ * xm_api.cu -- the C ABI of libxenomapper_b200.so (include/xenomapper_b200.h):
+ * context, device/pinned memory, the resident walk, the host-buffer walk with
+ * pinned double-buffered staging, and the file-descriptor walk.
+ *
+ * There is no CPU classification path in this library.  If no CUDA device is
+ * usable xm_create fails and every other entry point returns XM_ERR_CUDA.
+ */
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/xenomapper_b200.h"
+#include "xm_common.h"
+#include "xm_launch.h"
+#include "xm_walk.h"
+
+using namespace xm;
+
+static thread_local std::string g_create_error;
+
+struct DeviceBackend {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    std::string err;
+    int chk(cudaError_t e)
+    {
+        if (e == cudaSuccess) return 0;
+        err = cudaGetErrorString(e);
+        return 1;
+    }
+    void *alloc(size_t n)
+    {
+        void *p = nullptr;
+        if (chk(cudaMalloc(&p, n ? n : 16))) return nullptr;
+        return p;
+    }
+    void release(void *p) { if (p) cudaFree(p); }
+    int zero(void *p, size_t n) { return n ? chk(cudaMemsetAsync(p, 0, n, st)) : 0; }
+    int write(void *d, const void *s, size_t n) { return chk(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st)) || chk(cudaStreamSynchronize(st)); }
+    int read(void *d, const void *s, size_t n) { return chk(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st)) || chk(cudaStreamSynchronize(st)); }
+    int sync() { return chk(cudaStreamSynchronize(st)); }
+    void tick(int k) { cudaEventRecord(ev[k], st); }
+    float elapsed(int a, int b)
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[a], ev[b]);
+        return ms;
+    }
+    std::string last_error() { return err; }
+    int scan(const ScanArgs &a, bool small) { return chk(launch_scan(a, small, st)); }
+    int classify(const ClassifyArgs &a, bool small) { return chk(launch_classify(a, small, st)); }
+};
+
+struct DevBuf {
+    uint8_t *p = nullptr;
+    uint64_t cap = 0;
+};
+struct HostBuf {
+    uint8_t *p = nullptr;
+    uint64_t cap = 0, len = 0;
+};
+
+struct xm_ctx {
+    int device = 0;
+    DeviceBackend be;
+    cudaStream_t copy_st[2] = {nullptr, nullptr};
+    Scratch scratch;
+    uint32_t debug = 0;
+    std::string err;
+    /* host-buffer walk: device staging and outputs, host outputs */
+    DevBuf d_in[2], d_out[6];
+    HostBuf h_out[6];
+    HostBuf h_stage[2];      /* pinned staging for pageable sources */
+};
+
+static int fail(xm_ctx *c, int code, const std::string &msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+static int cuda_fail(xm_ctx *c, cudaError_t e, const char *what)
+{
+    return fail(c, XM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define XM_CUDA(c, call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail((c), e_, (what)); } while (0)
+
+extern "C" {
+
+int xm_abi_version(void) { return XM_ABI_VERSION; }
+
+const char *xm_last_error(const xm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+xm_ctx *xm_create(int device, uint32_t flags)
+{
+    (void)flags;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this library has no CPU path)";
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return nullptr; }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    if (prop.major != 10) {
+        g_create_error = "kernels are built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        return nullptr;
+    }
+    xm_ctx *c = new xm_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->be.st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_st[0], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_st[1], cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "cudaStreamCreate failed";
+        delete c;
+        return nullptr;
+    }
+    for (int k = 0; k < 3; ++k) cudaEventCreate(&c->be.ev[k]);
+    return c;
+}
+
+void xm_destroy(xm_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->be.st);
+    scratch_release(c->be, c->scratch);
+    for (auto &b : c->d_in) if (b.p) cudaFree(b.p);
+    for (auto &b : c->d_out) if (b.p) cudaFree(b.p);
+    for (auto &b : c->h_out) if (b.p) cudaFreeHost(b.p);
+    for (auto &b : c->h_stage) if (b.p) cudaFreeHost(b.p);
+    for (int k = 0; k < 3; ++k) if (c->be.ev[k]) cudaEventDestroy(c->be.ev[k]);
+    if (c->be.st) cudaStreamDestroy(c->be.st);
+    for (auto s : c->copy_st) if (s) cudaStreamDestroy(s);
+    delete c;
+}
+
+int xm_set_debug(xm_ctx *c, uint32_t flags)
+{
+    if (!c) return XM_ERR_ARG;
+    c->debug = flags;
+    return XM_OK;
+}
+
+/* ---- memory helpers ------------------------------------------------------ */
+int xm_dev_alloc(xm_ctx *c, uint64_t bytes, void **d_ptr)
+{
+    if (!c || !d_ptr) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaMalloc(d_ptr, bytes + 16);       /* readable up to the next multiple of 16 */
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(c, XM_ERR_NOMEM, "cudaMalloc: out of memory"); }
+    XM_CUDA(c, e, "cudaMalloc");
+    return XM_OK;
+}
+int xm_dev_free(xm_ctx *c, void *d_ptr)
+{
+    if (!c) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    XM_CUDA(c, cudaFree(d_ptr), "cudaFree");
+    return XM_OK;
+}
+int xm_host_alloc_pinned(xm_ctx *c, uint64_t bytes, void **h_ptr)
+{
+    if (!c || !h_ptr) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaHostAlloc(h_ptr, bytes + 16, cudaHostAllocDefault);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(c, XM_ERR_NOMEM, "cudaHostAlloc: out of memory"); }
+    XM_CUDA(c, e, "cudaHostAlloc");
+    return XM_OK;
+}
+int xm_host_free_pinned(xm_ctx *c, void *h_ptr)
+{
+    if (!c) return XM_ERR_ARG;
+    XM_CUDA(c, cudaFreeHost(h_ptr), "cudaFreeHost");
+    return XM_OK;
+}
+int xm_memcpy_h2d(xm_ctx *c, void *d, const void *h, uint64_t n)
+{
+    if (!c) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    XM_CUDA(c, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->be.st), "H2D copy");
+    XM_CUDA(c, cudaStreamSynchronize(c->be.st), "H2D copy");
+    return XM_OK;
+}
+int xm_memcpy_d2h(xm_ctx *c, void *h, const void *d, uint64_t n)
+{
+    if (!c) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    XM_CUDA(c, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->be.st), "D2H copy");
+    XM_CUDA(c, cudaStreamSynchronize(c->be.st), "D2H copy");
+    return XM_OK;
+}
+int xm_memcpy_d2d(xm_ctx *c, void *dst, const void *src, uint64_t n)
+{
+    if (!c) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    XM_CUDA(c, cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, c->be.st), "D2D copy");
+    XM_CUDA(c, cudaStreamSynchronize(c->be.st), "D2D copy");
+    return XM_OK;
+}
+int xm_dev_mem_info(xm_ctx *c, uint64_t *free_b, uint64_t *total_b)
+{
+    if (!c) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    size_t f = 0, t = 0;
+    XM_CUDA(c, cudaMemGetInfo(&f, &t), "cudaMemGetInfo");
+    if (free_b) *free_b = f;
+    if (total_b) *total_b = t;
+    return XM_OK;
+}
+
+/* ---- device-resident walk ---------------------------------------------------- */
+int xm_classify_device(xm_ctx *c, const void *d_prim, uint64_t prim_len, const void *d_sec, uint64_t sec_len,
+                       const xm_opts *opts, void *const d_out[6], const uint64_t out_cap[6], xm_result *res)
+{
+    if (!c || !opts || !res) return XM_ERR_ARG;
+    if (((uintptr_t)d_prim | (uintptr_t)d_sec) & 15) return fail(c, XM_ERR_ARG, "device inputs must be 16-byte aligned");
+    cudaSetDevice(c->device);
+    uint8_t *o6[6];
+    uint64_t cap6[6];
+    for (int b = 0; b < 6; ++b) { o6[b] = d_out ? (uint8_t *)d_out[b] : nullptr; cap6[b] = (out_cap && o6[b]) ? out_cap[b] : 0; }
+    std::string msg;
+    const int rc = walk_resident(c->be, c->scratch, StreamBuf{(const uint8_t *)d_prim, prim_len}, StreamBuf{(const uint8_t *)d_sec, sec_len},
+                                 *opts, o6, cap6, c->debug, res, msg);
+    c->err = msg;
+    return rc;
+}
+
+/* ---- host-buffer walk ----------------------------------------------------------- */
+static int reserve_dev(xm_ctx *c, DevBuf &b, uint64_t n)
+{
+    if (n <= b.cap && b.p) return XM_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    cudaError_t e = cudaMalloc((void **)&b.p, n + 64);
+    if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return fail(c, XM_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    b.cap = n;
+    return XM_OK;
+}
+static int reserve_host(xm_ctx *c, HostBuf &b, uint64_t n)
+{
+    if (n <= b.cap && b.p) return XM_OK;
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr; b.cap = 0;
+    cudaError_t e = cudaHostAlloc((void **)&b.p, n + 64, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return fail(c, XM_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+    b.cap = n;
+    return XM_OK;
+}
+
+/* upper bounds of what each bin can receive from these inputs (xm.py:332-350, 423-448):
+ * primary lines go to PS/PM/UA/UR, secondary lines to SS/SM/UR; an unterminated last
+ * line gains a newline; overlapping pair units can emit a line twice. */
+static void bin_bounds(uint64_t plen, uint64_t slen, int mode, uint32_t enabled, uint64_t cap[6])
+{
+    const uint64_t mul = mode == XM_MODE_SE ? 1 : 2;
+    const uint64_t pb = (plen + 1) * mul, sb = (slen + 1) * mul;
+    const uint64_t b[6] = {pb, sb, pb, sb, pb, pb + sb};
+    for (int k = 0; k < 6; ++k) cap[k] = ((enabled >> k) & 1u) ? b[k] : 0;
+}
+
+int xm_classify_host(xm_ctx *c, const void *prim, uint64_t prim_len, const void *sec, uint64_t sec_len,
+                     const xm_opts *opts, xm_result *res)
+{
+    if (!c || !opts || !res) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    for (auto &h : c->h_out) h.len = 0;
+    int rc;
+    if ((rc = reserve_dev(c, c->d_in[0], prim_len)) || (rc = reserve_dev(c, c->d_in[1], sec_len))) return rc;
+    uint64_t cap[6];
+    bin_bounds(prim_len, sec_len, opts->mode, opts->enabled_bins, cap);
+    for (int b = 0; b < 6; ++b) if ((rc = reserve_dev(c, c->d_out[b], cap[b]))) return rc;
+
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, c->be.st);
+    /* the two record regions travel on two copy streams; the scan starts as soon as the secondary one has landed */
+    cudaEvent_t in_done[2];
+    const void *src[2] = {prim, sec};
+    const uint64_t len[2] = {prim_len, sec_len};
+    for (int k = 0; k < 2; ++k) {
+        cudaEventCreateWithFlags(&in_done[k], cudaEventDisableTiming);
+        cudaStreamWaitEvent(c->copy_st[k], e0, 0);
+        if (len[k]) {
+            cudaError_t e = cudaMemcpyAsync(c->d_in[k].p, src[k], len[k], cudaMemcpyHostToDevice, c->copy_st[k]);
+            if (e != cudaSuccess) return cuda_fail(c, e, "H2D copy");
+        }
+        cudaEventRecord(in_done[k], c->copy_st[k]);
+        cudaStreamWaitEvent(c->be.st, in_done[k], 0);
+    }
+    uint8_t *o6[6];
+    for (int b = 0; b < 6; ++b) o6[b] = c->d_out[b].p;
+    std::string msg;
+    rc = walk_resident(c->be, c->scratch, StreamBuf{c->d_in[0].p, prim_len}, StreamBuf{c->d_in[1].p, sec_len}, *opts, o6, cap, c->debug, res, msg);
+    c->err = msg;
+    for (int k = 0; k < 2; ++k) cudaEventDestroy(in_done[k]);
+    if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM || rc == XM_ERR_ARG) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    /* bring the bins back (also after a failing record: everything before it was written) */
+    for (int b = 0; b < 6; ++b) {
+        const uint64_t n = res->out_len[b];
+        int r2 = reserve_host(c, c->h_out[b], n);
+        if (r2) return r2;
+        if (n) {
+            cudaError_t e = cudaMemcpyAsync(c->h_out[b].p, c->d_out[b].p, n, cudaMemcpyDeviceToHost, c->copy_st[b & 1]);
+            if (e != cudaSuccess) return cuda_fail(c, e, "D2H copy");
+        }
+        c->h_out[b].len = n;
+    }
+    for (int k = 0; k < 2; ++k) XM_CUDA(c, cudaStreamSynchronize(c->copy_st[k]), "D2H copy");
+    cudaEventRecord(e1, c->be.st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    res->ms_total = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+int xm_get_output(xm_ctx *c, int bin, const void **data, uint64_t *len)
+{
+    if (!c || bin < 0 || bin > 5 || !data || !len) return XM_ERR_ARG;
+    *data = c->h_out[bin].p;
+    *len = c->h_out[bin].len;
+    return XM_OK;
+}
+
+/* ---- file-descriptor walk ---------------------------------------------------------- */
+static int read_all(int fd, int64_t off, std::vector<uint8_t> &out, HostBuf &pinned, xm_ctx *c, uint64_t &n_out)
+{
+    const off_t end = lseek(fd, 0, SEEK_END);
+    if (end < 0) return fail(c, XM_ERR_IO, std::string("input must be seekable: ") + strerror(errno));
+    const uint64_t n = (uint64_t)end > (uint64_t)off ? (uint64_t)end - (uint64_t)off : 0;
+    int rc = reserve_host(c, pinned, n);
+    if (rc) return rc;
+    uint64_t got = 0;
+    while (got < n) {
+        ssize_t r = pread(fd, pinned.p + got, (size_t)std::min<uint64_t>(n - got, 1u << 30), (off_t)(off + (int64_t)got));
+        if (r < 0) { if (errno == EINTR) continue; return fail(c, XM_ERR_IO, std::string("pread: ") + strerror(errno)); }
+        if (r == 0) break;
+        got += (uint64_t)r;
+    }
+    (void)out;
+    n_out = got;
+    return XM_OK;
+}
+
+int xm_classify_fds(xm_ctx *c, int fd_prim, int64_t off_prim, int fd_sec, int64_t off_sec, const int out_fds[6],
+                    const xm_opts *opts, xm_result *res)
+{
+    if (!c || !opts || !res || !out_fds) return XM_ERR_ARG;
+    std::vector<uint8_t> unused;
+    uint64_t np = 0, ns = 0;
+    int rc;
+    if ((rc = read_all(fd_prim, off_prim, unused, c->h_stage[0], c, np)) || (rc = read_all(fd_sec, off_sec, unused, c->h_stage[1], c, ns))) return rc;
+    xm_opts o = *opts;
+    uint32_t en = 0;
+    for (int b = 0; b < 6; ++b) if (out_fds[b] >= 0) en |= 1u << b;
+    o.enabled_bins = en;
+    rc = xm_classify_host(c, c->h_stage[0].p, np, c->h_stage[1].p, ns, &o, res);
+    if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM || rc == XM_ERR_ARG) return rc;
+    for (int b = 0; b < 6; ++b) {
+        if (out_fds[b] < 0) continue;
+        uint64_t done = 0;
+        while (done < c->h_out[b].len) {
+            ssize_t w = write(out_fds[b], c->h_out[b].p + done, (size_t)std::min<uint64_t>(c->h_out[b].len - done, 1u << 30));
+            if (w < 0) { if (errno == EINTR) continue; return fail(c, XM_ERR_IO, std::string("write: ") + strerror(errno)); }
+            done += (uint64_t)w;
+        }
+    }
+    return rc;
+}
+
+/* ---- counting pass of the sharded walk ------------------------------------------------ */
+int xm_count_device(xm_ctx *c, const void *d_buf, uint64_t len, int skip_repeated, xm_shard_info *info)
+{
+    if (!c || !info) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    memset(info, 0, sizeof *info);
+    info->stop_at = ~0ull;
+    info->first_start = 0;
+    if (!len) return XM_OK;
+    const bool small = (c->debug & DBG_SMALL_TILES) != 0;
+    const uint64_t tile = tile_bytes(small);
+    const uint64_t nt = (len + tile - 1) / tile;
+    if (!scratch_reserve(c->be, c->scratch, nt, 0, 0)) return fail(c, XM_ERR_NOMEM, "out of device memory for scratch");
+    Globals init;
+    memset(&init, 0, sizeof init);
+    init.err = NO_ERROR;
+    if (c->be.write(c->scratch.g, &init, sizeof init) || c->be.zero(c->scratch.chain1_s, nt * 8)) return fail(c, XM_ERR_CUDA, c->be.err);
+    ScanArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.S = StreamBuf{(const uint8_t *)d_buf, len};
+    sa.sc = c->scratch.sc; sa.sc_cap = 0;
+    sa.chain1 = c->scratch.chain1_s; sa.g = c->scratch.g; sa.ntiles = (uint32_t)nt;
+    sa.skip = skip_repeated ? 1 : 0; sa.stream_id = 1; sa.debug = c->debug;
+    if (c->be.scan(sa, small) || c->be.sync()) return fail(c, XM_ERR_CUDA, "count kernel failed: " + c->be.err);
+    Globals G;
+    if (c->be.read(&G, c->scratch.g, sizeof G)) return fail(c, XM_ERR_CUDA, c->be.err);
+    if (G.overflow) return fail(c, XM_ERR_UNSUPPORTED, "lines shorter than 64 bytes on average: count with XM_DEBUG_SMALL_TILES");
+    info->n_records = G.n_stream[1];
+    if (G.end_off[1] < len) info->stop_at = G.n_stream[1];
+    return XM_OK;
+}
+
+}  // extern "C"

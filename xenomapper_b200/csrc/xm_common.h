@@ -1,0 +1,138 @@
+/*
+ * xm_common.h -- types shared by the CUDA kernels, the C-ABI runtime and the
+ * CPU emulation harness used by the tests (tests/emu).
+ */
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define XM_HD __host__ __device__ __forceinline__
+#else
+#define XM_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define XM_DEVICE_PASS 1
+#else
+#define XM_DEVICE_PASS 0
+#endif
+
+#if !defined(__CUDACC__)
+/* host-only builds (CPU emulation harness): the CUDA vector type the tile code uses */
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+#endif
+
+namespace xm {
+
+/* states / bins: reference output argument order, xm.py:291-297 */
+enum { PS = 0, SS = 1, PM = 2, SM = 3, UA = 4, UR = 5, NO_BIN = 7 };
+enum { MODE_SE = 0, MODE_PE_LIBERAL = 1, MODE_PE_CONSERVATIVE = 2 };
+enum { SCORE_AS_XS = 0, SCORE_AS_ZS = 1, SCORE_CIGAR_NM = 2 };
+
+/* -inf of the reference (missing tag, xm.py:188) */
+constexpr int32_t SCORE_ABSENT = INT32_MIN;
+
+/* per-line flags.  The low six travel in SCompact::meta. */
+enum : uint32_t {
+    F_DIRTY = 1,    /* output differs from the raw bytes: whitespace other than single tabs, CR, missing final newline */
+    F_AS_DUP = 2,   /* two tokens match the AS lookup: ValueError xm.py:190 */
+    F_AS_NUM = 4,   /* AS value is not a plain 31-bit decimal integer: host diagnoses ValueError vs unsupported */
+    F_XS_DUP = 8,
+    F_XS_NUM = 16,
+    F_TEXT = 32,    /* non-ASCII byte, lone CR, or a line too long for the meta word */
+    F_BLANK = 64,   /* no tokens: stops the walk, xm.py:105 */
+    F_FAR = 128     /* line not fully inside the staged window */
+};
+constexpr uint32_t META_LEN_BITS = 24;
+constexpr uint32_t META_LEN_MASK = (1u << META_LEN_BITS) - 1;
+
+/* error word: (record index << 8) | (code << 2) | (previous-record << 1) | stream; atomicMin keeps the first */
+enum { EC_ASSERT = 1, EC_TEXT = 2, EC_DUP = 3, EC_NUM_AS = 4, EC_NUM_XS = 5 };
+constexpr unsigned long long NO_ERROR = ~0ull;
+
+struct StreamBuf {
+    const uint8_t *p;
+    uint64_t len;
+};
+
+/* what the secondary-stream scan leaves behind, one entry per yielded record */
+struct SCompact {
+    uint64_t *start;     /* [n+1] byte offset of the record; [n] = offset just past the last one */
+    int32_t *as;         /* [n] */
+    int32_t *xs;         /* [n] */
+    uint32_t *h1, *h2;   /* [n] 64-bit QNAME hash */
+    uint32_t *meta;      /* [n] emitted length (24 bits) | flags << 24 */
+};
+
+struct Globals {
+    unsigned long long counts[36];
+    unsigned long long n_stream[2];   /* records before EOF / first blank line: [0] primary, [1] secondary */
+    unsigned long long err;           /* first error word, NO_ERROR if none */
+    unsigned long long out_len[6];
+    unsigned long long bytes_in[2];
+    unsigned long long end_off[2];    /* byte offset just past the last counted record of each stream */
+    unsigned long long limit_off;     /* byte offset of primary record `limit` (error re-run: locates the failing line) */
+    unsigned int overflow;            /* a tile held more lines than the geometry allows: relaunch smaller */
+    unsigned int ticket[2];
+    unsigned int pad;
+};
+
+/* decoupled look-back descriptors */
+constexpr unsigned long long C1_AGG = 1ull << 62, C1_INC = 2ull << 62, C1_STOP = 1ull << 61;
+constexpr unsigned long long C1_COUNT = (1ull << 61) - 1;
+constexpr int C2_SLOTS = 8;           /* six bins + raw primary bytes + spare */
+
+struct ScanArgs {
+    StreamBuf S;
+    SCompact sc;
+    uint64_t sc_cap;
+    unsigned long long *chain1;       /* [ntiles] */
+    Globals *g;
+    uint32_t ntiles;
+    int32_t score_src, skip;
+    int32_t stream_id;                /* which n_stream / ticket slot this scan owns */
+    uint32_t debug;
+};
+
+struct ClassifyArgs {
+    StreamBuf P, S;
+    SCompact sc;
+    unsigned long long *chain1;       /* [ntiles] */
+    uint32_t *c2_flag;                /* [ntiles] 0 none, 1 aggregate, 2 inclusive */
+    unsigned long long *c2_agg;       /* [ntiles][C2_SLOTS] */
+    unsigned long long *c2_inc;       /* [ntiles][C2_SLOTS] */
+    Globals *g;
+    uint32_t ntiles;
+    int32_t mode, score_src, skip;
+    long long thr;                    /* AS > min_score  <=>  AS >= thr */
+    uint32_t enabled;
+    uint64_t limit;                   /* records >= limit are dropped (error re-run) */
+    uint8_t *out[6];
+    uint64_t out_cap[6];
+    uint32_t debug;
+};
+
+constexpr uint32_t DBG_FORCE_GENERIC = 1, DBG_SMALL_TILES = 2;
+
+/* tile geometry */
+template <int TILE_, int HALO_, int THREADS_, int R_>
+struct Cfg {
+    static constexpr int TILE = TILE_;        /* bytes of the stream one CTA owns (lines are owned by their first byte) */
+    static constexpr int HALO = HALO_;        /* bytes staged before and after the tile */
+    static constexpr int THREADS = THREADS_;
+    static constexpr int R = R_;              /* lines per thread */
+    static constexpr int WIN = TILE + 2 * HALO;
+    static constexpr int NSLOT = WIN / 16 + 2;          /* 16-byte mask slots, covers WIN + 32 bits */
+    static constexpr int NW = NSLOT / 2;                /* 32-bit mask words */
+    static constexpr int NG = TILE / 128;               /* 4-word groups of the start mask */
+    static constexpr int LCAP = THREADS * R;
+    static constexpr int ITEMS = 2 * LCAP;
+    static_assert(TILE % 128 == 0 && HALO % 32 == 0, "geometry");
+    static_assert(NG <= THREADS, "one thread per start-mask group");
+};
+using CfgBig = Cfg<32768, 2048, 256, 2>;
+using CfgSmall = Cfg<1024, 1024, 256, 2>;     /* LCAP == TILE/2: can never overflow (non-blank lines need 2 bytes) */
+
+}  // namespace xm

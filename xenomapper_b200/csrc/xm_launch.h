@@ -1,0 +1,11 @@
+/* xm_launch.h -- host-callable launchers of the kernels in xm_kernels.cu */
+#pragma once
+#include <cuda_runtime.h>
+#include "xm_common.h"
+
+namespace xm {
+uint32_t tile_bytes(bool small);
+cudaError_t launch_scan(const ScanArgs &a, bool small, cudaStream_t st);
+cudaError_t launch_classify(const ClassifyArgs &a, bool small, cudaStream_t st);
+cudaError_t launch_fill_u64(unsigned long long *p, unsigned long long v, size_t n, cudaStream_t st);
+}  // namespace xm

@@ -1,0 +1,496 @@
+/*
+ * xm_parse.h -- per-line logic of the read-binning path: byte classes, the
+ * exact tokeniser, tag/score extraction, the category decision.
+ *
+ * Compiled twice from one source: as device code inside the sm_100a kernels
+ * (xm_kernels.cu) and as host code inside the CPU emulation harness the tests
+ * use to exercise the tile logic without a GPU (tests/emu/xm_emu.cpp).  The
+ * host build is test scaffolding only; libxenomapper_b200.so never runs it.
+ *
+ * Reference semantics restated here (xenomapper/xenomapper.py, "xm.py"):
+ *   tokenise       line.strip('\n').split()                      xm.py:103
+ *   get_tag        substring match on tokens >= 11, value after
+ *                  the last ':'                                  xm.py:186-191
+ *   ZS alias       xm.py:204-205
+ *   CIGAR score    xm.py:247-255
+ *   decision       get_mapping_state                             xm.py:275-289
+ *   pair chains    xm.py:423-448 (liberal), 521-550 (conservative)
+ */
+#pragma once
+#include "xm_common.h"
+
+namespace xm {
+
+/* ---- portable bit helpers ------------------------------------------- */
+XM_HD int ffs32(uint32_t x)
+{
+#if XM_DEVICE_PASS
+    return __ffs((int)x);
+#else
+    return x ? __builtin_ctz(x) + 1 : 0;
+#endif
+}
+XM_HD int clz32(uint32_t x)
+{
+#if XM_DEVICE_PASS
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+XM_HD int popc32(uint32_t x)
+{
+#if XM_DEVICE_PASS
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+XM_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#if XM_DEVICE_PASS
+    return __funnelshift_r(lo, hi, sh);
+#else
+    sh &= 31;
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+XM_HD uint32_t umulhi32(uint32_t a, uint32_t b)
+{
+#if XM_DEVICE_PASS
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+XM_HD uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+/* ---- SIMD-in-register byte classes (four bytes per 32-bit word) ------- */
+/* bit 7 of each byte set where the byte is < 0x21 or >= 0x80: every ASCII
+ * whitespace, every control byte, every non-ASCII byte.  Clean SAM has only
+ * '\t' and '\n' in this class. */
+XM_HD uint32_t ctrl_mask(uint32_t w)
+{
+    uint32_t t = (w & 0x7f7f7f7fu) + 0x5f5f5f5fu;
+    return (~t | w) & 0x80808080u;
+}
+/* bit 7 of each byte set where the byte equals the (ASCII) byte replicated in pat; exact */
+XM_HD uint32_t eq_mask(uint32_t w, uint32_t pat)
+{
+    uint32_t x = w ^ pat;
+    uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(t | x) & 0x80808080u;
+}
+/* gather the four bit-7 flags of a word into a nibble (byte 0 -> bit 0) */
+XM_HD uint32_t pack4(uint32_t z) { return umulhi32(z, 0x02040810u) & 0xfu; }
+
+XM_HD bool is_ascii_space(uint8_t c) { return c == ' ' || (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x1f); }
+
+/* ---- QNAME hash: 2 x 32-bit lanes over little-endian words ------------ */
+struct Hash2 {
+    uint32_t a, b;
+};
+XM_HD void hash_init(Hash2 &h) { h.a = 0x243f6a88u; h.b = 0x85a308d3u; }
+XM_HD void hash_word(Hash2 &h, uint32_t w)
+{
+    uint32_t k = w * 0xcc9e2d51u;
+    k = rotl32(k, 15) * 0x1b873593u;
+    h.a = rotl32(h.a ^ k, 13) * 5u + 0xe6546b64u;
+    uint32_t j = w * 0x85ebca6bu;
+    j = rotl32(j, 13) * 0xc2b2ae35u;
+    h.b = rotl32(h.b ^ j, 17) * 9u + 0x52dce729u;
+}
+XM_HD uint32_t fmix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+XM_HD void hash_final(Hash2 &h, uint32_t len)
+{
+    h.a = fmix32(h.a ^ len);
+    h.b = fmix32(h.b ^ (len * 0x9e3779b1u));
+}
+
+/* ---- decimal integers: the device grammar [+-]?[0-9]+, |v| < 2^31 ------ */
+struct NumSt {
+    uint32_t v;
+    uint32_t st;    /* 0 start, 1 after sign, 2 in digits; bit 8 bad; bit 9 negative */
+};
+XM_HD void num_reset(NumSt &n) { n.v = 0; n.st = 0; }
+XM_HD void num_feed(NumSt &n, uint32_t c)
+{
+    uint32_t d = c - '0';
+    if (d <= 9u) {
+        if (n.v > 214748364u || (n.v == 214748364u && d > 7u)) n.st |= 0x100;
+        else n.v = n.v * 10u + d;
+        n.st = (n.st & ~3u) | 2u;
+    } else if ((n.st & 3u) == 0 && (c == '+' || c == '-')) {
+        n.st |= 1u | (c == '-' ? 0x200u : 0u);
+    } else {
+        n.st |= 0x100;
+    }
+}
+XM_HD bool num_ok(const NumSt &n, int32_t &out)
+{
+    if ((n.st & 0x100) || (n.st & 3u) != 2u) return false;
+    out = (n.st & 0x200) ? -(int32_t)n.v : (int32_t)n.v;
+    return true;
+}
+
+/* ---- CIGAR walk, xm.py:251-255 ----------------------------------------- */
+struct CigSt {
+    uint32_t run, nd_big;      /* nd_big: bit 0 digits pending, bit 1 run too large, bit 2 unsupported seen */
+    uint32_t n_id;
+    unsigned long long sum_id, sum_s;
+};
+XM_HD void cig_reset(CigSt &c) { c.run = 0; c.nd_big = 0; c.n_id = 0; c.sum_id = 0; c.sum_s = 0; }
+XM_HD void cig_feed(CigSt &c, uint32_t ch)
+{
+    uint32_t d = ch - '0';
+    if (d <= 9u) {
+        if (c.run > 99999999u) c.nd_big |= 2;
+        else c.run = c.run * 10u + d;
+        c.nd_big |= 1;
+    } else {
+        if (c.nd_big & 1) {
+            if (ch == 'I' || ch == 'D') { if (c.nd_big & 2) c.nd_big |= 4; c.n_id++; c.sum_id += c.run; }
+            else if (ch == 'S') { if (c.nd_big & 2) c.nd_big |= 4; c.sum_s += c.run; }
+        }
+        c.run = 0;
+        c.nd_big &= 4;
+    }
+}
+XM_HD bool cig_score(const CigSt &c, int32_t mm, int32_t &out)
+{
+    if (c.nd_big & 4) return false;
+    long long v = -6ll * mm - 5ll * (long long)c.n_id - 3ll * (long long)c.sum_id - 2ll * (long long)c.sum_s;
+    if (v > 2147483647ll || v < -2147483647ll) return false;
+    out = (int32_t)v;
+    return true;
+}
+
+/* ---- one parsed line --------------------------------------------------- */
+struct LineRec {
+    uint32_t s;         /* start, relative to the window origin g0 */
+    uint32_t rawbytes;  /* bytes the line occupies in the input, terminator included */
+    uint32_t outlen;    /* bytes it occupies in an output: tokens joined by tabs + '\n' */
+    uint32_t qs, qlen;  /* QNAME (token 0), start relative to g0 */
+    uint32_t h1, h2;    /* QNAME hash */
+    uint32_t flags;
+    int32_t as, xs;
+};
+
+/* byte source for the exact path: the staged window where it covers the
+ * address, global memory elsewhere (long lines, secondary-stream lines) */
+struct Reader {
+    const uint8_t *win;
+    const uint8_t *glob;
+    uint64_t g0;
+    uint32_t wbytes;
+    uint64_t len;
+    XM_HD uint8_t at(uint64_t p) const
+    {
+        uint64_t r = p - g0;
+        return r < wbytes ? win[r] : glob[p];
+    }
+};
+
+/*
+ * Exact tokeniser + tag extraction for one line starting at global offset gs.
+ * Handles every input the reference accepts as ASCII text: any whitespace as
+ * separator (runs collapse, leading/trailing dropped), CRLF, a missing final
+ * newline, lines of any length.  One pass, O(1) state.
+ */
+XM_HD void generic_parse(const Reader &rd, uint64_t gs, int score_src, LineRec &L)
+{
+    const bool cigar = score_src == SCORE_CIGAR_NM;
+    const uint32_t xsch = score_src == SCORE_AS_ZS ? 'Z' : 'X';
+    uint32_t flags = 0, ntok = 0, toklen = 0, prevc = 0, tokm = 0;   /* tokm: bit0 AS, bit1 XS, bit2 NM seen in this token */
+    uint32_t as_cnt = 0, xs_cnt = 0, nm_cnt = 0, as_ok = 0, xs_ok = 0, nm_ok = 0;
+    int32_t as_v = 0, xs_v = 0, nm_v = 0;
+    bool in_tok = false, nontab = false, eof = false;
+    NumSt num; num_reset(num);
+    CigSt cig; cig_reset(cig);
+    Hash2 h; hash_init(h);
+    uint32_t wacc = 0, qlen = 0;
+    uint64_t qs = gs;
+    uint64_t p = gs;
+    for (;; ++p) {
+        uint32_t c = 0;
+        bool end = false, ws;
+        if (p >= rd.len) { end = true; eof = true; }
+        else { c = rd.at(p); end = (c == '\n'); }
+        if (end) ws = true;
+        else if (c == '\r') {
+            ws = true;
+            if (!(p + 1 < rd.len && rd.at(p + 1) == '\n')) flags |= F_TEXT;   /* lone CR is a line break for the reference */
+        } else if (c >= 0x80) { ws = false; flags |= F_TEXT; }
+        else ws = is_ascii_space((uint8_t)c);
+        if (ws) {
+            if (!end && c != '\t') nontab = true;
+            if (in_tok) {
+                in_tok = false;
+                if (ntok == 1) { if (qlen & 3) hash_word(h, wacc); }
+                if (ntok > 11) {
+                    if (!cigar && (tokm & 1)) { if (++as_cnt == 1) as_ok = num_ok(num, as_v); }
+                    if (tokm & 2) { if (++xs_cnt == 1) xs_ok = num_ok(num, xs_v); }
+                    if (cigar && (tokm & 4)) { if (++nm_cnt == 1) nm_ok = num_ok(num, nm_v); }
+                }
+            }
+            if (end) break;
+        } else {
+            if (!in_tok) {
+                in_tok = true; ++ntok; prevc = 0; tokm = 0; num_reset(num);
+                if (ntok == 1) qs = p;
+            }
+            ++toklen;
+            if (ntok == 1) {
+                wacc |= c << (8 * (qlen & 3));
+                if ((++qlen & 3) == 0) { hash_word(h, wacc); wacc = 0; }
+            } else if (ntok == 6) {
+                if (cigar) cig_feed(cig, c);
+            } else if (ntok > 11) {
+                if (c == 'S') { if (prevc == 'A') tokm |= 1; if (prevc == xsch) tokm |= 2; }
+                else if (c == 'M' && prevc == 'N') tokm |= 4;
+                if (c == ':') num_reset(num); else num_feed(num, c);
+            }
+            prevc = c;
+        }
+    }
+    hash_final(h, qlen);
+    uint64_t raw = (p - gs) + (eof ? 0 : 1);
+    uint64_t outlen = ntok ? (uint64_t)toklen + ntok : 0;
+    if (ntok == 0) flags |= F_BLANK;
+    if (nontab || eof || (p - gs) + 1 != outlen) flags |= F_DIRTY;
+    if (outlen > META_LEN_MASK || raw > 0xffffffffull) { flags |= F_TEXT; outlen &= META_LEN_MASK; }
+    int32_t as = SCORE_ABSENT, xs = SCORE_ABSENT;
+    if (cigar) {
+        if (nm_cnt) {
+            if (!nm_ok || !cig_score(cig, nm_v, as)) { flags |= F_AS_NUM; as = SCORE_ABSENT; }
+        }
+    } else if (as_cnt == 1) { if (as_ok) as = as_v; else flags |= F_AS_NUM; }
+    else if (as_cnt > 1) flags |= F_AS_DUP;
+    if (xs_cnt == 1) { if (xs_ok) xs = xs_v; else flags |= F_XS_NUM; }
+    else if (xs_cnt > 1) flags |= F_XS_DUP;
+    L.s = (uint32_t)(gs - rd.g0);
+    L.rawbytes = (uint32_t)raw;
+    L.outlen = (uint32_t)outlen;
+    L.qs = (uint32_t)(qs - rd.g0);
+    L.qlen = qlen;
+    L.h1 = h.a; L.h2 = h.b;
+    L.flags = flags;
+    L.as = as; L.xs = xs;
+}
+
+/* masks of the staged window, one bit per byte */
+struct WinMasks {
+    const uint8_t *win;
+    const uint32_t *wsm;   /* ctrl_mask bits */
+    const uint32_t *nlm;   /* '\n' bits (plus a virtual one at EOF when the last line is unterminated) */
+    int nbits;             /* mask bits that are meaningful */
+    int virt;              /* position of the virtual newline, -1 if none */
+};
+
+/* position after the nearest separator bit strictly below q (q is inside a token past `floor`) */
+XM_HD int token_start(const uint32_t *wsm, int q)
+{
+    int w = q >> 5;
+    uint32_t m = wsm[w] & ((1u << (q & 31)) - 1u);
+    while (!m) m = wsm[--w];
+    return (w << 5) + 32 - clz32(m);
+}
+/* first separator bit at or above q (the line's newline bounds the search) */
+XM_HD int token_end(const uint32_t *wsm, int q)
+{
+    int w = q >> 5;
+    uint32_t m = wsm[w] & (0xffffffffu << (q & 31));
+    while (!m) m = wsm[++w];
+    return (w << 5) + ffs32(m) - 1;
+}
+/* plain integer after the last ':' of the token [ts, te) */
+XM_HD bool token_value(const uint8_t *win, int ts, int te, int32_t &out)
+{
+    int vs = te;
+    while (vs > ts && win[vs - 1] != ':') --vs;
+    NumSt n; num_reset(n);
+    for (int p = vs; p < te; ++p) num_feed(n, win[p]);
+    return num_ok(n, out);
+}
+
+/*
+ * Fast path for a clean line that lies inside the staged window: separators
+ * come from the bitmasks, the aux region is scanned a word at a time.
+ * Returns false (and leaves L untouched) whenever the line needs the exact
+ * path: any control byte other than single tabs, CR, non-ASCII, unterminated
+ * or extending past the window.
+ */
+XM_HD bool fast_parse(const WinMasks &M, int s, int score_src, LineRec &L)
+{
+    const uint8_t *win = M.win;
+    const uint32_t *w32 = (const uint32_t *)win;
+    /* line end */
+    int wi = s >> 5;
+    const int nwords = (M.nbits + 31) >> 5;
+    uint32_t m = M.nlm[wi] & (0xffffffffu << (s & 31));
+    while (!m) {
+        if (++wi >= nwords) return false;
+        m = M.nlm[wi];
+    }
+    const int e = (wi << 5) + ffs32(m) - 1;
+    if (e >= M.nbits || e == M.virt) return false;
+    if (e == s) {   /* empty line */
+        L.s = (uint32_t)s; L.rawbytes = 1; L.outlen = 0; L.qs = (uint32_t)s; L.qlen = 0;
+        L.h1 = L.h2 = 0; L.flags = F_BLANK; L.as = L.xs = SCORE_ABSENT;
+        return true;
+    }
+    /* separators: all single tabs, none leading or trailing */
+    int nsep = 0, prev = s - 1, sep0 = e, sep4 = -1, sep5 = -1, sep10 = -1;
+    uint32_t bad = 0;
+    const int w0 = s >> 5, w1 = (e - 1) >> 5;
+    for (int w = w0; w <= w1; ++w) {
+        uint32_t mm = M.wsm[w];
+        if (w == w0) mm &= 0xffffffffu << (s & 31);
+        if (w == w1) mm &= 0xffffffffu >> (31 - ((e - 1) & 31));
+        while (mm) {
+            int p = (w << 5) + ffs32(mm) - 1;
+            mm &= mm - 1;
+            bad |= (uint32_t)(win[p] != '\t') | (uint32_t)(p == prev + 1);
+            prev = p;
+            if (nsep == 0) sep0 = p;
+            else if (nsep == 4) sep4 = p;
+            else if (nsep == 5) sep5 = p;
+            else if (nsep == 10) sep10 = p;
+            ++nsep;
+        }
+    }
+    bad |= (uint32_t)(prev == e - 1);
+    if (bad) return false;
+    /* QNAME hash over [s, sep0) */
+    const int qlen = sep0 - s;
+    Hash2 h; hash_init(h);
+    {
+        const int base = s >> 2;
+        const uint32_t sh = (uint32_t)(s & 3) * 8u;
+        const int nw = (qlen + 3) >> 2;
+        uint32_t lo = w32[base];
+        for (int k = 0; k < nw; ++k) {
+            uint32_t hi = w32[base + k + 1];
+            uint32_t w = funnel_r(lo, hi, sh);
+            lo = hi;
+            if (k == nw - 1 && (qlen & 3)) w &= (1u << (8 * (qlen & 3))) - 1u;
+            hash_word(h, w);
+        }
+    }
+    hash_final(h, (uint32_t)qlen);
+    /* aux tokens (index >= 11): look for the tag letters a word at a time */
+    uint32_t flags = 0;
+    int32_t as = SCORE_ABSENT, xs = SCORE_ABSENT;
+    if (nsep >= 11) {
+        const bool cigar = score_src == SCORE_CIGAR_NM;
+        const uint32_t xsch = score_src == SCORE_AS_ZS ? 'Z' : 'X';
+        const int a = sep10 + 1;
+        int as_ts = -1, xs_ts = -1, nm_ts = -1;
+        uint32_t as_cnt = 0, xs_cnt = 0;
+        const int k0 = a >> 2, k1 = (e - 1) >> 2;
+        for (int k = k0; k <= k1; ++k) {
+            uint32_t w = w32[k];
+            uint32_t z = eq_mask(w, 0x53535353u);                 /* 'S' */
+            if (cigar) z |= eq_mask(w, 0x4d4d4d4du);              /* 'M' */
+            if (k == k0) z &= 0xffffffffu << (8 * (a & 3));
+            if (k == k1) z &= 0xffffffffu >> (8 * (3 - ((e - 1) & 3)));
+            while (z) {
+                int p = (k << 2) + ((ffs32(z) - 1) >> 3);
+                z &= z - 1;
+                if (p <= a) continue;
+                uint32_t c1 = win[p], c0 = win[p - 1];
+                if (c1 == 'S') {
+                    if (c0 == 'A' && !cigar) {
+                        int ts = token_start(M.wsm, p - 1);
+                        if (as_cnt == 0) { as_ts = ts; as_cnt = 1; } else if (ts != as_ts) as_cnt = 2;
+                    }
+                    if (c0 == xsch) {
+                        int ts = token_start(M.wsm, p - 1);
+                        if (xs_cnt == 0) { xs_ts = ts; xs_cnt = 1; } else if (ts != xs_ts) xs_cnt = 2;
+                    }
+                } else if (c0 == 'N' && nm_ts < 0) {
+                    nm_ts = token_start(M.wsm, p - 1);
+                }
+            }
+        }
+        if (cigar) {
+            if (nm_ts >= 0) {
+                int32_t mm;
+                bool ok = token_value(win, nm_ts, token_end(M.wsm, nm_ts), mm);
+                CigSt cg; cig_reset(cg);
+                for (int p = sep4 + 1; p < sep5; ++p) cig_feed(cg, win[p]);
+                if (!ok || !cig_score(cg, mm, as)) { flags |= F_AS_NUM; as = SCORE_ABSENT; }
+            }
+        } else if (as_cnt == 1) {
+            if (!token_value(win, as_ts, token_end(M.wsm, as_ts), as)) { flags |= F_AS_NUM; as = SCORE_ABSENT; }
+        } else if (as_cnt > 1) flags |= F_AS_DUP;
+        if (xs_cnt == 1) {
+            if (!token_value(win, xs_ts, token_end(M.wsm, xs_ts), xs)) { flags |= F_XS_NUM; xs = SCORE_ABSENT; }
+        } else if (xs_cnt > 1) flags |= F_XS_DUP;
+    }
+    const uint32_t outlen = (uint32_t)(e - s) + 1u;
+    if (outlen > META_LEN_MASK) return false;
+    L.s = (uint32_t)s; L.rawbytes = outlen; L.outlen = outlen;
+    L.qs = (uint32_t)s; L.qlen = (uint32_t)qlen;
+    L.h1 = h.a; L.h2 = h.b; L.flags = flags; L.as = as; L.xs = xs;
+    return true;
+}
+
+/* exact QNAME comparison of two tokens given by global offsets */
+XM_HD bool names_equal(const Reader &rd, uint64_t a, uint32_t alen, uint64_t b, uint32_t blen)
+{
+    if (alen != blen) return false;
+    const uint64_t ra = a - rd.g0, rb = b - rd.g0;
+    if (ra + alen + 4 <= rd.wbytes && rb + blen + 4 <= rd.wbytes) {
+        /* both inside the window: compare word-wise through aligned loads */
+        const uint32_t *w32 = (const uint32_t *)rd.win;
+        const int ba = (int)(ra >> 2), bb = (int)(rb >> 2);
+        const uint32_t sa = (uint32_t)(ra & 3) * 8u, sb = (uint32_t)(rb & 3) * 8u;
+        const int nw = (int)((alen + 3) >> 2);
+        for (int k = 0; k < nw; ++k) {
+            uint32_t x = funnel_r(w32[ba + k], w32[ba + k + 1], sa) ^ funnel_r(w32[bb + k], w32[bb + k + 1], sb);
+            if (k == nw - 1 && (alen & 3)) x &= (1u << (8 * (alen & 3))) - 1u;
+            if (x) return false;
+        }
+        return true;
+    }
+    for (uint32_t k = 0; k < alen; ++k)
+        if (rd.at(a + k) != rd.at(b + k)) return false;
+    return true;
+}
+
+/* ---- the category decision, xm.py:275-289, on integer scores ----------- */
+/* SCORE_ABSENT plays -inf; `thr` encodes min_score: AS > min_score <=> AS >= thr. */
+XM_HD int mapping_state(int32_t as1, int32_t xs1, int32_t as2, int32_t xs2, long long thr)
+{
+    const bool g1 = as1 != SCORE_ABSENT && (long long)as1 >= thr;
+    const bool g2 = as2 != SCORE_ABSENT && (long long)as2 >= thr;
+    if (!g1 && !g2) return UA;
+    if (g1 && (!g2 || as1 > as2)) return (xs1 == 0 || as1 > xs1) ? PS : PM;
+    if (as1 == as2) return UR;
+    return (xs2 == 0 || as2 > xs2) ? SS : SM;
+}
+
+/* liberal chain xm.py:423-448: PS > SS > PM > SM > UR > UA */
+XM_HD int pair_bin_liberal(int f, int r)
+{
+    /* priority rank of each state; the pair takes the better ranked of the two */
+    const uint32_t rank = (0u << (4 * PS)) | (1u << (4 * SS)) | (2u << (4 * PM)) | (3u << (4 * SM)) | (4u << (4 * UR)) | (5u << (4 * UA));
+    uint32_t rf = (rank >> (4 * f)) & 15u, rr = (rank >> (4 * r)) & 15u;
+    return rf <= rr ? f : r;
+}
+/* conservative chain xm.py:521-550 */
+XM_HD int pair_bin_conservative(int f, int r)
+{
+    if (f == UA || r == UA) return UA;
+    const bool fp = (f == PS || f == PM), fs = (f == SS || f == SM);
+    const bool rp = (r == PS || r == PM), rs = (r == SS || r == SM);
+    if (f == UR || r == UR || (fp && rs) || (fs && rp)) return UR;
+    return pair_bin_liberal(f, r);
+}
+
+}  // namespace xm

@@ -1,0 +1,359 @@
+/*
+ * xm_walk.h -- host orchestration of one resident walk: scratch sizing, the
+ * two kernel launches, the re-runs (tile-geometry overflow, compact-array
+ * growth, exact-prefix re-run after a failing record) and the mapping of
+ * device error words onto the reference's exception classes.
+ *
+ * Written against a small Backend interface so that the CUDA runtime
+ * (xm_api.cu) and the CPU emulation harness of the tests (tests/emu) run the
+ * same logic.  Backend:
+ *     void *alloc(size_t)            scratch in the backend's memory space
+ *     void  release(void *)
+ *     int   zero(void *, size_t)
+ *     int   fill64(void *, unsigned long long v, size_t n)
+ *     int   read(void *host_dst, const void *src, size_t)     (D2H, synchronous)
+ *     int   write(void *dst, const void *host_src, size_t)    (H2D, synchronous)
+ *     std::string last_error()
+ *     int   scan(const ScanArgs &, bool small)
+ *     int   classify(const ClassifyArgs &, bool small)
+ *     int   sync()
+ *     void  tick(int which) / float elapsed(...)               optional timing
+ */
+#pragma once
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/xenomapper_b200.h"
+#include "xm_common.h"
+
+namespace xm {
+
+/* AS > min_score  <=>  AS >= threshold, for integer AS (xm.py:275-284 compare with > and <=) */
+inline long long score_threshold(double min_score)
+{
+    if (min_score == -INFINITY) return -(1ll << 40);
+    if (min_score == INFINITY) return 1ll << 40;
+    const double f = floor(min_score);
+    if (f >= 2147483647.0) return 1ll << 40;
+    if (f < -2147483648.0) return -(1ll << 40);
+    return (long long)f + 1;
+}
+
+/* ---- host-side diagnosis of a failing record's text ------------------------ */
+inline bool host_is_space(unsigned char c) { return c == ' ' || (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x1f); }
+
+inline bool utf8_valid(const unsigned char *s, size_t n)
+{
+    size_t i = 0;
+    while (i < n) {
+        unsigned char c = s[i];
+        if (c < 0x80) { i++; continue; }
+        int k;
+        uint32_t v, lo;
+        if (c >= 0xc2 && c < 0xe0) { k = 1; v = c & 0x1f; lo = 0x80; }
+        else if (c >= 0xe0 && c < 0xf0) { k = 2; v = c & 0x0f; lo = 0x800; }
+        else if (c >= 0xf0 && c < 0xf5) { k = 3; v = c & 0x07; lo = 0x10000; }
+        else return false;
+        for (int j = 1; j <= k; j++) {
+            if (i + j >= n || (s[i + j] & 0xc0) != 0x80) return false;
+            v = (v << 6) | (s[i + j] & 0x3f);
+        }
+        if (v < lo || v > 0x10ffff || (v >= 0xd800 && v <= 0xdfff)) return false;
+        i += k + 1;
+    }
+    return true;
+}
+
+/* PEP 515: every '_' sits between two digits; returns false when violated */
+inline bool strip_underscores(const std::string &in, std::string &out)
+{
+    out.clear();
+    for (size_t i = 0; i < in.size(); i++) {
+        if (in[i] == '_') {
+            if (i == 0 || i + 1 >= in.size() || !isdigit((unsigned char)in[i - 1]) || !isdigit((unsigned char)in[i + 1])) return false;
+            continue;
+        }
+        out.push_back(in[i]);
+    }
+    return true;
+}
+inline bool ci_equal(const char *s, const char *lit)
+{
+    for (; *lit; s++, lit++) if (tolower((unsigned char)*s) != *lit) return false;
+    return *s == 0;
+}
+/* would Python's float() accept it?  (xm.py:191) */
+inline bool py_float_accepts(const std::string &raw)
+{
+    std::string t;
+    if (!strip_underscores(raw, t)) return false;
+    const char *p = t.c_str();
+    if (*p == '+' || *p == '-') p++;
+    if (ci_equal(p, "inf") || ci_equal(p, "infinity") || ci_equal(p, "nan")) return true;
+    int nd = 0;
+    while (isdigit((unsigned char)*p)) { p++; nd++; }
+    if (*p == '.') { p++; while (isdigit((unsigned char)*p)) { p++; nd++; } }
+    if (!nd) return false;
+    if (*p == 'e' || *p == 'E') {
+        p++;
+        if (*p == '+' || *p == '-') p++;
+        if (!isdigit((unsigned char)*p)) return false;
+        while (isdigit((unsigned char)*p)) p++;
+    }
+    return *p == 0;
+}
+/* would Python's int() accept it?  (xm.py:250) */
+inline bool py_int_accepts(const std::string &raw)
+{
+    std::string t;
+    if (!strip_underscores(raw, t)) return false;
+    const char *p = t.c_str();
+    if (*p == '+' || *p == '-') p++;
+    if (!isdigit((unsigned char)*p)) return false;
+    while (isdigit((unsigned char)*p)) p++;
+    return *p == 0;
+}
+
+/* class of a "value is not a plain 31-bit integer" report for one line and one lookup */
+inline int diagnose_number(const std::string &line, int score_src, bool want_xs)
+{
+    for (unsigned char c : line) if (c >= 0x80) return XM_ERR_UNSUPPORTED;
+    std::vector<std::string> tok;
+    size_t i = 0;
+    while (i < line.size()) {
+        while (i < line.size() && host_is_space((unsigned char)line[i])) i++;
+        size_t j = i;
+        while (j < line.size() && !host_is_space((unsigned char)line[j])) j++;
+        if (j > i) tok.push_back(line.substr(i, j - i));
+        i = j;
+    }
+    const bool nm = score_src == SCORE_CIGAR_NM && !want_xs;
+    const char *tag = want_xs ? (score_src == SCORE_AS_ZS ? "ZS" : "XS") : (nm ? "NM" : "AS");
+    for (size_t k = 11; k < tok.size(); k++) {
+        if (tok[k].find(tag) == std::string::npos) continue;
+        const size_t c = tok[k].rfind(':');
+        const std::string val = c == std::string::npos ? tok[k] : tok[k].substr(c + 1);
+        const bool ok = nm ? py_int_accepts(val) : py_float_accepts(val);
+        return ok ? XM_ERR_UNSUPPORTED : XM_ERR_VALUE;      /* first match: duplicates were reported as such */
+    }
+    return XM_ERR_UNSUPPORTED;
+}
+
+/* ---- scratch --------------------------------------------------------------- */
+struct Scratch {
+    unsigned long long *chain1_s = nullptr, *chain1_p = nullptr, *c2_agg = nullptr, *c2_inc = nullptr;
+    uint32_t *c2_flag = nullptr;
+    uint64_t cap_tiles_s = 0, cap_tiles_p = 0;
+    SCompact sc{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t sc_cap = 0;
+    Globals *g = nullptr;
+};
+
+template <class BE>
+inline void scratch_release(BE &be, Scratch &s)
+{
+    be.release(s.chain1_s); be.release(s.chain1_p); be.release(s.c2_agg); be.release(s.c2_inc); be.release(s.c2_flag);
+    be.release(s.sc.start); be.release(s.sc.as); be.release(s.sc.xs); be.release(s.sc.h1); be.release(s.sc.h2); be.release(s.sc.meta);
+    be.release(s.g);
+    s = Scratch();
+}
+
+template <class BE>
+inline bool scratch_reserve(BE &be, Scratch &s, uint64_t tiles_s, uint64_t tiles_p, uint64_t sc_cap)
+{
+    if (!s.g) { s.g = (Globals *)be.alloc(sizeof(Globals)); if (!s.g) return false; }
+    if (tiles_s > s.cap_tiles_s) {
+        be.release(s.chain1_s);
+        s.chain1_s = (unsigned long long *)be.alloc(tiles_s * 8);
+        if (!s.chain1_s) return false;
+        s.cap_tiles_s = tiles_s;
+    }
+    if (tiles_p > s.cap_tiles_p) {
+        be.release(s.chain1_p); be.release(s.c2_agg); be.release(s.c2_inc); be.release(s.c2_flag);
+        s.chain1_p = (unsigned long long *)be.alloc(tiles_p * 8);
+        s.c2_agg = (unsigned long long *)be.alloc(tiles_p * 8 * C2_SLOTS);
+        s.c2_inc = (unsigned long long *)be.alloc(tiles_p * 8 * C2_SLOTS);
+        s.c2_flag = (uint32_t *)be.alloc(tiles_p * 4);
+        if (!s.chain1_p || !s.c2_agg || !s.c2_inc || !s.c2_flag) return false;
+        s.cap_tiles_p = tiles_p;
+    }
+    if (sc_cap > s.sc_cap) {
+        be.release(s.sc.start); be.release(s.sc.as); be.release(s.sc.xs); be.release(s.sc.h1); be.release(s.sc.h2); be.release(s.sc.meta);
+        s.sc.start = (uint64_t *)be.alloc((sc_cap + 1) * 8);
+        s.sc.as = (int32_t *)be.alloc(sc_cap * 4 + 16);
+        s.sc.xs = (int32_t *)be.alloc(sc_cap * 4 + 16);
+        s.sc.h1 = (uint32_t *)be.alloc(sc_cap * 4 + 16);
+        s.sc.h2 = (uint32_t *)be.alloc(sc_cap * 4 + 16);
+        s.sc.meta = (uint32_t *)be.alloc(sc_cap * 4 + 16);
+        if (!s.sc.start || !s.sc.as || !s.sc.xs || !s.sc.h1 || !s.sc.h2 || !s.sc.meta) { s.sc_cap = 0; return false; }
+        s.sc_cap = sc_cap;
+    }
+    return true;
+}
+
+/* one line of a resident stream, fetched to the host (error paths only) */
+template <class BE>
+inline std::string fetch_line(BE &be, const StreamBuf &B, uint64_t off)
+{
+    std::string out;
+    const size_t blk = 1 << 16;
+    std::vector<char> buf(blk);
+    while (off < B.len && out.size() < (64u << 20)) {
+        const size_t n = (size_t)((B.len - off) < blk ? (B.len - off) : blk);
+        be.read(buf.data(), B.p + off, n);
+        const void *nl = memchr(buf.data(), '\n', n);
+        if (nl) { out.append(buf.data(), (const char *)nl - buf.data()); return out; }
+        out.append(buf.data(), n);
+        off += n;
+    }
+    return out;
+}
+/* start of the line that precedes the one starting at off */
+template <class BE>
+inline uint64_t prev_line_off(BE &be, const StreamBuf &B, uint64_t off)
+{
+    if (off < 2) return 0;
+    uint64_t end = off - 1;                 /* the newline that ends the previous line */
+    const size_t blk = 1 << 16;
+    std::vector<char> buf(blk);
+    while (end > 0) {
+        const size_t n = (size_t)(end < blk ? end : blk);
+        be.read(buf.data(), B.p + (end - n), n);
+        for (size_t k = n; k > 0; k--) if (buf[k - 1] == '\n') return end - n + k;
+        end -= n;
+    }
+    return 0;
+}
+
+struct WalkTimes {
+    float ms_scan = 0, ms_classify = 0, ms_total = 0;
+    uint32_t launches = 0;
+};
+
+/*
+ * The resident walk.  P, S, out[] are in the backend's memory space.
+ * Returns an xm_status; res is always filled as far as known.
+ */
+template <class BE>
+inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBuf &S, const xm_opts &o,
+                         uint8_t *const out[6], const uint64_t out_cap[6], uint32_t debug, xm_result *res, std::string &errmsg)
+{
+    memset(res, 0, sizeof *res);
+    res->err_stream = -1;
+    if (o.mode < 0 || o.mode > 2 || o.score_src < 0 || o.score_src > 2) { errmsg = "bad mode / score_src"; return res->status = XM_ERR_ARG; }
+    if (o.min_score != o.min_score) { errmsg = "min_score is NaN"; return res->status = XM_ERR_UNSUPPORTED; }
+    if (P.len == 0 || S.len == 0) return res->status = XM_OK;       /* readline() == '' on the first call: nothing is yielded */
+
+    bool small = (debug & DBG_SMALL_TILES) != 0;
+    uint64_t limit = ~0ull;
+    uint64_t sc_need = 0;
+    Globals G;
+    int code_first = 0;
+    unsigned long long err_first = NO_ERROR;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        const uint64_t tile = small ? (uint64_t)CfgSmall::TILE : (uint64_t)CfgBig::TILE;
+        const uint64_t nt_s = (S.len + tile - 1) / tile, nt_p = (P.len + tile - 1) / tile;
+        if (nt_s > 0xffffffffull || nt_p > 0xffffffffull) { errmsg = "stream too large for one call"; return res->status = XM_ERR_ARG; }
+        if (!sc_need) {
+            /* size the per-record arrays from the mean line length of the first 256 KiB */
+            const size_t n = (size_t)(S.len < (256u << 10) ? S.len : (256u << 10));
+            std::vector<char> smp(n);
+            if (be.read(smp.data(), S.p, n)) { errmsg = "sample read failed"; return res->status = XM_ERR_CUDA; }
+            uint64_t nl = 0;
+            for (size_t k = 0; k < n; k++) nl += smp[k] == '\n';
+            const double mean = nl ? (double)n / (double)nl : (double)n;
+            sc_need = (uint64_t)((double)S.len / mean * 1.05) + 4096;
+        }
+        if (!scratch_reserve(be, sc, nt_s, nt_p, sc_need)) { errmsg = "out of device memory for scratch"; return res->status = XM_ERR_NOMEM; }
+        Globals init;
+        memset(&init, 0, sizeof init);
+        init.err = NO_ERROR;
+        init.limit_off = ~0ull;
+        if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_s * 8) || be.zero(sc.chain1_p, nt_p * 8) ||
+            be.zero(sc.c2_flag, nt_p * 4)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
+
+        ScanArgs sa;
+        memset(&sa, 0, sizeof sa);
+        sa.S = S; sa.sc = sc.sc; sa.sc_cap = sc.sc_cap; sa.chain1 = sc.chain1_s; sa.g = sc.g; sa.ntiles = (uint32_t)nt_s;
+        sa.score_src = o.score_src; sa.skip = o.skip_repeated ? 1 : 0; sa.stream_id = 1; sa.debug = debug;
+        ClassifyArgs ca;
+        memset(&ca, 0, sizeof ca);
+        ca.P = P; ca.S = S; ca.sc = sc.sc; ca.chain1 = sc.chain1_p; ca.c2_flag = sc.c2_flag; ca.c2_agg = sc.c2_agg; ca.c2_inc = sc.c2_inc;
+        ca.g = sc.g; ca.ntiles = (uint32_t)nt_p; ca.mode = o.mode; ca.score_src = o.score_src; ca.skip = sa.skip;
+        ca.thr = score_threshold(o.min_score); ca.enabled = o.enabled_bins & 0x3f; ca.limit = limit; ca.debug = debug;
+        for (int b = 0; b < 6; ++b) { ca.out[b] = out[b]; ca.out_cap[b] = ((ca.enabled >> b) & 1u) ? out_cap[b] : 0; }
+
+        be.tick(0);
+        if (be.scan(sa, small)) { errmsg = "scan kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+        be.tick(1);
+        if (be.classify(ca, small)) { errmsg = "classify kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+        be.tick(2);
+        if (be.sync()) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+        res->n_launches += 2;
+        res->ms_scan = be.elapsed(0, 1); res->ms_classify = be.elapsed(1, 2); res->ms_total += be.elapsed(0, 2);
+        if (be.read(&G, sc.g, sizeof G)) { errmsg = "result read failed"; return res->status = XM_ERR_CUDA; }
+
+        if (G.overflow && !small) { small = true; continue; }           /* pathologically short lines: 1 KiB tiles cannot overflow */
+        if (G.n_stream[1] > sc.sc_cap) { sc_need = G.n_stream[1] + 1; continue; }
+        if (G.err != NO_ERROR && limit == ~0ull) {
+            /* re-run cut at the failing record: outputs and counts of everything before it, like the reference's streaming writes */
+            err_first = G.err;
+            code_first = (int)((G.err >> 2) & 63);
+            limit = G.err >> 8;
+            continue;
+        }
+        break;
+    }
+
+    unsigned long long n = G.n_stream[0] < G.n_stream[1] ? G.n_stream[0] : G.n_stream[1];
+    if (limit < n) n = limit;
+    res->n_records = n;
+    for (int k = 0; k < 36; ++k) res->counts[k] = G.counts[k];
+    for (int b = 0; b < 6; ++b) res->out_len[b] = G.out_len[b];
+    res->bytes_in[0] = G.bytes_in[0];
+    if (n > 0) {
+        unsigned long long s0 = 0, s1 = 0;
+        be.read(&s0, sc.sc.start, 8);
+        be.read(&s1, sc.sc.start + n, 8);
+        res->bytes_in[1] = s1 - s0;
+    }
+    for (int b = 0; b < 6; ++b)
+        if (((o.enabled_bins >> b) & 1u) && G.out_len[b] > out_cap[b]) {
+            errmsg = "output buffer too small for bin " + std::to_string(b);
+            return res->status = XM_ERR_ARG;
+        }
+    if (err_first == NO_ERROR) return res->status = XM_OK;
+
+    /* map the device report onto the reference's exception class */
+    const int stream = (int)(err_first & 1), prev = (int)((err_first >> 1) & 1);
+    res->err_record = limit;
+    res->err_stream = stream;
+    int status;
+    if (code_first == EC_ASSERT) { status = XM_ERR_ASSERT; errmsg = "QNAMEs differ at record " + std::to_string(limit); }
+    else if (code_first == EC_DUP) { status = XM_ERR_VALUE; errmsg = "SAM line has multiple values of a score tag at record " + std::to_string(limit); }
+    else {
+        /* fetch the text of the line the report points at */
+        uint64_t off = 0;
+        const StreamBuf &B = stream ? S : P;
+        if (stream) { unsigned long long v = 0; be.read(&v, sc.sc.start + (limit - (prev ? 1 : 0)), 8); off = v; }
+        else { off = G.limit_off; if (prev) off = prev_line_off(be, P, off); }
+        const std::string line = fetch_line(be, B, off);
+        if (code_first == EC_TEXT) {
+            bool ascii = true;
+            for (unsigned char c : line) if (c >= 0x80) ascii = false;
+            status = (!ascii && !utf8_valid((const unsigned char *)line.data(), line.size())) ? XM_ERR_UNICODE : XM_ERR_UNSUPPORTED;
+            errmsg = status == XM_ERR_UNICODE ? "invalid UTF-8 in record " : "text outside the device grammar (non-ASCII byte, lone CR or oversized line) in record ";
+            errmsg += std::to_string(limit);
+        } else {
+            status = diagnose_number(line, o.score_src, code_first == EC_NUM_XS);
+            errmsg = (status == XM_ERR_VALUE ? "score tag value is not a number at record " : "score tag value outside the device grammar (plain 31-bit integer) at record ") + std::to_string(limit);
+        }
+    }
+    return res->status = status;
+}
+
+}  // namespace xm
