@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+# encoding: utf-8
+"""
+xenomapper_b200.xenomapper -- host side of the B200 read-binning path.
+
+Same names, arguments, return values and exceptions as
+xenomapper/xenomapper.py of genomematt/xenomapper v1.0.2 ("xm.py"), so a
+caller (or the reference's own test-suite) can switch modules without other
+changes.  What differs is where the work happens: the lockstep walk of
+getReadPairs + main_single_end / main_paired_end /
+conservative_main_paired_end (xm.py:95-118, 291-556) is ONE call into
+libxenomapper_b200.so (include/xenomapper_b200.h), which runs the sm_100a CUDA
+kernels.  There is no Python or CPU implementation of the walk in this module:
+without the library and a B200 the walk raises.
+
+What stays in Python, because it is text glue around the walk and not part of
+it: SAM header handling (xm.py:36-46, 120-174), the summary table
+(xm.py:558-566) and the command line (xm.py:568-743).  get_tag*,
+get_cigarbased_AS_tag and get_mapping_state are kept as single-record
+utilities and as the `tag_func` selectors of the walks; the walks never call
+them (tags are parsed in-kernel).
+"""
+import argparse
+import io
+import os
+import re
+import sys
+import textwrap
+from collections import Counter
+
+from . import _lib
+from ._lib import UnsupportedInput, XenomapperLibraryError  # noqa: F401  (re-exported)
+
+__version__ = "1.0.2"        # the reference version this module mirrors; written into @PG lines (xm.py:128)
+
+STATES = _lib.BINS
+NEG_INF = float("-inf")
+
+
+# ---------------------------------------------------------------------------
+# headers (boundary glue; byte parity "headers included")
+
+def get_sam_header(samfile):
+    """Leading '@' lines of a SAM file, without newlines; leaves the file at the
+    first record.  Mirrors xm.py:36-46, including IndexError on a header-only
+    or empty file."""
+    header = []
+    while True:
+        mark = samfile.tell()
+        line = samfile.readline().strip('\n')
+        if line[0] != '@':          # '' raises IndexError, as in the reference
+            samfile.seek(mark)
+            return header
+        header.append(line)
+
+
+def get_bam_header(bamfile):
+    """Header text lines stored in a BAM file (the `samtools view -H` of xm.py:48-54)."""
+    from . import bam
+    text = bam.read_header_text(bamfile)
+    bamfile.seek(0)
+    return [x for x in text.split('\n') if x]
+
+
+def add_pg_tag(sam_header_list, comment=None):
+    """Header plus Xenomapper's @PG line (chained with PP: to a trailing @PG) and an
+    optional @CO line.  Mirrors xm.py:120-131."""
+    out = list(sam_header_list)
+    if any(not h.startswith('@') for h in out):
+        raise ValueError('Incorrect SAM header format :\n{0}'.format('\n'.join(out)))
+    pp = ''
+    if out[-1][:3] == '@PG':        # IndexError on an empty header, as in the reference
+        ids = [t for t in out[-1].split() if t[:2] == 'ID']
+        pp = 'PP' + ids[0][2:] + '\t'
+    out.append('@PG\tID:Xenomapper\tPN:Xenomapper\t' + pp + 'VN:{0}'.format(__version__))
+    if comment:
+        out.append('@CO\t' + comment)
+    return out
+
+
+def process_headers(file1, file2, primary_specific=sys.stdout, secondary_specific=None,
+                    primary_multi=None, secondary_multi=None, unassigned=None, unresolved=None, bam=False):
+    """Write each enabled output's header.  Mirrors xm.py:133-174: primary-species
+    header for primary_*, unassigned and unresolved; secondary-species header
+    for secondary_*."""
+    reader = get_bam_header if bam else get_sam_header
+    h1, h2 = reader(file1), reader(file2)
+    print('\n'.join(add_pg_tag(h1, comment='species specific reads')), file=primary_specific)
+    plan = ((secondary_specific, h2, 'species specific reads'),
+            (primary_multi, h1, 'species specific multimapping reads'),
+            (secondary_multi, h2, 'species specific multimapping reads'),
+            (unassigned, h1, 'reads that could not be assigned'),
+            (unresolved, h1, 'reads that could not be resolved'))
+    for out, hdr, comment in plan:
+        if out:
+            print('\n'.join(add_pg_tag(hdr, comment=comment)), file=out)
+
+
+# ---------------------------------------------------------------------------
+# single-record utilities and tag_func selectors (not used by the walks)
+
+def get_tag(sam_line, tag='AS'):
+    """Value of a numeric SAM tag, -inf if absent.  Mirrors xm.py:176-191
+    (substring match on fields >= 11, ValueError on several matches)."""
+    hits = [f for f in sam_line[11:] if tag in f]
+    if not hits:
+        return NEG_INF
+    if len(hits) > 1:
+        raise ValueError('SAM line has multiple values of {0}: {1}'.format(tag, sam_line))
+    return float(hits[0].split(':')[-1])
+
+
+def get_tag_with_ZS_as_XS(sam_line, tag='AS'):
+    """get_tag, answering requests for XS with the ZS tag (HISAT).  Mirrors xm.py:193-206."""
+    return get_tag(sam_line, 'ZS' if tag == 'XS' else tag)
+
+
+_CIGAR_OP = re.compile(r'([0-9]+)([MIDNSHPX=])')
+
+
+def get_cigarbased_AS_tag(sam_line, tag='AS'):
+    """Score derived from CIGAR and NM: -6/mismatch, -5/gap open, -3/gap base,
+    -2/soft-clipped base.  Other tags come from get_tag.  Mirrors xm.py:228-256."""
+    if tag != 'AS':
+        return get_tag(sam_line, tag)
+    nm = [f for f in sam_line[11:] if 'NM' in f]
+    if not nm:
+        return NEG_INF
+    mismatches = int(nm[0].split(':')[-1])
+    gaps, gap_bases, clipped = 0, 0, 0
+    for n, op in _CIGAR_OP.findall(sam_line[5]):
+        if op in 'ID':
+            gaps += 1
+            gap_bases += int(n)
+        elif op == 'S':
+            clipped += int(n)
+    return -6 * mismatches - 5 * gaps - 3 * gap_bases - 2 * clipped
+
+
+def get_mapping_state(AS1, XS1, AS2, XS2, min_score=NEG_INF):
+    """The six-way decision of xm.py:258-289 for one read."""
+    if AS1 <= min_score and AS2 <= min_score:
+        return 'unassigned'
+    if AS1 > min_score and (AS2 <= min_score or AS1 > AS2):
+        return 'primary_specific' if (not XS1 or AS1 > XS1) else 'primary_multi'
+    if AS1 == AS2:
+        return 'unresolved'
+    if AS2 > min_score and (AS1 <= min_score or AS2 > AS1):
+        return 'secondary_specific' if (not XS2 or AS2 > XS2) else 'secondary_multi'
+    raise RuntimeError('Error in processing logic with values {0} '.format((AS1, XS1, AS2, XS2)))
+
+
+_SCORE_SRC = {get_tag: _lib.SCORE_AS_XS, get_tag_with_ZS_as_XS: _lib.SCORE_AS_ZS,
+              get_cigarbased_AS_tag: _lib.SCORE_CIGAR_NM}
+
+
+# ---------------------------------------------------------------------------
+# the lockstep reader: a handle on the two record regions
+
+class ReadPairs:
+    """What getReadPairs returns: the two inputs positioned after their headers,
+    plus the skip flag.  main_single_end / main_paired_end /
+    conservative_main_paired_end recognise it and hand both record regions to
+    the library in one call.  Iterating it yields (fields1, fields2) like the
+    reference's generator, for callers that consume the pairs themselves."""
+
+    def __init__(self, sam1, sam2, skip_repeated_reads=False, bam=False):
+        self.sam1, self.sam2 = sam1, sam2
+        self.skip_repeated_reads = bool(skip_repeated_reads)
+        self.bam = bam
+
+    def record_regions(self):
+        """bytes of both record regions, through the inputs' own text layer
+        (so decoding errors and universal newlines behave as in the reference)"""
+        if self.bam:
+            from . import bam
+            return bam.records_as_sam_text(self.sam1), bam.records_as_sam_text(self.sam2)
+        return _remaining_bytes(self.sam1), _remaining_bytes(self.sam2)
+
+    def __iter__(self):
+        p, s = self.record_regions()
+        l1 = iter(p.decode('utf-8', 'surrogateescape').split('\n'))
+        l2 = iter(s.decode('utf-8', 'surrogateescape').split('\n'))
+        a, b = next(l1, '').split(), next(l2, '').split()
+        while a and b:
+            assert a[0] == b[0]
+            yield a, b
+            if self.skip_repeated_reads:
+                na, nb = a[0], b[0]
+                while a and b and a[0] == na:
+                    a = next(l1, '').split()
+                while a and b and b[0] == nb:
+                    b = next(l2, '').split()
+            else:
+                a, b = next(l1, '').split(), next(l2, '').split()
+
+
+def _remaining_bytes(f):
+    data = f.read()
+    if isinstance(data, str):
+        data = data.encode('utf-8', 'surrogateescape')
+    return data
+
+
+def getReadPairs(sam1, sam2, skip_repeated_reads=False):
+    """Pair up the records of two SAM files read in lockstep (xm.py:95-118)."""
+    return ReadPairs(sam1, sam2, skip_repeated_reads)
+
+
+def getBamReadPairs(bamfile1, bamfile2, skip_repeated_reads=False):
+    """Pair up the records of two BAM files (xm.py:66-93), decoded without samtools."""
+    return ReadPairs(bamfile1, bamfile2, skip_repeated_reads, bam=True)
+
+
+def _serialise_pairs(readpairs):
+    """A caller-supplied iterable of (fields1, fields2): back to two SAM record regions."""
+    p, s = [], []
+    for a, b in readpairs:
+        for fields in (a, b):
+            if not fields or any((not t) or len(t.split()) != 1 or t != t.strip() for t in fields):
+                raise UnsupportedInput("field lists with empty or whitespace-bearing fields cannot be re-serialised")
+        p.append('\t'.join(a))
+        s.append('\t'.join(b))
+    enc = lambda rows: ('\n'.join(rows) + '\n').encode('utf-8', 'surrogateescape') if rows else b''
+    return enc(p), enc(s)
+
+
+# ---------------------------------------------------------------------------
+# the walks
+
+def _raise_for(rc, ctx, res):
+    msg = ctx.error()
+    if rc == _lib.XM_ERR_ASSERT:
+        raise AssertionError(msg)
+    if rc == _lib.XM_ERR_VALUE:
+        raise ValueError(msg)
+    if rc == _lib.XM_ERR_RUNTIME:
+        raise RuntimeError(msg)
+    if rc == _lib.XM_ERR_UNICODE:
+        raise UnicodeDecodeError('utf-8', b'', 0, 1, msg)
+    if rc == _lib.XM_ERR_UNSUPPORTED:
+        raise UnsupportedInput(msg)
+    raise XenomapperLibraryError(msg)
+
+
+def _counter(res, paired):
+    c = Counter()
+    if paired:
+        for f in range(6):
+            for r in range(6):
+                n = res.counts[f * 6 + r]
+                if n:
+                    c[(STATES[f], STATES[r])] = n
+    else:
+        for k in range(6):
+            if res.counts[k]:
+                c[STATES[k]] = res.counts[k]
+    return c
+
+
+def _walk(mode, readpairs, outputs, min_score, tag_func):
+    try:
+        score_src = _SCORE_SRC[tag_func]
+    except (KeyError, TypeError):
+        raise NotImplementedError(
+            "tag_func must be get_tag, get_tag_with_ZS_as_XS or get_cigarbased_AS_tag: scores are parsed "
+            "inside the CUDA kernels, arbitrary Python callables cannot run there")
+    if isinstance(readpairs, ReadPairs):
+        prim, sec = readpairs.record_regions()
+        skip = readpairs.skip_repeated_reads
+    else:
+        prim, sec = _serialise_pairs(readpairs)
+        skip = False
+    enabled = 0
+    for b, out in enumerate(outputs):
+        if out:                      # the reference tests truthiness (xm.py:333)
+            enabled |= 1 << b
+    ctx = _lib.default_context()
+    opts = ctx.opts(mode, score_src, skip, float(min_score), enabled)
+    rc, res, outs = ctx.classify_host(prim, sec, opts)
+    # everything before a failing record is written, like the reference's streaming prints
+    for b, out in enumerate(outputs):
+        if out and outs[b]:
+            out.write(outs[b].decode('utf-8', 'surrogateescape'))
+    if rc != _lib.XM_OK:
+        _raise_for(rc, ctx, res)
+    return _counter(res, mode != _lib.MODE_SE)
+
+
+def main_single_end(readpairs, primary_specific=sys.stdout, secondary_specific=None, primary_multi=None,
+                    secondary_multi=None, unassigned=None, unresolved=None, min_score=NEG_INF, tag_func=get_tag):
+    """Bin single-end reads (xm.py:291-352).  Returns a Counter keyed by category."""
+    outs = (primary_specific, secondary_specific, primary_multi, secondary_multi, unassigned, unresolved)
+    return _walk(_lib.MODE_SE, readpairs, outs, min_score, tag_func)
+
+
+def main_paired_end(readpairs, primary_specific=sys.stdout, secondary_specific=None, primary_multi=None,
+                    secondary_multi=None, unassigned=None, unresolved=None, min_score=NEG_INF, tag_func=get_tag):
+    """Bin interlaced read pairs, liberal priority chain (xm.py:354-454).
+    Returns a Counter keyed by (forward, reverse) category."""
+    outs = (primary_specific, secondary_specific, primary_multi, secondary_multi, unassigned, unresolved)
+    return _walk(_lib.MODE_PE_LIBERAL, readpairs, outs, min_score, tag_func)
+
+
+def conservative_main_paired_end(readpairs, primary_specific=sys.stdout, secondary_specific=None, primary_multi=None,
+                                 secondary_multi=None, unassigned=None, unresolved=None, min_score=NEG_INF,
+                                 tag_func=get_tag):
+    """Bin interlaced read pairs, conservative chain (xm.py:456-556)."""
+    outs = (primary_specific, secondary_specific, primary_multi, secondary_multi, unassigned, unresolved)
+    return _walk(_lib.MODE_PE_CONSERVATIVE, readpairs, outs, min_score, tag_func)
+
+
+def output_summary(category_counts, outfile=sys.stderr):
+    """The markdown table of xm.py:558-566."""
+    w = lambda *a, **k: print(*a, file=outfile, **k)
+    w('-' * 80)
+    w('Read Count Category Summary\n')
+    w('|       {0:45s}|     {1:10s}  |'.format('Category', 'Count'))
+    w('|:' + '-' * 50 + ':|:' + '-' * 15 + ':|')
+    for category in sorted(category_counts):
+        w('|  {0:50s}|{1:15d}  |'.format(str(category), category_counts[category]))
+    w()
+
+
+# ---------------------------------------------------------------------------
+# command line (same flags as xm.py:568-678)
+
+def command_line_interface(argv=None):
+    p = argparse.ArgumentParser(
+        prog="xenomapper", formatter_class=argparse.RawDescriptionHelpFormatter,
+        description=textwrap.dedent("""\
+            Sorts the reads of two SAM (or BAM) files, the same reads aligned to a primary and a
+            secondary species, into species specific, multimapping, unresolved and unassigned
+            outputs.  B200 build: the read-binning walk runs on the GPU.
+
+            Both files need AS and XS scores where higher is better (Bowtie2 --local; with -p also
+            --reorder), the reads in the same order.  --cigar_scores and --use_zs cover aligners
+            without usable AS/XS tags.  Inputs must be seekable."""),
+        epilog="To write BAM use process substitution:  --primary_specific >(samtools view -bS - > out.bam)")
+    a = p.add_argument
+    a('--primary_sam', type=argparse.FileType('rt'), default=None, help='SAM file of the alignment to the primary species')
+    a('--secondary_sam', type=argparse.FileType('rt'), default=None, help='SAM file of the alignment to the secondary species')
+    a('--primary_bam', type=argparse.FileType('rb'), default=None, help='BAM file of the alignment to the primary species')
+    a('--secondary_bam', type=argparse.FileType('rb'), default=None, help='BAM file of the alignment to the secondary species')
+    a('--primary_specific', type=argparse.FileType('wt'), default=sys.stdout, help='output: reads specific to the primary species')
+    a('--secondary_specific', type=argparse.FileType('wt'), default=None, help='output: reads specific to the secondary species')
+    a('--primary_multi', type=argparse.FileType('wt'), default=None, help='output: reads multimapping in the primary species')
+    a('--secondary_multi', type=argparse.FileType('wt'), default=None, help='output: reads multimapping in the secondary species')
+    a('--unassigned', type=argparse.FileType('wt'), default=None, help='output: reads mapping in neither species')
+    a('--unresolved', type=argparse.FileType('wt'), default=None, help='output: reads mapping equally well in both species')
+    a('--paired', action='store_true', help='reads are paired, mates interlaced, each pair once')
+    a('--conservative', action='store_true', help='paired reads: any unassigned mate makes the pair unassigned, discordant species unresolved')
+    a('--min_score', type=float, default=NEG_INF, help='scores less than or equal to this count as unmapped')
+    a('--cigar_scores', action='store_true', help='score = -6*NM -5*gap opens -3*gap bases -2*soft clipped bases, from CIGAR and NM')
+    a('--use_zs', action='store_true', help='take the next-best score from ZS instead of XS (HISAT)')
+    a('--version', action='store_true', help='print version information and exit')
+    args = p.parse_args(argv)
+    if args.version:
+        print(__version__)
+        sys.exit()
+    if (not args.primary_sam or not args.secondary_sam) and (not args.primary_bam or not args.secondary_bam):
+        print('ERROR: You must provide --primary_sam and --secondary_sam\n or --primary_bam and --secondary_bam\n')
+        p.print_help()
+        sys.exit(1)
+    return args
+
+
+def main(argv=None):
+    """Console entry point (xm.py:681-743)."""
+    args = command_line_interface(argv)
+    tag_func = get_cigarbased_AS_tag if args.cigar_scores else (get_tag_with_ZS_as_XS if args.use_zs else get_tag)
+    outs = dict(primary_specific=args.primary_specific, secondary_specific=args.secondary_specific,
+                primary_multi=args.primary_multi, secondary_multi=args.secondary_multi,
+                unassigned=args.unassigned, unresolved=args.unresolved)
+    skip = not args.paired                       # xm.py:691
+    if args.primary_sam:
+        process_headers(args.primary_sam, args.secondary_sam, **outs)
+        pairs = getReadPairs(args.primary_sam, args.secondary_sam, skip_repeated_reads=skip)
+    else:
+        process_headers(args.primary_bam, args.secondary_bam, bam=True, **outs)
+        pairs = getBamReadPairs(args.primary_bam, args.secondary_bam, skip_repeated_reads=skip)
+    walk = main_single_end if not args.paired else (conservative_main_paired_end if args.conservative else main_paired_end)
+    counts = walk(pairs, min_score=args.min_score, tag_func=tag_func, **outs)
+    for f in outs.values():
+        if f:
+            f.flush()
+    output_summary(counts)
+
+
+if __name__ == '__main__':
+    main()
