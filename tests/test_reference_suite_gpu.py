@@ -1,0 +1,107 @@
+"""The reference's own known-answer walk tests (xenomapper/tests/test_xenomapper.py:56-161), run against
+xenomapper_b200.xenomapper: same calls, same assertions, the walk on the GPU."""
+import hashlib
+import io
+
+import pytest
+
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _open(key, which):
+    return io.TextIOWrapper(io.BytesIO(G.fixture_bytes(key, which)))
+
+
+def _six():
+    return dict(primary_specific=io.StringIO(), secondary_specific=io.StringIO(), primary_multi=io.StringIO(),
+                secondary_multi=io.StringIO(), unresolved=io.StringIO(), unassigned=io.StringIO())
+
+
+def nlines(f):
+    return len(f.getvalue().split('\n'))
+
+
+def test_consistent_output_SE():
+    """test_xenomapper.py:56-96"""
+    from xenomapper_b200.xenomapper import process_headers, main_single_end, getReadPairs
+    o = _six()
+    sam1, sam2 = _open("se", "primary"), _open("se", "secondary")
+    process_headers(sam1, sam2, **o)
+    cat_counts = main_single_end(getReadPairs(sam1, sam2), **o)
+    for k in ("primary_specific", "primary_multi", "secondary_specific", "secondary_multi", "unassigned"):
+        assert cat_counts[k] == nlines(o[k]) - 4
+    assert hashlib.sha224(o["primary_specific"].getvalue().encode('latin-1')).hexdigest() == \
+        '381325b12dd9a9cd3afdd72eeb16b23cc92ddd16f675bb21bb21e08e'
+
+
+def test_consistent_output_PE():
+    """test_xenomapper.py:98-128"""
+    from xenomapper_b200.xenomapper import process_headers, main_paired_end, getReadPairs
+    o = _six()
+    sam1, sam2 = _open("pe", "primary"), _open("pe", "secondary")
+    process_headers(sam1, sam2, primary_specific=o["primary_specific"], secondary_specific=o["secondary_specific"])
+    c = main_paired_end(getReadPairs(sam1, sam2), **o)
+    assert sum(c[x] for x in c if 'primary_specific' in x) * 2 == nlines(o["primary_specific"]) - 30
+    assert sum(c[x] for x in c if 'secondary_specific' in x and 'primary_specific' not in x) * 2 == nlines(o["secondary_specific"]) - 27
+    assert sum(c[x] for x in c if 'primary_multi' in x and 'primary_specific' not in x and 'secondary_specific' not in x) * 2 == \
+        nlines(o["primary_multi"]) - 1
+    assert sum(c[x] for x in c if 'secondary_multi' in x and 'primary_multi' not in x and 'primary_specific' not in x
+               and 'secondary_specific' not in x) * 2 == nlines(o["secondary_multi"]) - 1
+    assert hashlib.sha224(o["primary_specific"].getvalue().encode('latin-1')).hexdigest() == \
+        '64c0e24bf141c5aa3bb0993c73b34cdfe630a504ac424843f746918d'
+
+
+def test_consistent_output_conservative_PE():
+    """test_xenomapper.py:130-161"""
+    from xenomapper_b200.xenomapper import process_headers, conservative_main_paired_end, getReadPairs
+    o = _six()
+    sam1, sam2 = _open("pe", "primary"), _open("pe", "secondary")
+    process_headers(sam1, sam2, primary_specific=o["primary_specific"], secondary_specific=o["secondary_specific"])
+    c = conservative_main_paired_end(getReadPairs(sam1, sam2), **o)
+    assert c[('primary_specific', 'secondary_specific')] * 4 + c[('unresolved', 'unresolved')] * 4 == nlines(o["unresolved"]) - 1
+    assert c[('primary_multi', 'primary_multi')] * 2 == nlines(o["primary_multi"]) - 1
+    assert c[('secondary_multi', 'secondary_multi')] * 2 == nlines(o["secondary_multi"]) - 1
+    assert (c[('primary_specific', 'primary_specific')] + c[('primary_specific', 'primary_multi')] +
+            c[('primary_multi', 'primary_specific')]) * 2 == nlines(o["primary_specific"]) - 30
+    assert (c[('secondary_specific', 'secondary_specific')] + c[('secondary_specific', 'secondary_multi')] +
+            c[('secondary_multi', 'secondary_specific')]) * 2 == nlines(o["secondary_specific"]) - 27
+    assert c[('unassigned', 'unassigned')] * 2 == nlines(o["unassigned"]) - 1
+    assert hashlib.sha224(o["primary_specific"].getvalue().encode('latin-1')).hexdigest() == \
+        'c4de3de755092c8f9ff1eb2cd360a502d74ebd4c1e65ed282515ed3e'
+
+
+@pytest.mark.parametrize("name", ["fixture_se_mode0_src0_skip0_min-inf", "fixture_pe_mode1_src0_skip0_min-inf",
+                                  "fixture_pe_mode2_src0_skip0_min-inf", "fixture_pe_mode1_src2_skip0_min-inf",
+                                  "fixture_se_mode0_src0_skip1_min-inf", "fixture_pe_mode2_src0_skip0_min60.0"])
+def test_full_files_headers_included(name):
+    """six complete output files (header + records) and the summary text, byte for byte as the reference CLI writes them"""
+    from xenomapper_b200 import xenomapper as xm
+    case = G.BY_NAME[name]
+    key, o = case["input"]["key"], case["opts"]
+    outs = [io.StringIO() for _ in range(6)]
+    f1, f2 = _open(key, "primary"), _open(key, "secondary")
+    xm.process_headers(f1, f2, *outs)
+    walk = (xm.main_single_end, xm.main_paired_end, xm.conservative_main_paired_end)[o["mode"]]
+    tag = (xm.get_tag, xm.get_tag_with_ZS_as_XS, xm.get_cigarbased_AS_tag)[o["score_src"]]
+    counts = walk(xm.getReadPairs(f1, f2, skip_repeated_reads=o["skip_repeated"]), *outs, min_score=o["min_score"], tag_func=tag)
+    e = case["expect"]
+    assert [G.sha(x.getvalue().encode()) for x in outs] == e["full_sha256"]
+    summary = io.StringIO()
+    xm.output_summary(counts, outfile=summary)
+    assert G.sha(summary.getvalue().encode()) == e["summary_sha256"]
+
+
+def test_cli_end_to_end(tmp_path, capsys):
+    """the console entry point on real files, stdout default for primary_specific (xm.py:618)"""
+    from xenomapper_b200 import xenomapper as xm
+    p, s = tmp_path / "h.sam", tmp_path / "m.sam"
+    p.write_bytes(G.fixture_bytes("pe", "primary")); s.write_bytes(G.fixture_bytes("pe", "secondary"))
+    un = tmp_path / "unresolved.sam"
+    xm.main(["--primary_sam", str(p), "--secondary_sam", str(s), "--paired", "--conservative", "--unresolved", str(un)])
+    cap = capsys.readouterr()
+    e = G.BY_NAME["fixture_pe_mode2_src0_skip0_min-inf"]["expect"]
+    assert G.sha(cap.out.encode()) == e["full_sha256"][0]
+    assert G.sha(un.read_bytes()) == e["full_sha256"][5]
+    assert G.sha(cap.err.encode()) == e["summary_sha256"]

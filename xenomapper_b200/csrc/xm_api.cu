@@ -28,7 +28,7 @@ static thread_local std::string g_create_error;
 
 struct DeviceBackend {
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int chk(cudaError_t e)
     {
@@ -127,7 +127,7 @@ xm_ctx *xm_create(int device, uint32_t flags)
         delete c;
         return nullptr;
     }
-    for (int k = 0; k < 3; ++k) cudaEventCreate(&c->be.ev[k]);
+    for (int k = 0; k < 4; ++k) cudaEventCreate(&c->be.ev[k]);
     return c;
 }
 
@@ -141,7 +141,7 @@ void xm_destroy(xm_ctx *c)
     for (auto &b : c->d_out) if (b.p) cudaFree(b.p);
     for (auto &b : c->h_out) if (b.p) cudaFreeHost(b.p);
     for (auto &b : c->h_stage) if (b.p) cudaFreeHost(b.p);
-    for (int k = 0; k < 3; ++k) if (c->be.ev[k]) cudaEventDestroy(c->be.ev[k]);
+    for (int k = 0; k < 4; ++k) if (c->be.ev[k]) cudaEventDestroy(c->be.ev[k]);
     if (c->be.st) cudaStreamDestroy(c->be.st);
     for (auto s : c->copy_st) if (s) cudaStreamDestroy(s);
     delete c;

@@ -273,6 +273,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         memset(&init, 0, sizeof init);
         init.err = NO_ERROR;
         init.limit_off = ~0ull;
+        be.tick(0);                                  /* the step starts here: scratch init is part of it */
         if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_s * 8) || be.zero(sc.chain1_p, nt_p * 8) ||
             be.zero(sc.c2_flag, nt_p * 4)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
 
@@ -287,14 +288,14 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         ca.thr = score_threshold(o.min_score); ca.enabled = o.enabled_bins & 0x3f; ca.limit = limit; ca.debug = debug;
         for (int b = 0; b < 6; ++b) { ca.out[b] = out[b]; ca.out_cap[b] = ((ca.enabled >> b) & 1u) ? out_cap[b] : 0; }
 
-        be.tick(0);
+        be.tick(3);
         if (be.scan(sa, small)) { errmsg = "scan kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
         be.tick(1);
         if (be.classify(ca, small)) { errmsg = "classify kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
         be.tick(2);
         if (be.sync()) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
         res->n_launches += 2;
-        res->ms_scan = be.elapsed(0, 1); res->ms_classify = be.elapsed(1, 2); res->ms_total += be.elapsed(0, 2);
+        res->ms_scan = be.elapsed(3, 1); res->ms_classify = be.elapsed(1, 2); res->ms_total += be.elapsed(0, 2);
         if (be.read(&G, sc.g, sizeof G)) { errmsg = "result read failed"; return res->status = XM_ERR_CUDA; }
 
         if (G.overflow && !small) { small = true; continue; }           /* pathologically short lines: 1 KiB tiles cannot overflow */
