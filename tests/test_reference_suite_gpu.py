@@ -93,15 +93,19 @@ def test_full_files_headers_included(name):
     assert G.sha(summary.getvalue().encode()) == e["summary_sha256"]
 
 
-def test_cli_end_to_end(tmp_path, capsys):
-    """the console entry point on real files, stdout default for primary_specific (xm.py:618)"""
-    from xenomapper_b200 import xenomapper as xm
+def test_cli_end_to_end(tmp_path):
+    """the console entry point on real files, stdout default for primary_specific (xm.py:618), run as a process"""
+    import os
+    import subprocess
+    import sys
     p, s = tmp_path / "h.sam", tmp_path / "m.sam"
     p.write_bytes(G.fixture_bytes("pe", "primary")); s.write_bytes(G.fixture_bytes("pe", "secondary"))
     un = tmp_path / "unresolved.sam"
-    xm.main(["--primary_sam", str(p), "--secondary_sam", str(s), "--paired", "--conservative", "--unresolved", str(un)])
-    cap = capsys.readouterr()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "xenomapper_b200.xenomapper", "--primary_sam", str(p), "--secondary_sam", str(s),
+                        "--paired", "--conservative", "--unresolved", str(un)], cwd=root, capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()
     e = G.BY_NAME["fixture_pe_mode2_src0_skip0_min-inf"]["expect"]
-    assert G.sha(cap.out.encode()) == e["full_sha256"][0]
+    assert G.sha(r.stdout) == e["full_sha256"][0]
     assert G.sha(un.read_bytes()) == e["full_sha256"][5]
-    assert G.sha(cap.err.encode()) == e["summary_sha256"]
+    assert G.sha(r.stderr) == e["summary_sha256"]

@@ -60,9 +60,7 @@ struct StreamBuf {
 /* what the secondary-stream scan leaves behind, one entry per yielded record */
 struct SCompact {
     uint64_t *start;     /* [n+1] byte offset of the record; [n] = offset just past the last one */
-    int32_t *as;         /* [n] */
-    int32_t *xs;         /* [n] */
-    uint32_t *h1, *h2;   /* [n] 64-bit QNAME hash */
+    uint4 *rec;          /* [n] x = AS, y = XS (SCORE_ABSENT when missing), z,w = 64-bit QNAME hash */
     uint32_t *meta;      /* [n] emitted length (24 bits) | flags << 24 */
 };
 
@@ -82,7 +80,8 @@ struct Globals {
 /* decoupled look-back descriptors */
 constexpr unsigned long long C1_AGG = 1ull << 62, C1_INC = 2ull << 62, C1_STOP = 1ull << 61;
 constexpr unsigned long long C1_COUNT = (1ull << 61) - 1;
-constexpr int C2_SLOTS = 8;           /* six bins + raw primary bytes + spare */
+constexpr int C2_SLOTS = 8;           /* six bins + raw primary bytes + spare (per-tile sums; the chain carries the six bins) */
+constexpr unsigned long long C2_AGG = 1ull << 62, C2_INC = 2ull << 62, C2_VAL = (1ull << 62) - 1;
 
 struct ScanArgs {
     StreamBuf S;
@@ -100,9 +99,7 @@ struct ClassifyArgs {
     StreamBuf P, S;
     SCompact sc;
     unsigned long long *chain1;       /* [ntiles] */
-    uint32_t *c2_flag;                /* [ntiles] 0 none, 1 aggregate, 2 inclusive */
-    unsigned long long *c2_agg;       /* [ntiles][C2_SLOTS] */
-    unsigned long long *c2_inc;       /* [ntiles][C2_SLOTS] */
+    unsigned long long *chain2;       /* [ntiles][C2_SLOTS] status << 62 | bytes, one look-back chain per bin */
     Globals *g;
     uint32_t ntiles;
     int32_t mode, score_src, skip;
@@ -116,23 +113,20 @@ struct ClassifyArgs {
 
 constexpr uint32_t DBG_FORCE_GENERIC = 1, DBG_SMALL_TILES = 2;
 
-/* tile geometry */
-template <int TILE_, int HALO_, int THREADS_, int R_>
+/* tile geometry: one line per thread */
+template <int TILE_, int HALO_, int THREADS_>
 struct Cfg {
     static constexpr int TILE = TILE_;        /* bytes of the stream one CTA owns (lines are owned by their first byte) */
     static constexpr int HALO = HALO_;        /* bytes staged before and after the tile */
     static constexpr int THREADS = THREADS_;
-    static constexpr int R = R_;              /* lines per thread */
     static constexpr int WIN = TILE + 2 * HALO;
-    static constexpr int NSLOT = WIN / 16 + 2;          /* 16-byte mask slots, covers WIN + 32 bits */
-    static constexpr int NW = NSLOT / 2;                /* 32-bit mask words */
-    static constexpr int NG = TILE / 128;               /* 4-word groups of the start mask */
-    static constexpr int LCAP = THREADS * R;
-    static constexpr int ITEMS = 2 * LCAP;
-    static_assert(TILE % 128 == 0 && HALO % 32 == 0, "geometry");
-    static_assert(NG <= THREADS, "one thread per start-mask group");
+    static constexpr int NW = WIN / 32 + 2;             /* 32-bit mask words: the window, the virtual newline bit, one spare */
+    static constexpr int WPT = (NW + THREADS - 1) / THREADS;   /* mask words per thread in the index pass */
+    static constexpr int LCAP = THREADS;                /* owned lines a tile can hold */
+    static_assert(TILE % 32 == 0 && HALO % 32 == 0 && HALO > 0, "geometry");
+    static_assert(WIN + 1 < 65535, "line starts are kept as 16-bit window offsets");
 };
-using CfgBig = Cfg<32768, 2048, 256, 2>;
-using CfgSmall = Cfg<1024, 1024, 256, 2>;     /* LCAP == TILE/2: can never overflow (non-blank lines need 2 bytes) */
+using CfgBig = Cfg<32768, 2048, 256>;
+using CfgSmall = Cfg<512, 512, 256>;          /* LCAP == TILE/2: cannot lose the stop (non-blank lines need 2 bytes) */
 
 }  // namespace xm

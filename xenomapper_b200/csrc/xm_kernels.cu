@@ -4,11 +4,13 @@
  *   k_scan<Cfg>      one CTA per tile of the secondary stream   (xm_tile.h scan_tile)
  *   k_classify<Cfg>  one CTA per tile of the primary stream     (xm_tile.h classify_tile)
  *
- * plus the device-only pieces the tile code calls: block collectives, the two
- * decoupled look-back chains and the warp copy engine.
+ * plus the device-only pieces the tile code calls: window staging by TMA bulk
+ * copy, block collectives, the two decoupled look-back chains and the copy
+ * engines.
  *
- * Tiles are handed out by an atomic ticket, so a CTA only ever waits on tiles
- * whose CTAs have already started: the look-back spins cannot deadlock.
+ * Tile = blockIdx.x.  The look-back spins wait only on lower-numbered tiles,
+ * which the hardware dispatches first (the ordering every single-pass
+ * decoupled look-back scan relies on).
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,53 +21,109 @@
 namespace xm {
 
 /* ---- block collectives --------------------------------------------------- */
-/* scratch: scr[0..31] warp totals, scr[32..63] warp exclusive prefixes */
-__device__ uint32_t dev_block_scan(uint32_t v, uint32_t *scr, uint32_t &total)
+/* One barrier each.  wt: one word per warp; consecutive collectives alternate between two banks so that a
+ * slow reader of one never meets the next one's writes. */
+__device__ uint32_t dev_block_scan(uint32_t v, uint32_t *wt, uint32_t &total)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint32_t x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
     }
-    __syncthreads();                     /* scratch may still be read by the previous collective */
-    if (lane == 31) scr[warp] = x;
+    if (lane == 31) wt[warp] = x;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t w = lane < nw ? scr[lane] : 0u, s = w;
+    /* every warp scans the (at most 32) warp totals for itself */
+    const uint32_t t = lane < nw ? wt[lane] : 0u;
+    uint32_t s = t;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += y;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += y;
+    }
+    total = __shfl_sync(0xffffffffu, s, 31);
+    const uint32_t pre = __shfl_sync(0xffffffffu, s - t, warp);
+    return pre + x - v;
+}
+
+__device__ uint32_t dev_block_min(uint32_t v, uint32_t *wt)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t x = __reduce_min_sync(0xffffffffu, v);
+    if (lane == 0) wt[warp] = x;
+    __syncthreads();
+    return __reduce_min_sync(0xffffffffu, lane < nw ? wt[lane] : 0xffffffffu);
+}
+
+/* Exclusive offsets of each thread's bytes inside its bin, over the whole CTA: warp scans per bin, per-warp
+ * totals in wt[warp][8] (slot 6 = raw input bytes), one barrier, then the prefix over the warps before. */
+__device__ uint32_t dev_scan_bins(uint32_t bin, uint32_t bytes, uint32_t raw, uint32_t *wt)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t mine = 0;
+#pragma unroll
+    for (uint32_t b = 0; b < 6; ++b) {
+        const uint32_t v = bin == b ? bytes : 0u;
+        uint32_t x = 0;
+        if (__any_sync(0xffffffffu, v != 0u)) {
+            x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (bin == b) mine = x - v;
         }
-        scr[32 + lane] = s - w;
+        if (lane == 31) wt[warp * 8 + b] = x;
+    }
+    const uint32_t r = __reduce_add_sync(0xffffffffu, raw);
+    if (lane == 31) { wt[warp * 8 + 6] = r; wt[warp * 8 + 7] = 0; }
+    __syncthreads();
+    if (bin < 6u)
+        for (int w = 0; w < warp; ++w) mine += wt[w * 8 + bin];
+    return mine;
+}
+/* the CTA's totals per slot, 64-bit; called by warp 0 after dev_scan_bins */
+__device__ void dev_bin_totals(const uint32_t *wt, unsigned long long *tot)
+{
+    const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane < C2_SLOTS) {
+        unsigned long long t = 0;
+        for (int w = 0; w < nw; ++w) t += wt[w * 8 + lane];
+        tot[lane] = t;
+    }
+    __syncwarp();
+}
+
+/* warp-aggregated histogram increment: one shared-memory atomic per distinct key in the warp */
+__device__ void dev_hist_add(uint32_t *hist, uint32_t key)
+{
+    if (__all_sync(0xffffffffu, key >= 36u)) return;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key < 36u && (int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+}
+
+/* ---- window staging: one TMA bulk copy per tile -------------------------------- */
+__device__ void dev_stage_window(uint8_t *win, const uint8_t *src, uint32_t bytes, unsigned long long *mbar)
+{
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    total = scr[32 + nw - 1] + scr[nw - 1];
-    return scr[32 + warp] + x - v;
-}
-
-__device__ uint32_t dev_block_min(uint32_t v, uint32_t *scr)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    uint32_t x = __reduce_min_sync(0xffffffffu, v);
-    __syncthreads();
-    if (lane == 0) scr[warp] = x;
-    __syncthreads();
-    uint32_t w = lane < nw ? scr[lane] : 0xffffffffu;
-    return __reduce_min_sync(0xffffffffu, w);
-}
-
-__device__ uint32_t dev_block_or(uint32_t v, uint32_t *scr)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    uint32_t x = __reduce_or_sync(0xffffffffu, v);
-    __syncthreads();
-    if (lane == 0) scr[warp] = x;
-    __syncthreads();
-    uint32_t w = lane < nw ? scr[lane] : 0u;
-    return __reduce_or_sync(0xffffffffu, w);
+    if (threadIdx.x == 0) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(win);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+    }
 }
 
 /* ---- look-back chains ------------------------------------------------------ */
@@ -99,32 +157,48 @@ __device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v)
 /*
  * Chain 1: records per tile plus a stop flag (a blank line ends the stream).
  * One 64-bit word per tile carries status, flag and count, so a single store
- * publishes it.  The fold is "the oldest stop wins": counts add up to and
- * including the first tile that stops.  Called by warp 0.
+ * publishes it and a single load reads it.  The fold is "the oldest stop
+ * wins": counts add up to and including the first tile that stops.
+ * A tile publishes its own count as early as it knows it (dev_publish1) and
+ * resolves its exclusive prefix later (dev_resolve1, warp 0): 256 predecessor
+ * descriptors are fetched per round trip, so a whole wave of concurrently
+ * running tiles is crossed in two or three steps.
  */
-__device__ void dev_lookback1(unsigned long long *desc, uint32_t tile, unsigned long long agg_count, bool agg_stop,
-                              unsigned long long *out)
+__device__ void dev_publish1(unsigned long long *desc, uint32_t tile, unsigned long long agg_count, bool agg_stop)
+{
+    st_volatile64(desc + tile, C1_AGG | (agg_stop ? C1_STOP : 0ull) | agg_count);
+}
+
+__device__ void dev_resolve1(unsigned long long *desc, uint32_t tile, unsigned long long agg_count, bool agg_stop,
+                             unsigned long long *out)
 {
     const int lane = threadIdx.x & 31;
-    if (lane == 0) st_volatile64(desc + tile, C1_AGG | (agg_stop ? C1_STOP : 0ull) | agg_count);
     unsigned long long ex_count = 0;
-    bool ex_stop = false;
-    for (long long j = (long long)tile - 1; j >= 0; j -= 32) {
-        const long long idx = j - lane;
-        unsigned long long d = C1_INC;                       /* before the first tile: inclusive zero */
-        if (idx >= 0) {
-            do { d = ld_volatile64(desc + idx); } while ((d >> 62) == 0);
+    bool ex_stop = false, done = false;
+    for (long long j = (long long)tile - 1; j >= 0 && !done; j -= 256) {
+        unsigned long long d[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const long long idx = j - 32 * q - lane;
+            d[q] = idx >= 0 ? ld_volatile64(desc + idx) : C1_INC;      /* before the first tile: inclusive zero */
         }
-        const unsigned incmask = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-        const int L = incmask ? __ffs((int)incmask) - 1 : 31;  /* nearest inclusive prefix */
-        const bool part = lane <= L;
-        const unsigned stopmask = __ballot_sync(0xffffffffu, part && (d & C1_STOP));
-        const int M = stopmask ? 31 - __clz((int)stopmask) : -1;   /* oldest stopping tile in the window */
-        unsigned long long c = (part && lane >= (M >= 0 ? M : 0)) ? (d & C1_COUNT) : 0ull;
-        c = warp_sum64(c);
-        if (M >= 0) { ex_count = c; ex_stop = true; }       /* everything nearer than a stop is dropped */
-        else ex_count += c;
-        if (incmask) break;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (done) break;
+            const long long idx = j - 32 * q - lane;
+            if (idx >= 0)
+                while ((d[q] >> 62) == 0) d[q] = ld_volatile64(desc + idx);
+            const unsigned incmask = __ballot_sync(0xffffffffu, (d[q] >> 62) == 2);
+            const int L = incmask ? __ffs((int)incmask) - 1 : 31;  /* nearest inclusive prefix */
+            const bool part = lane <= L;
+            const unsigned stopmask = __ballot_sync(0xffffffffu, part && (d[q] & C1_STOP));
+            const int M = stopmask ? 31 - __clz((int)stopmask) : -1;   /* oldest stopping tile in the window */
+            unsigned long long c = (part && lane >= (M >= 0 ? M : 0)) ? (d[q] & C1_COUNT) : 0ull;
+            c = warp_sum64(c);
+            if (M >= 0) { ex_count = c; ex_stop = true; }       /* everything nearer than a stop is dropped */
+            else ex_count += c;
+            if (incmask) done = true;
+        }
     }
     if (lane == 0) {
         out[0] = ex_count;
@@ -134,50 +208,48 @@ __device__ void dev_lookback1(unsigned long long *desc, uint32_t tile, unsigned 
 }
 
 /*
- * Chain 2: bytes per output bin (six) + raw primary bytes.  Values first,
- * fence, then the flag.  Called by warp 0 with totals in tot[0..7]; returns
- * the exclusive bases in the same array.
+ * Chain 2: bytes per output bin.  Six independent chains share one 64-byte
+ * row per tile; every word carries its own status, so rows need no fence and
+ * no separate flag.  Called by warp 0.
  */
-__device__ void dev_lookback2(uint32_t *flag, unsigned long long *agg, unsigned long long *inc, uint32_t tile,
-                              unsigned long long *tot)
+__device__ void dev_publish2(unsigned long long *chain, uint32_t tile, const unsigned long long *tot)
 {
     const int lane = threadIdx.x & 31;
-    unsigned long long mine = lane < C2_SLOTS ? tot[lane] : 0ull;
-    if (lane < C2_SLOTS) agg[(size_t)tile * C2_SLOTS + lane] = mine;
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) st_volatile32(flag + tile, 1u);
-    unsigned long long acc[C2_SLOTS];
+    if (lane < 6) st_volatile64(chain + (size_t)tile * C2_SLOTS + lane, C2_AGG | tot[lane]);
+}
+
+__device__ void dev_resolve2(unsigned long long *chain, uint32_t tile, unsigned long long *tot)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long acc[6];
 #pragma unroll
-    for (int b = 0; b < C2_SLOTS; ++b) acc[b] = 0;
-    for (long long j = (long long)tile - 1; j >= 0; j -= 32) {
+    for (int b = 0; b < 6; ++b) acc[b] = 0;
+    unsigned pending = 0x3fu;                              /* bins still looking for an inclusive prefix */
+    for (long long j = (long long)tile - 1; j >= 0 && pending; j -= 32) {
         const long long idx = j - lane;
-        uint32_t f = 2u;
-        if (idx >= 0) {
-            do { f = ld_volatile32(flag + idx); } while (f == 0u);
-        }
-        __threadfence();
-        const unsigned incmask = __ballot_sync(0xffffffffu, f == 2u);
-        const int L = incmask ? __ffs((int)incmask) - 1 : 31;
-        const bool part = lane <= L && idx >= 0;
-        const unsigned long long *src = (f == 2u ? inc : agg) + (size_t)(idx >= 0 ? idx : 0) * C2_SLOTS;
+        const unsigned long long *row = chain + (size_t)(idx >= 0 ? idx : 0) * C2_SLOTS;
+        unsigned long long d[6];
 #pragma unroll
-        for (int b = 0; b < C2_SLOTS; ++b) {
-            unsigned long long v = part ? ld_volatile64(src + b) : 0ull;
-            acc[b] += warp_sum64(v);
+        for (int b = 0; b < 6; ++b) d[b] = idx >= 0 ? ld_volatile64(row + b) : C2_INC;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            if (!((pending >> b) & 1u)) continue;
+            if (idx >= 0)
+                while ((d[b] >> 62) == 0) d[b] = ld_volatile64(row + b);
+            const unsigned incmask = __ballot_sync(0xffffffffu, (d[b] >> 62) == 2);
+            const int L = incmask ? __ffs((int)incmask) - 1 : 31;
+            acc[b] += warp_sum64(lane <= L ? (d[b] & C2_VAL) : 0ull);
+            if (incmask) pending &= ~(1u << b);
         }
-        if (incmask) break;
     }
     unsigned long long ex = 0;
 #pragma unroll
-    for (int b = 0; b < C2_SLOTS; ++b) if (lane == b) ex = acc[b];
-    if (lane < C2_SLOTS) {
-        inc[(size_t)tile * C2_SLOTS + lane] = ex + mine;
+    for (int b = 0; b < 6; ++b) if (lane == b) ex = acc[b];
+    if (lane < 6) {
+        st_volatile64(chain + (size_t)tile * C2_SLOTS + lane, C2_INC | (ex + tot[lane]));
         tot[lane] = ex;
     }
-    __threadfence();
     __syncwarp();
-    if (lane == 0) st_volatile32(flag + tile, 2u);
 }
 
 /* ---- warp copy engine ------------------------------------------------------- */
@@ -232,31 +304,62 @@ __device__ void dev_warp_copy(uint8_t *dst, const uint8_t *src_smem, const uint8
     if ((uint32_t)lane < tail) d[16u * nchunk + lane] = s[16u * nchunk + lane];
 }
 
+/*
+ * Copies len bytes from the staged window to an arbitrarily aligned global destination: unaligned head and
+ * tail bytes by single lanes, the 16-byte aligned body as vector stores assembled from two aligned shared-memory
+ * vectors with funnel shifts (the shift is the same for the whole piece).  Called by a full warp.
+ */
+__device__ void dev_copy_piece(uint8_t *dst, const uint8_t *win, uint32_t src_off, uint32_t len)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+    if (head > len) head = len;
+    const uint32_t rest = len - head, nchunk = rest >> 4, tail = rest & 15u;
+    const uint32_t so = src_off + head;
+    const uint32_t u = so & 15u;
+    const uint8_t *sa = win + (so - u);
+    uint8_t *body = dst + head;
+    if (lane < head) dst[lane] = win[src_off + lane];
+    if (lane < tail) body[16u * nchunk + lane] = win[so + 16u * nchunk + lane];
+    const uint32_t bsh = (u & 3u) * 8u;
+    if (u == 0) {
+        for (uint32_t c = lane; c < nchunk; c += 32u)
+            __stcs((uint4 *)(body + 16u * c), *(const uint4 *)(sa + 16u * c));
+        return;
+    }
+    for (uint32_t c = lane; c < nchunk; c += 32u) {
+        const uint4 q0 = *(const uint4 *)(sa + 16u * c);
+        const uint4 q1 = *(const uint4 *)(sa + 16u * c + 16u);
+        uint4 o;
+        switch (u >> 2) {
+        case 0: o.x = __funnelshift_r(q0.x, q0.y, bsh); o.y = __funnelshift_r(q0.y, q0.z, bsh); o.z = __funnelshift_r(q0.z, q0.w, bsh); o.w = __funnelshift_r(q0.w, q1.x, bsh); break;
+        case 1: o.x = __funnelshift_r(q0.y, q0.z, bsh); o.y = __funnelshift_r(q0.z, q0.w, bsh); o.z = __funnelshift_r(q0.w, q1.x, bsh); o.w = __funnelshift_r(q1.x, q1.y, bsh); break;
+        case 2: o.x = __funnelshift_r(q0.z, q0.w, bsh); o.y = __funnelshift_r(q0.w, q1.x, bsh); o.z = __funnelshift_r(q1.x, q1.y, bsh); o.w = __funnelshift_r(q1.y, q1.z, bsh); break;
+        default: o.x = __funnelshift_r(q0.w, q1.x, bsh); o.y = __funnelshift_r(q1.x, q1.y, bsh); o.z = __funnelshift_r(q1.y, q1.z, bsh); o.w = __funnelshift_r(q1.z, q1.w, bsh); break;
+        }
+        __stcs((uint4 *)(body + 16u * c), o);
+    }
+}
+
 /* ---- kernels ------------------------------------------------------------------ */
 template <class C>
-__global__ void __launch_bounds__(C::THREADS) k_scan(const ScanArgs a)
+__global__ void __launch_bounds__(C::THREADS, 4) k_scan(const ScanArgs a)
 {
     extern __shared__ uint4 xm_smem[];
-    __shared__ uint32_t s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&a.g->ticket[a.stream_id], 1u);
-    __syncthreads();
     TileCtx<C> T;
     T.m = carve<C>(xm_smem);
     T.emu = nullptr;
-    scan_tile<C>(T, a, s_tile);
+    scan_tile<C>(T, a, blockIdx.x);
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::THREADS) k_classify(const ClassifyArgs a)
+__global__ void __launch_bounds__(C::THREADS, 4) k_classify(const ClassifyArgs a)
 {
     extern __shared__ uint4 xm_smem[];
-    __shared__ uint32_t s_tile;
-    if (threadIdx.x == 0) s_tile = atomicAdd(&a.g->ticket[0], 1u);
-    __syncthreads();
     TileCtx<C> T;
     T.m = carve<C>(xm_smem);
     T.emu = nullptr;
-    classify_tile<C>(T, a, s_tile);
+    classify_tile<C>(T, a, blockIdx.x);
 }
 
 /* ---- launchers ------------------------------------------------------------------ */

@@ -84,6 +84,37 @@ XM_HD uint32_t eq_mask(uint32_t w, uint32_t pat)
 /* gather the four bit-7 flags of a word into a nibble (byte 0 -> bit 0) */
 XM_HD uint32_t pack4(uint32_t z) { return umulhi32(z, 0x02040810u) & 0xfu; }
 
+/* 4 x u8 dot product with accumulate (IDP4A on the device) */
+XM_HD uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c)
+{
+#if XM_DEVICE_PASS
+    return __dp4a(a, b, c);
+#else
+    for (int k = 0; k < 4; ++k) c += ((a >> (8 * k)) & 0xffu) * ((b >> (8 * k)) & 0xffu);
+    return c;
+#endif
+}
+/* sixteen bit-7 byte flags (four words) -> 16 mask bits, byte 0 of z0 -> bit 0 */
+XM_HD uint32_t pack16(uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3)
+{
+    const uint32_t lo = dp4a_u(z1, 0x80402010u, dp4a_u(z0, 0x08040201u, 0u));   /* 128 * bits 0..7 */
+    const uint32_t hi = dp4a_u(z3, 0x80402010u, dp4a_u(z2, 0x08040201u, 0u));   /* 128 * bits 8..15 */
+    return (lo + (hi << 8)) >> 7;
+}
+/* the two byte-class masks of 16 staged bytes: W = byte < 0x21 or >= 0x80, T = byte == '\t' */
+XM_HD void masks16(const uint4 v, uint32_t &W, uint32_t &T)
+{
+    W = pack16(ctrl_mask(v.x), ctrl_mask(v.y), ctrl_mask(v.z), ctrl_mask(v.w));
+    T = pack16(eq_mask(v.x, 0x09090909u), eq_mask(v.y, 0x09090909u), eq_mask(v.z, 0x09090909u), eq_mask(v.w, 0x09090909u));
+}
+/* exact newline mask of 16 staged bytes (tiles whose W & ~T bytes are not all '\n') */
+XM_HD uint32_t newlines16(const uint4 v)
+{
+    return pack16(eq_mask(v.x, 0x0a0a0a0au), eq_mask(v.y, 0x0a0a0a0au), eq_mask(v.z, 0x0a0a0a0au), eq_mask(v.w, 0x0a0a0a0au));
+}
+
+XM_HD bool is_w_byte(uint32_t c) { return c < 0x21u || c >= 0x80u; }
+
 XM_HD bool is_ascii_space(uint8_t c) { return c == ' ' || (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x1f); }
 
 /* ---- QNAME hash: 2 x 32-bit lanes over little-endian words ------------ */
@@ -93,12 +124,9 @@ struct Hash2 {
 XM_HD void hash_init(Hash2 &h) { h.a = 0x243f6a88u; h.b = 0x85a308d3u; }
 XM_HD void hash_word(Hash2 &h, uint32_t w)
 {
-    uint32_t k = w * 0xcc9e2d51u;
-    k = rotl32(k, 15) * 0x1b873593u;
-    h.a = rotl32(h.a ^ k, 13) * 5u + 0xe6546b64u;
-    uint32_t j = w * 0x85ebca6bu;
-    j = rotl32(j, 13) * 0xc2b2ae35u;
-    h.b = rotl32(h.b ^ j, 17) * 9u + 0x52dce729u;
+    /* two multiply-add lanes with unrelated odd multipliers; fmix32 in hash_final spreads the bits */
+    h.a = h.a * 0x9e3779b1u + w;
+    h.b = (h.b ^ w) * 0x85ebca6bu;
 }
 XM_HD uint32_t fmix32(uint32_t x)
 {
@@ -285,26 +313,44 @@ XM_HD void generic_parse(const Reader &rd, uint64_t gs, int score_src, LineRec &
 /* masks of the staged window, one bit per byte */
 struct WinMasks {
     const uint8_t *win;
-    const uint32_t *wsm;   /* ctrl_mask bits */
-    const uint32_t *nlm;   /* '\n' bits (plus a virtual one at EOF when the last line is unterminated) */
-    int nbits;             /* mask bits that are meaningful */
-    int virt;              /* position of the virtual newline, -1 if none */
+    const uint32_t *tbm;   /* T: byte == '\t' */
+    const uint32_t *nlm;   /* N: line terminator candidates, W & ~T (W = byte < 0x21 or >= 0x80) */
+    const uint16_t *trk;   /* tabs in the window before each mask word */
+    uint32_t wbytes;       /* staged data bytes */
+    bool adj;              /* somewhere in the window a W byte directly follows another W byte */
+    XM_HD uint32_t wsm(int w) const { return tbm[w] | nlm[w]; }
 };
 
-/* position after the nearest separator bit strictly below q (q is inside a token past `floor`) */
-XM_HD int token_start(const uint32_t *wsm, int q)
+XM_HD uint32_t tabs_before(const WinMasks &M, int p)
+{
+    const int w = p >> 5;
+    return (uint32_t)M.trk[w] + (uint32_t)popc32(M.tbm[w] & ((1u << (p & 31)) - 1u));
+}
+/* window position of the tab with window rank r, known to lie in mask words [wlo, whi] */
+XM_HD int tab_select(const WinMasks &M, uint32_t r, int wlo, int whi)
+{
+    while (whi > wlo) {                 /* largest word whose rank is <= r */
+        const int mid = (wlo + whi + 1) >> 1;
+        if ((uint32_t)M.trk[mid] <= r) wlo = mid; else whi = mid - 1;
+    }
+    uint32_t bits = M.tbm[wlo];
+    for (uint32_t k = r - (uint32_t)M.trk[wlo]; k; --k) bits &= bits - 1;
+    return (wlo << 5) + ffs32(bits) - 1;
+}
+/* start of the token that holds position q: the byte after the nearest separator below q */
+XM_HD int token_start(const WinMasks &M, int q)
 {
     int w = q >> 5;
-    uint32_t m = wsm[w] & ((1u << (q & 31)) - 1u);
-    while (!m) m = wsm[--w];
+    uint32_t m = M.wsm(w) & ((1u << (q & 31)) - 1u);
+    while (!m) { --w; m = M.wsm(w); }
     return (w << 5) + 32 - clz32(m);
 }
-/* first separator bit at or above q (the line's newline bounds the search) */
-XM_HD int token_end(const uint32_t *wsm, int q)
+/* first separator bit at or above q (the line's terminator bounds the search) */
+XM_HD int token_end(const WinMasks &M, int q)
 {
     int w = q >> 5;
-    uint32_t m = wsm[w] & (0xffffffffu << (q & 31));
-    while (!m) m = wsm[++w];
+    uint32_t m = M.wsm(w) & (0xffffffffu << (q & 31));
+    while (!m) { ++w; m = M.wsm(w); }
     return (w << 5) + ffs32(m) - 1;
 }
 /* plain integer after the last ':' of the token [ts, te) */
@@ -318,54 +364,50 @@ XM_HD bool token_value(const uint8_t *win, int ts, int te, int32_t &out)
 }
 
 /*
- * Fast path for a clean line that lies inside the staged window: separators
- * come from the bitmasks, the aux region is scanned a word at a time.
- * Returns false (and leaves L untouched) whenever the line needs the exact
- * path: any control byte other than single tabs, CR, non-ASCII, unterminated
- * or extending past the window.
+ * Fast path for the line [s, e) whose terminator candidate sits at window
+ * position e (the first N bit at or after s, taken from the line index).
+ * By construction every separator inside [s, e) is a tab; the line is clean --
+ * its output equals its raw bytes -- when in addition the terminator is a real
+ * '\n' inside the staged data and no two W bytes touch anywhere in [s-1, e]
+ * (no empty token, no leading or trailing tab, not a blank line).
+ *
+ * fast_head does those checks and the QNAME (length, hash); it returns false
+ * (L untouched) whenever the line needs the exact byte-wise path.  fast_tail
+ * finishes the line: the aux tokens and the scores.  They are separate so that
+ * a run-skipping walk can rank its records between the two.
  */
-XM_HD bool fast_parse(const WinMasks &M, int s, int score_src, LineRec &L)
+struct FastCtx {
+    uint32_t r0, ntab;     /* tabs before the line's first byte, tabs inside the line */
+};
+
+XM_HD bool fast_head(const WinMasks &M, int s, int e, LineRec &L, FastCtx &fc)
 {
     const uint8_t *win = M.win;
     const uint32_t *w32 = (const uint32_t *)win;
-    /* line end */
-    int wi = s >> 5;
-    const int nwords = (M.nbits + 31) >> 5;
-    uint32_t m = M.nlm[wi] & (0xffffffffu << (s & 31));
-    while (!m) {
-        if (++wi >= nwords) return false;
-        m = M.nlm[wi];
-    }
-    const int e = (wi << 5) + ffs32(m) - 1;
-    if (e >= M.nbits || e == M.virt) return false;
-    if (e == s) {   /* empty line */
-        L.s = (uint32_t)s; L.rawbytes = 1; L.outlen = 0; L.qs = (uint32_t)s; L.qlen = 0;
-        L.h1 = L.h2 = 0; L.flags = F_BLANK; L.as = L.xs = SCORE_ABSENT;
-        return true;
-    }
-    /* separators: all single tabs, none leading or trailing */
-    int nsep = 0, prev = s - 1, sep0 = e, sep4 = -1, sep5 = -1, sep10 = -1;
-    uint32_t bad = 0;
-    const int w0 = s >> 5, w1 = (e - 1) >> 5;
-    for (int w = w0; w <= w1; ++w) {
-        uint32_t mm = M.wsm[w];
-        if (w == w0) mm &= 0xffffffffu << (s & 31);
-        if (w == w1) mm &= 0xffffffffu >> (31 - ((e - 1) & 31));
-        while (mm) {
-            int p = (w << 5) + ffs32(mm) - 1;
-            mm &= mm - 1;
-            bad |= (uint32_t)(win[p] != '\t') | (uint32_t)(p == prev + 1);
-            prev = p;
-            if (nsep == 0) sep0 = p;
-            else if (nsep == 4) sep4 = p;
-            else if (nsep == 5) sep5 = p;
-            else if (nsep == 10) sep10 = p;
-            ++nsep;
+    if ((uint32_t)e >= M.wbytes || e <= s || win[e] != '\n') return false;
+    if (s == 0 && (M.wsm(0) & 1u)) return false;            /* the stream opens with a separator */
+    const int w0 = s >> 5, w1 = e >> 5;
+    if (M.adj) {
+        for (int w = w0; w <= w1; ++w) {
+            const uint32_t x = M.wsm(w);
+            uint32_t a = x & ((x << 1) | (w ? M.wsm(w - 1) >> 31 : 0u));
+            if (w == w0) a &= 0xffffffffu << (s & 31);
+            if (w == w1) a &= 0xffffffffu >> (31 - (e & 31));
+            if (a) return false;
         }
     }
-    bad |= (uint32_t)(prev == e - 1);
-    if (bad) return false;
-    /* QNAME hash over [s, sep0) */
+    const uint32_t outlen = (uint32_t)(e - s) + 1u;
+    if (outlen > META_LEN_MASK) return false;
+    fc.r0 = tabs_before(M, s);
+    fc.ntab = tabs_before(M, e) - fc.r0;
+    /* QNAME = [s, first tab) */
+    int sep0 = e;
+    if (fc.ntab) {
+        int w = w0;
+        uint32_t m = M.tbm[w] & (0xffffffffu << (s & 31));
+        while (!m) m = M.tbm[++w];
+        sep0 = (w << 5) + ffs32(m) - 1;
+    }
     const int qlen = sep0 - s;
     Hash2 h; hash_init(h);
     {
@@ -374,7 +416,7 @@ XM_HD bool fast_parse(const WinMasks &M, int s, int score_src, LineRec &L)
         const int nw = (qlen + 3) >> 2;
         uint32_t lo = w32[base];
         for (int k = 0; k < nw; ++k) {
-            uint32_t hi = w32[base + k + 1];
+            const uint32_t hi = w32[base + k + 1];
             uint32_t w = funnel_r(lo, hi, sh);
             lo = hi;
             if (k == nw - 1 && (qlen & 3)) w &= (1u << (8 * (qlen & 3))) - 1u;
@@ -382,62 +424,68 @@ XM_HD bool fast_parse(const WinMasks &M, int s, int score_src, LineRec &L)
         }
     }
     hash_final(h, (uint32_t)qlen);
+    L.s = (uint32_t)s; L.rawbytes = outlen; L.outlen = outlen;
+    L.qs = (uint32_t)s; L.qlen = (uint32_t)qlen;
+    L.h1 = h.a; L.h2 = h.b; L.flags = 0; L.as = SCORE_ABSENT; L.xs = SCORE_ABSENT;
+    return true;
+}
+
+XM_HD void fast_tail(const WinMasks &M, int s, int e, int score_src, const FastCtx &fc, LineRec &L)
+{
+    if (fc.ntab < 11) return;           /* no token with index >= 11: both scores absent (xm.py:186-188) */
+    const uint8_t *win = M.win;
+    const uint32_t *w32 = (const uint32_t *)win;
+    const int w0 = s >> 5, w1 = e >> 5;
     /* aux tokens (index >= 11): look for the tag letters a word at a time */
     uint32_t flags = 0;
     int32_t as = SCORE_ABSENT, xs = SCORE_ABSENT;
-    if (nsep >= 11) {
-        const bool cigar = score_src == SCORE_CIGAR_NM;
-        const uint32_t xsch = score_src == SCORE_AS_ZS ? 'Z' : 'X';
-        const int a = sep10 + 1;
-        int as_ts = -1, xs_ts = -1, nm_ts = -1;
-        uint32_t as_cnt = 0, xs_cnt = 0;
-        const int k0 = a >> 2, k1 = (e - 1) >> 2;
-        for (int k = k0; k <= k1; ++k) {
-            uint32_t w = w32[k];
-            uint32_t z = eq_mask(w, 0x53535353u);                 /* 'S' */
-            if (cigar) z |= eq_mask(w, 0x4d4d4d4du);              /* 'M' */
-            if (k == k0) z &= 0xffffffffu << (8 * (a & 3));
-            if (k == k1) z &= 0xffffffffu >> (8 * (3 - ((e - 1) & 3)));
-            while (z) {
-                int p = (k << 2) + ((ffs32(z) - 1) >> 3);
-                z &= z - 1;
-                if (p <= a) continue;
-                uint32_t c1 = win[p], c0 = win[p - 1];
-                if (c1 == 'S') {
-                    if (c0 == 'A' && !cigar) {
-                        int ts = token_start(M.wsm, p - 1);
-                        if (as_cnt == 0) { as_ts = ts; as_cnt = 1; } else if (ts != as_ts) as_cnt = 2;
-                    }
-                    if (c0 == xsch) {
-                        int ts = token_start(M.wsm, p - 1);
-                        if (xs_cnt == 0) { xs_ts = ts; xs_cnt = 1; } else if (ts != xs_ts) xs_cnt = 2;
-                    }
-                } else if (c0 == 'N' && nm_ts < 0) {
-                    nm_ts = token_start(M.wsm, p - 1);
+    const bool cigar = score_src == SCORE_CIGAR_NM;
+    const uint32_t xsch = score_src == SCORE_AS_ZS ? 'Z' : 'X';
+    const int a = tab_select(M, fc.r0 + 10, w0, w1) + 1;
+    int as_ts = -1, xs_ts = -1, nm_ts = -1;
+    uint32_t as_cnt = 0, xs_cnt = 0;
+    const int k0 = a >> 2, k1 = (e - 1) >> 2;
+    for (int k = k0; k <= k1; ++k) {
+        const uint32_t w = w32[k];
+        uint32_t z = eq_mask(w, 0x53535353u);                 /* 'S' */
+        if (cigar) z |= eq_mask(w, 0x4d4d4d4du);              /* 'M' */
+        if (k == k0) z &= 0xffffffffu << (8 * (a & 3));
+        if (k == k1) z &= 0xffffffffu >> (8 * (3 - ((e - 1) & 3)));
+        while (z) {
+            const int p = (k << 2) + ((ffs32(z) - 1) >> 3);
+            z &= z - 1;
+            if (p <= a) continue;
+            const uint32_t c1 = win[p], c0 = win[p - 1];
+            if (c1 == 'S') {
+                if (c0 == 'A' && !cigar) {
+                    const int ts = token_start(M, p - 1);
+                    if (as_cnt == 0) { as_ts = ts; as_cnt = 1; } else if (ts != as_ts) as_cnt = 2;
                 }
+                if (c0 == xsch) {
+                    const int ts = token_start(M, p - 1);
+                    if (xs_cnt == 0) { xs_ts = ts; xs_cnt = 1; } else if (ts != xs_ts) xs_cnt = 2;
+                }
+            } else if (c0 == 'N' && nm_ts < 0) {
+                nm_ts = token_start(M, p - 1);
             }
         }
-        if (cigar) {
-            if (nm_ts >= 0) {
-                int32_t mm;
-                bool ok = token_value(win, nm_ts, token_end(M.wsm, nm_ts), mm);
-                CigSt cg; cig_reset(cg);
-                for (int p = sep4 + 1; p < sep5; ++p) cig_feed(cg, win[p]);
-                if (!ok || !cig_score(cg, mm, as)) { flags |= F_AS_NUM; as = SCORE_ABSENT; }
-            }
-        } else if (as_cnt == 1) {
-            if (!token_value(win, as_ts, token_end(M.wsm, as_ts), as)) { flags |= F_AS_NUM; as = SCORE_ABSENT; }
-        } else if (as_cnt > 1) flags |= F_AS_DUP;
-        if (xs_cnt == 1) {
-            if (!token_value(win, xs_ts, token_end(M.wsm, xs_ts), xs)) { flags |= F_XS_NUM; xs = SCORE_ABSENT; }
-        } else if (xs_cnt > 1) flags |= F_XS_DUP;
     }
-    const uint32_t outlen = (uint32_t)(e - s) + 1u;
-    if (outlen > META_LEN_MASK) return false;
-    L.s = (uint32_t)s; L.rawbytes = outlen; L.outlen = outlen;
-    L.qs = (uint32_t)s; L.qlen = (uint32_t)qlen;
-    L.h1 = h.a; L.h2 = h.b; L.flags = flags; L.as = as; L.xs = xs;
-    return true;
+    if (cigar) {
+        if (nm_ts >= 0) {
+            int32_t mm;
+            const bool ok = token_value(win, nm_ts, token_end(M, nm_ts), mm);
+            const int sep4 = tab_select(M, fc.r0 + 4, w0, w1), sep5 = tab_select(M, fc.r0 + 5, w0, w1);
+            CigSt cg; cig_reset(cg);
+            for (int p = sep4 + 1; p < sep5; ++p) cig_feed(cg, win[p]);
+            if (!ok || !cig_score(cg, mm, as)) { flags |= F_AS_NUM; as = SCORE_ABSENT; }
+        }
+    } else if (as_cnt == 1) {
+        if (!token_value(win, as_ts, token_end(M, as_ts), as)) { flags |= F_AS_NUM; as = SCORE_ABSENT; }
+    } else if (as_cnt > 1) flags |= F_AS_DUP;
+    if (xs_cnt == 1) {
+        if (!token_value(win, xs_ts, token_end(M, xs_ts), xs)) { flags |= F_XS_NUM; xs = SCORE_ABSENT; }
+    } else if (xs_cnt > 1) flags |= F_XS_DUP;
+    L.flags = flags; L.as = as; L.xs = xs;
 }
 
 /* exact QNAME comparison of two tokens given by global offsets */

@@ -145,10 +145,9 @@ inline int diagnose_number(const std::string &line, int score_src, bool want_xs)
 
 /* ---- scratch --------------------------------------------------------------- */
 struct Scratch {
-    unsigned long long *chain1_s = nullptr, *chain1_p = nullptr, *c2_agg = nullptr, *c2_inc = nullptr;
-    uint32_t *c2_flag = nullptr;
+    unsigned long long *chain1_s = nullptr, *chain1_p = nullptr, *chain2 = nullptr;
     uint64_t cap_tiles_s = 0, cap_tiles_p = 0;
-    SCompact sc{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    SCompact sc{nullptr, nullptr, nullptr};
     uint64_t sc_cap = 0;
     Globals *g = nullptr;
 };
@@ -156,8 +155,8 @@ struct Scratch {
 template <class BE>
 inline void scratch_release(BE &be, Scratch &s)
 {
-    be.release(s.chain1_s); be.release(s.chain1_p); be.release(s.c2_agg); be.release(s.c2_inc); be.release(s.c2_flag);
-    be.release(s.sc.start); be.release(s.sc.as); be.release(s.sc.xs); be.release(s.sc.h1); be.release(s.sc.h2); be.release(s.sc.meta);
+    be.release(s.chain1_s); be.release(s.chain1_p); be.release(s.chain2);
+    be.release(s.sc.start); be.release(s.sc.rec); be.release(s.sc.meta);
     be.release(s.g);
     s = Scratch();
 }
@@ -173,23 +172,18 @@ inline bool scratch_reserve(BE &be, Scratch &s, uint64_t tiles_s, uint64_t tiles
         s.cap_tiles_s = tiles_s;
     }
     if (tiles_p > s.cap_tiles_p) {
-        be.release(s.chain1_p); be.release(s.c2_agg); be.release(s.c2_inc); be.release(s.c2_flag);
+        be.release(s.chain1_p); be.release(s.chain2);
         s.chain1_p = (unsigned long long *)be.alloc(tiles_p * 8);
-        s.c2_agg = (unsigned long long *)be.alloc(tiles_p * 8 * C2_SLOTS);
-        s.c2_inc = (unsigned long long *)be.alloc(tiles_p * 8 * C2_SLOTS);
-        s.c2_flag = (uint32_t *)be.alloc(tiles_p * 4);
-        if (!s.chain1_p || !s.c2_agg || !s.c2_inc || !s.c2_flag) return false;
+        s.chain2 = (unsigned long long *)be.alloc(tiles_p * 8 * C2_SLOTS);
+        if (!s.chain1_p || !s.chain2) return false;
         s.cap_tiles_p = tiles_p;
     }
     if (sc_cap > s.sc_cap) {
-        be.release(s.sc.start); be.release(s.sc.as); be.release(s.sc.xs); be.release(s.sc.h1); be.release(s.sc.h2); be.release(s.sc.meta);
+        be.release(s.sc.start); be.release(s.sc.rec); be.release(s.sc.meta);
         s.sc.start = (uint64_t *)be.alloc((sc_cap + 1) * 8);
-        s.sc.as = (int32_t *)be.alloc(sc_cap * 4 + 16);
-        s.sc.xs = (int32_t *)be.alloc(sc_cap * 4 + 16);
-        s.sc.h1 = (uint32_t *)be.alloc(sc_cap * 4 + 16);
-        s.sc.h2 = (uint32_t *)be.alloc(sc_cap * 4 + 16);
+        s.sc.rec = (uint4 *)be.alloc(sc_cap * 16 + 16);
         s.sc.meta = (uint32_t *)be.alloc(sc_cap * 4 + 16);
-        if (!s.sc.start || !s.sc.as || !s.sc.xs || !s.sc.h1 || !s.sc.h2 || !s.sc.meta) { s.sc_cap = 0; return false; }
+        if (!s.sc.start || !s.sc.rec || !s.sc.meta) { s.sc_cap = 0; return false; }
         s.sc_cap = sc_cap;
     }
     return true;
@@ -275,7 +269,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         init.limit_off = ~0ull;
         be.tick(0);                                  /* the step starts here: scratch init is part of it */
         if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_s * 8) || be.zero(sc.chain1_p, nt_p * 8) ||
-            be.zero(sc.c2_flag, nt_p * 4)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
+            be.zero(sc.chain2, nt_p * 8 * C2_SLOTS)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
 
         ScanArgs sa;
         memset(&sa, 0, sizeof sa);
@@ -283,7 +277,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         sa.score_src = o.score_src; sa.skip = o.skip_repeated ? 1 : 0; sa.stream_id = 1; sa.debug = debug;
         ClassifyArgs ca;
         memset(&ca, 0, sizeof ca);
-        ca.P = P; ca.S = S; ca.sc = sc.sc; ca.chain1 = sc.chain1_p; ca.c2_flag = sc.c2_flag; ca.c2_agg = sc.c2_agg; ca.c2_inc = sc.c2_inc;
+        ca.P = P; ca.S = S; ca.sc = sc.sc; ca.chain1 = sc.chain1_p; ca.chain2 = sc.chain2;
         ca.g = sc.g; ca.ntiles = (uint32_t)nt_p; ca.mode = o.mode; ca.score_src = o.score_src; ca.skip = sa.skip;
         ca.thr = score_threshold(o.min_score); ca.enabled = o.enabled_bins & 0x3f; ca.limit = limit; ca.debug = debug;
         for (int b = 0; b < 6; ++b) { ca.out[b] = out[b]; ca.out_cap[b] = ((ca.enabled >> b) & 1u) ? out_cap[b] : 0; }
