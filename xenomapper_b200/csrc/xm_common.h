@@ -8,8 +8,10 @@
 
 #if defined(__CUDACC__)
 #define XM_HD __host__ __device__ __forceinline__
+#define XM_COLD __host__ __device__ __noinline__      /* rare paths: kept out of line so the hot loop fits the instruction cache */
 #else
 #define XM_HD inline
+#define XM_COLD inline
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -122,11 +124,14 @@ struct Cfg {
     static constexpr int WIN = TILE + 2 * HALO;
     static constexpr int NW = WIN / 32 + 2;             /* 32-bit mask words: the window, the virtual newline bit, one spare */
     static constexpr int WPT = (NW + THREADS - 1) / THREADS;   /* mask words per thread in the index pass */
-    static constexpr int LCAP = THREADS;                /* owned lines a tile can hold */
+    static constexpr int LCAP = THREADS - 1;            /* owned lines a tile can hold; the last thread serves the halo line */
     static_assert(TILE % 32 == 0 && HALO % 32 == 0 && HALO > 0, "geometry");
     static_assert(WIN + 1 < 65535, "line starts are kept as 16-bit window offsets");
 };
-using CfgBig = Cfg<32768, 2048, 256>;
-using CfgSmall = Cfg<512, 512, 256>;          /* LCAP == TILE/2: cannot lose the stop (non-blank lines need 2 bytes) */
+#ifndef XM_BIG_THREADS
+#define XM_BIG_THREADS 256
+#endif
+using CfgBig = Cfg<32768, 2048, XM_BIG_THREADS>;
+using CfgSmall = Cfg<480, 512, 256>;          /* LCAP >= TILE/2: cannot lose the stop (non-blank lines need 2 bytes) */
 
 }  // namespace xm

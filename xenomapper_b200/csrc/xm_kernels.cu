@@ -226,20 +226,27 @@ __device__ void dev_resolve2(unsigned long long *chain, uint32_t tile, unsigned 
     for (int b = 0; b < 6; ++b) acc[b] = 0;
     unsigned pending = 0x3fu;                              /* bins still looking for an inclusive prefix */
     for (long long j = (long long)tile - 1; j >= 0 && pending; j -= 32) {
-        const long long idx = j - lane;
-        const unsigned long long *row = chain + (size_t)(idx >= 0 ? idx : 0) * C2_SLOTS;
-        unsigned long long d[6];
+        unsigned long long d[1][6];
 #pragma unroll
-        for (int b = 0; b < 6; ++b) d[b] = idx >= 0 ? ld_volatile64(row + b) : C2_INC;
+        for (int q = 0; q < 1; ++q) {
+            const long long idx = j - 32 * q - lane;
 #pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            if (!((pending >> b) & 1u)) continue;
-            if (idx >= 0)
-                while ((d[b] >> 62) == 0) d[b] = ld_volatile64(row + b);
-            const unsigned incmask = __ballot_sync(0xffffffffu, (d[b] >> 62) == 2);
-            const int L = incmask ? __ffs((int)incmask) - 1 : 31;
-            acc[b] += warp_sum64(lane <= L ? (d[b] & C2_VAL) : 0ull);
-            if (incmask) pending &= ~(1u << b);
+            for (int b = 0; b < 6; ++b) d[q][b] = idx >= 0 ? ld_volatile64(chain + (size_t)idx * C2_SLOTS + b) : C2_INC;
+        }
+#pragma unroll
+        for (int q = 0; q < 1; ++q) {
+            if (!pending) break;
+            const long long idx = j - 32 * q - lane;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                if (!((pending >> b) & 1u)) continue;
+                if (idx >= 0)
+                    while ((d[q][b] >> 62) == 0) d[q][b] = ld_volatile64(chain + (size_t)idx * C2_SLOTS + b);
+                const unsigned incmask = __ballot_sync(0xffffffffu, (d[q][b] >> 62) == 2);
+                const int L = incmask ? __ffs((int)incmask) - 1 : 31;
+                acc[b] += warp_sum64(lane <= L ? (d[q][b] & C2_VAL) : 0ull);
+                if (incmask) pending &= ~(1u << b);
+            }
         }
     }
     unsigned long long ex = 0;

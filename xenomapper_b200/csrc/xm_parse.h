@@ -229,7 +229,7 @@ struct Reader {
  * separator (runs collapse, leading/trailing dropped), CRLF, a missing final
  * newline, lines of any length.  One pass, O(1) state.
  */
-XM_HD void generic_parse(const Reader &rd, uint64_t gs, int score_src, LineRec &L)
+XM_COLD void generic_parse(const Reader &rd, uint64_t gs, int score_src, LineRec &L)
 {
     const bool cigar = score_src == SCORE_CIGAR_NM;
     const uint32_t xsch = score_src == SCORE_AS_ZS ? 'Z' : 'X';

@@ -449,51 +449,91 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
 #endif
     }
 
-    /* parse the owned lines; the last thread also parses the line before the first one when the walk needs it */
-    const bool split = fr.early && skip;
+    /* Parse the owned lines.  In a clean tile with at most THREADS/2 lines two threads share a line: thread i
+     * does the checks and the QNAME (fast_head), thread THREADS/2+i the aux tokens (fast_tail) and leaves its
+     * result in qx[THREADS/2+1+i].  The last thread owns no line: it parses the line before the first owned one
+     * when the walk needs it. */
+    constexpr int HALF = C::THREADS / 2;
+    const bool pair = fr.early && fr.nlines <= (uint32_t)HALF;
+    const bool split = pair && skip;
+    if (skip && !split) fr.early = false;
     XM_THREADS_BEGIN
         const WinMasks M_{T.m.win, T.m.tbm, T.m.nlm, T.m.trk, geo.wbytes, adj};
-        const Reader rd_{T.m.win, B.p, geo.g0, geo.wbytes, B.len};
-        uint32_t fb = 0xffffffffu;
+        Reader rd_{T.m.win, B.p, geo.g0, geo.wbytes, B.len};
         th.rank = NOT_YIELDED;
         th.sraw = 0;
-        th.yoff = 0;                    /* split parse: 1 = the aux half is still to do */
-        if ((uint32_t)tid < fr.nlines) {
-            const int s = (int)T.m.lstart[tid];
-            const uint16_t nx = T.m.lstart[tid + 1];
-            FastCtx fc;
-            if (!dirty && nx != LSTART_FAR && fast_head(M_, s, (int)nx - 1, th.L, fc)) {
-                if (split) { th.yoff = 1; th.ybytes = fc.r0; th.ymeta = fc.ntab; }
-                else fast_tail(M_, s, (int)nx - 1, score_src, fc, th.L);
-            } else generic_parse(rd_, geo.g0 + (uint64_t)s, score_src, th.L);
-            if (th.L.flags & F_BLANK) fb = (uint32_t)tid;
-            if (split) T.m.qx[tid + 1] = make_uint4(th.L.qs, th.L.qlen, th.L.h1, th.L.h2);
-        }
-        th.sin = fb;
+        th.yoff = 0;                    /* 1 = the aux half of the line is done by the partner thread */
+        th.sin = 0xffffffffu;
+        const bool mine = (uint32_t)tid < fr.nlines;
+        bool halo = false, farline = false, clean = false, tjob = false;
+        int s = 0, e = 0;
+        uint64_t gs = 0;
+        FastCtx fc;
+        fc.r0 = 0; fc.ntab = 0;
         if (tid == C::THREADS - 1) {
             T.m.scr[SCR_HALO_VALID] = 0;
             if (need_prev && fr.nlines > 0 && geo.g0 + T.m.lstart[0] > 0) {
+                halo = true;
                 const int s0 = (int)T.m.lstart[0];
-                uint64_t ps = prev_line_start(T.m.nlm, B.p, geo.g0, s0);
-                if (!dirty && ps > geo.g0 && T.m.win[ps - geo.g0 - 1] != '\n') {
+                gs = prev_line_start(T.m.nlm, B.p, geo.g0, s0);
+                if (!dirty && gs > geo.g0 && T.m.win[gs - geo.g0 - 1] != '\n') {
                     /* the candidate before the halo line is not a newline: find its real start byte-wise */
-                    --ps;
-                    while (ps > 0 && rd_.at(ps - 1) != '\n') --ps;
+                    --gs;
+                    while (gs > 0 && rd_.at(gs - 1) != '\n') --gs;
                 }
-                LineRec H;
-                FastCtx fc;
-                Reader rh_ = rd_;
-                const bool far = ps < geo.g0;
-                if (far) { rh_.wbytes = 0; rh_.g0 = ps; }       /* read it all from global memory */
-                if (!far && !dirty && fast_head(M_, (int)(ps - geo.g0), s0 - 1, H, fc)) fast_tail(M_, (int)(ps - geo.g0), s0 - 1, score_src, fc, H);
-                else generic_parse(rh_, ps, score_src, H);
-                T.m.scr64[S64_HALO_START] = ps;
-                T.m.scr64[S64_HALO_QS] = rh_.g0 + H.qs;
-                T.m.scr[SCR_HALO_QLEN] = H.qlen; T.m.scr[SCR_HALO_H1] = H.h1; T.m.scr[SCR_HALO_H2] = H.h2;
-                T.m.scr[SCR_HALO_FLAGS] = H.flags; T.m.scr[SCR_HALO_OUTLEN] = H.outlen;
-                T.m.scr[SCR_HALO_AS] = (uint32_t)H.as; T.m.scr[SCR_HALO_XS] = (uint32_t)H.xs;
-                T.m.scr[SCR_HALO_VALID] = 1;
+                farline = gs < geo.g0;
+                if (farline) { rd_.wbytes = 0; rd_.g0 = gs; }       /* read it all from global memory */
+                s = (int)(gs - geo.g0);
+                e = s0 - 1;
             }
+        }
+        if (mine) {
+            s = (int)T.m.lstart[tid];
+            const uint16_t nx = T.m.lstart[tid + 1];
+            e = (int)nx - 1;
+            farline = nx == LSTART_FAR;
+            gs = geo.g0 + (uint64_t)s;
+        }
+        if (mine || halo) {
+            if (!dirty && !farline) clean = fast_head(M_, s, e, th.L, fc);
+            if (!clean) {               /* out of line: keep its operands off this thread's registers' stack */
+                const Reader rg_ = rd_;
+                LineRec G;
+                generic_parse(rg_, gs, score_src, G);
+                th.L = G;
+            }
+            tjob = clean && !(pair && mine);
+            if (clean && pair && mine) th.yoff = 1;
+        } else if (pair && tid >= HALF && (uint32_t)(tid - HALF) < fr.nlines) {
+            s = (int)T.m.lstart[tid - HALF];
+            const uint16_t nx = T.m.lstart[tid - HALF + 1];
+            e = (int)nx - 1;
+            /* the conditions under which fast_head accepts the line in a tile without touching W bytes */
+            if (nx != LSTART_FAR && (uint32_t)e < geo.wbytes && e > s && T.m.win[e] == '\n' && !(s == 0 && (M_.wsm(0) & 1u))) {
+                fc.r0 = tabs_before(M_, s);
+                fc.ntab = tabs_before(M_, e) - fc.r0;
+                tjob = true;
+            }
+        }
+        if (tjob) {
+            LineRec X;
+            X.flags = 0; X.as = SCORE_ABSENT; X.xs = SCORE_ABSENT;
+            fast_tail(M_, s, e, score_src, fc, X);
+            if (mine || halo) { th.L.flags = X.flags; th.L.as = X.as; th.L.xs = X.xs; }
+            else T.m.qx[tid + 1] = make_uint4(X.flags, (uint32_t)X.as, (uint32_t)X.xs, 1u);
+        }
+        if (mine) {
+            if (th.L.flags & F_BLANK) th.sin = (uint32_t)tid;
+            if (split) T.m.qx[tid + 1] = make_uint4(th.L.qs, th.L.qlen, th.L.h1, th.L.h2);
+        }
+        if (halo) {
+            const LineRec &H = th.L;
+            T.m.scr64[S64_HALO_START] = gs;
+            T.m.scr64[S64_HALO_QS] = rd_.g0 + H.qs;
+            T.m.scr[SCR_HALO_QLEN] = H.qlen; T.m.scr[SCR_HALO_H1] = H.h1; T.m.scr[SCR_HALO_H2] = H.h2;
+            T.m.scr[SCR_HALO_FLAGS] = H.flags; T.m.scr[SCR_HALO_OUTLEN] = H.outlen;
+            T.m.scr[SCR_HALO_AS] = (uint32_t)H.as; T.m.scr[SCR_HALO_XS] = (uint32_t)H.xs;
+            T.m.scr[SCR_HALO_VALID] = 1;
         }
     XM_THREADS_END
     if (split) {
@@ -530,12 +570,6 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
         XM_THREADS_BEGIN
             if ((uint32_t)tid < fr.nlines) {
                 if (th.sin) th.rank = th.sout;
-                if (th.yoff) {
-                    const WinMasks M_{T.m.win, T.m.tbm, T.m.nlm, T.m.trk, geo.wbytes, adj};
-                    FastCtx fc;
-                    fc.r0 = th.ybytes; fc.ntab = th.ymeta;
-                    fast_tail(M_, (int)T.m.lstart[tid], (int)T.m.lstart[tid + 1] - 1, score_src, fc, th.L);
-                }
             }
         XM_THREADS_END
     } else if (adj || dirty) {
@@ -543,6 +577,15 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
         XM_BLOCK_MIN(0, fb_);
         fr.stop = fb_ < fr.nlines;
         fr.n_eff = fr.stop ? fb_ : fr.nlines;
+    }
+    if (pair) {
+        if (!split) XM_BARRIER();       /* (the split walk has passed a barrier since the aux halves were written) */
+        XM_THREADS_BEGIN
+            if ((uint32_t)tid < fr.nlines && th.yoff) {
+                const uint4 r = T.m.qx[HALF + 1 + tid];
+                th.L.flags = r.x; th.L.as = (int32_t)r.y; th.L.xs = (int32_t)r.z;
+            }
+        XM_THREADS_END
     }
     /* where the stream stops, if it does so here (needed after the masks are gone) */
     XM_THREADS_BEGIN
@@ -680,7 +723,7 @@ XM_HD void eval_error(uint32_t pflags, uint32_t sflags, int &code, int &stream)
 /* byte-wise writer for lines whose output differs from their raw bytes:
  * tokens joined by single tabs + '\n' (xm.py:334).  gs may point at the
  * line's first byte or its first token. */
-XM_HD void write_normalised(const Reader &rd, uint64_t gs, int nlines, uint8_t *dst)
+XM_COLD void write_normalised(const Reader &rd, uint64_t gs, int nlines, uint8_t *dst)
 {
     uint64_t p = gs;
     for (int l = 0; l < nlines; ++l) {
