@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxenomapper_b200.so")
+LIB_PATH = os.environ.get("XM_LIB_PATH") or os.path.join(_HERE, "libxenomapper_b200.so")
 
 BINS = ("primary_specific", "secondary_specific", "primary_multi",
         "secondary_multi", "unassigned", "unresolved")

@@ -34,6 +34,11 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed building libxenomapper_b200.so")
         with open(os.path.join(HERE, "build.log"), "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout)
+    if os.environ.get("XM_BUILD_PROF"):
+        # profiling twin with per-phase cycle counters (never loaded by the package; XM_LIB_PATH selects it in bench.py)
+        prof = os.path.join(HERE, "libxenomapper_b200_prof.so")
+        cmd = [os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")] + NVCC_FLAGS + ["-DXM_PHASE_TIMING=1", "-o", prof] + [os.path.join(CSRC, f) for f in SOURCES]
+        subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, check=True)
     from . import synth
     synth_so = os.path.join(HERE, "_xm_synth.so")
     if force or _stale(synth_so, [os.path.join(CSRC, "xm_synth.c")]):

@@ -77,6 +77,7 @@ struct Globals {
     unsigned int overflow;            /* a tile held more lines than the geometry allows: relaunch smaller */
     unsigned int ticket[2];
     unsigned int pad;
+    unsigned long long phase[48];     /* XM_PHASE_TIMING builds: thread-0 clock cycles per tile phase, summed over tiles */
 };
 
 /* decoupled look-back descriptors */
@@ -127,11 +128,21 @@ struct Cfg {
     static constexpr int LCAP = THREADS - 1;            /* owned lines a tile can hold; the last thread serves the halo line */
     static_assert(TILE % 32 == 0 && HALO % 32 == 0 && HALO > 0, "geometry");
     static_assert(WIN + 1 < 65535, "line starts are kept as 16-bit window offsets");
+    static_assert(THREADS <= 512 && THREADS % 32 == 0, "per-warp scratch holds 16 warps");
 };
 #ifndef XM_BIG_THREADS
 #define XM_BIG_THREADS 256
 #endif
-using CfgBig = Cfg<32768, 2048, XM_BIG_THREADS>;
+#ifndef XM_BIG_TILE
+#define XM_BIG_TILE 32768
+#endif
+#ifndef XM_BIG_HALO
+#define XM_BIG_HALO 2048
+#endif
+#ifndef XM_BIG_OCC
+#define XM_BIG_OCC 4
+#endif
+using CfgBig = Cfg<XM_BIG_TILE, XM_BIG_HALO, XM_BIG_THREADS>;
 using CfgSmall = Cfg<480, 512, 256>;          /* LCAP >= TILE/2: cannot lose the stop (non-blank lines need 2 bytes) */
 
 }  // namespace xm

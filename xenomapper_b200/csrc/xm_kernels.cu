@@ -15,6 +15,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef XM_OPT_BACKOFF_NS
+#define XM_OPT_BACKOFF_NS 0
+#endif
+#if XM_OPT_BACKOFF_NS
+#define XM_BACKOFF() __nanosleep(XM_OPT_BACKOFF_NS)      /* polling a descriptor that is not there yet: do not hammer L2 */
+#else
+#define XM_BACKOFF() ((void)0)
+#endif
+#ifndef XM_OPT_LASTWARP
+#define XM_OPT_LASTWARP 0
+#endif
+#ifndef XM_OPT_SERVICE
+#define XM_OPT_SERVICE 0
+#endif
 #include "xm_tile.h"
 #include "xm_launch.h"
 
@@ -187,7 +201,7 @@ __device__ void dev_resolve1(unsigned long long *desc, uint32_t tile, unsigned l
             if (done) break;
             const long long idx = j - 32 * q - lane;
             if (idx >= 0)
-                while ((d[q] >> 62) == 0) d[q] = ld_volatile64(desc + idx);
+                while ((d[q] >> 62) == 0) { XM_BACKOFF(); d[q] = ld_volatile64(desc + idx); }
             const unsigned incmask = __ballot_sync(0xffffffffu, (d[q] >> 62) == 2);
             const int L = incmask ? __ffs((int)incmask) - 1 : 31;  /* nearest inclusive prefix */
             const bool part = lane <= L;
@@ -218,14 +232,22 @@ __device__ void dev_publish2(unsigned long long *chain, uint32_t tile, const uns
     if (lane < 6) st_volatile64(chain + (size_t)tile * C2_SLOTS + lane, C2_AGG | tot[lane]);
 }
 
-__device__ void dev_resolve2(unsigned long long *chain, uint32_t tile, unsigned long long *tot)
+__device__ void dev_resolve2(unsigned long long *chain, uint32_t tile, unsigned long long *tot, unsigned long long *dbg)
 {
+#ifdef XM_PHASE_TIMING
+    unsigned long long n_win = 0, n_spin = 0;   /* windows walked, polls that found nothing */
+#else
+    (void)dbg;
+#endif
     const int lane = threadIdx.x & 31;
     unsigned long long acc[6];
 #pragma unroll
     for (int b = 0; b < 6; ++b) acc[b] = 0;
     unsigned pending = 0x3fu;                              /* bins still looking for an inclusive prefix */
     for (long long j = (long long)tile - 1; j >= 0 && pending; j -= 32) {
+#ifdef XM_PHASE_TIMING
+        ++n_win;
+#endif
         unsigned long long d[1][6];
 #pragma unroll
         for (int q = 0; q < 1; ++q) {
@@ -241,7 +263,13 @@ __device__ void dev_resolve2(unsigned long long *chain, uint32_t tile, unsigned 
             for (int b = 0; b < 6; ++b) {
                 if (!((pending >> b) & 1u)) continue;
                 if (idx >= 0)
-                    while ((d[q][b] >> 62) == 0) d[q][b] = ld_volatile64(chain + (size_t)idx * C2_SLOTS + b);
+                    while ((d[q][b] >> 62) == 0) {
+                        XM_BACKOFF();
+                        d[q][b] = ld_volatile64(chain + (size_t)idx * C2_SLOTS + b);
+#ifdef XM_PHASE_TIMING
+                        ++n_spin;
+#endif
+                    }
                 const unsigned incmask = __ballot_sync(0xffffffffu, (d[q][b] >> 62) == 2);
                 const int L = incmask ? __ffs((int)incmask) - 1 : 31;
                 acc[b] += warp_sum64(lane <= L ? (d[q][b] & C2_VAL) : 0ull);
@@ -256,7 +284,19 @@ __device__ void dev_resolve2(unsigned long long *chain, uint32_t tile, unsigned 
         st_volatile64(chain + (size_t)tile * C2_SLOTS + lane, C2_INC | (ex + tot[lane]));
         tot[lane] = ex;
     }
+#ifdef XM_PHASE_TIMING
+    if (dbg) {
+        if (lane == 0) atomicAdd(dbg, n_win);
+        n_spin = warp_sum64(n_spin);
+        if (lane == 0) atomicAdd(dbg + 1, n_spin);
+    }
+#endif
     __syncwarp();
+}
+
+__device__ void dev_prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 /* ---- warp copy engine ------------------------------------------------------- */
@@ -350,7 +390,7 @@ __device__ void dev_copy_piece(uint8_t *dst, const uint8_t *win, uint32_t src_of
 
 /* ---- kernels ------------------------------------------------------------------ */
 template <class C>
-__global__ void __launch_bounds__(C::THREADS, 4) k_scan(const ScanArgs a)
+__global__ void __launch_bounds__(C::THREADS, (C::THREADS == XM_BIG_THREADS ? XM_BIG_OCC : 4)) k_scan(const ScanArgs a)
 {
     extern __shared__ uint4 xm_smem[];
     TileCtx<C> T;
@@ -360,7 +400,7 @@ __global__ void __launch_bounds__(C::THREADS, 4) k_scan(const ScanArgs a)
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::THREADS, 4) k_classify(const ClassifyArgs a)
+__global__ void __launch_bounds__(C::THREADS, (C::THREADS == XM_BIG_THREADS ? XM_BIG_OCC : 4)) k_classify(const ClassifyArgs a)
 {
     extern __shared__ uint4 xm_smem[];
     TileCtx<C> T;

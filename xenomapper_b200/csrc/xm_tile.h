@@ -63,8 +63,8 @@ struct TileMem {
 };
 
 /* scratch slots */
-enum { SCR_WT0 = 0, SCR_WT1 = 32, SCR_BINS = 64 /* [8 warps][8] */, SCR_FAKE = 128, SCR_ADJ, SCR_NRARE, SCR_SPARE,
-       SCR_HALO_QLEN, SCR_HALO_H1, SCR_HALO_H2, SCR_HALO_FLAGS, SCR_HALO_OUTLEN, SCR_HALO_AS, SCR_HALO_XS, SCR_HALO_VALID, SCR_WORDS = 160 };
+enum { SCR_WT0 = 0, SCR_WT1 = 32, SCR_BINS = 64 /* [16 warps][8] */, SCR_FAKE = 192, SCR_ADJ, SCR_NRARE, SCR_SPARE,
+       SCR_HALO_QLEN, SCR_HALO_H1, SCR_HALO_H2, SCR_HALO_FLAGS, SCR_HALO_OUTLEN, SCR_HALO_AS, SCR_HALO_XS, SCR_HALO_VALID, SCR_WORDS = 208 };
 enum { S64_TOT = 0 /* 0..7 */, S64_TSUM = 8 /* 8..15 */, S64_HALO_START = 16, S64_HALO_QS, S64_BASE, S64_PSTOP, S64_BLANK_OFF, S64_MBAR, S64_WORDS = 24 };
 
 template <class C>
@@ -174,6 +174,22 @@ XM_HD uint32_t shl_pack(uint32_t outlen, int state, int evalerr, int evalstream,
 #define XM_SMEM_INC(p, result) do { result = (*(p))++; } while (0)
 #endif
 
+/* which warp runs the serial look-back sections */
+#if defined(XM_OPT_LASTWARP) && XM_OPT_LASTWARP
+#define XM_LB_WARP(C) (threadIdx.x >= C::THREADS - 32)
+#else
+#define XM_LB_WARP(C) (threadIdx.x < 32)
+#endif
+
+/* phase timing (profiling builds only): thread 0 adds the cycles since the previous mark to Globals::phase[k] */
+#if XM_DEVICE_PASS && defined(XM_PHASE_TIMING)
+#define XM_MARK(fr, k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&(fr).g->phase[(fr).pbase + (k)], (unsigned long long)(t_ - (fr).tmark)); (fr).tmark = t_; } } while (0)
+#define XM_MARK_INIT(fr, gp, base) do { (fr).g = (gp); (fr).pbase = (base); (fr).tmark = clock64(); } while (0)
+#else
+#define XM_MARK(fr, k) ((void)0)
+#define XM_MARK_INIT(fr, gp, base) ((void)0)
+#endif
+
 #if defined(__CUDACC__)
 /* device collectives, window staging, look-back and the copy engines: xm_kernels.cu */
 __device__ uint32_t dev_block_scan(uint32_t v, uint32_t *wt, uint32_t &total);
@@ -186,7 +202,9 @@ __device__ void dev_publish1(unsigned long long *desc, uint32_t tile, unsigned l
 __device__ void dev_resolve1(unsigned long long *desc, uint32_t tile, unsigned long long agg_count, bool agg_stop,
                              unsigned long long *out /* [0] exclusive count, [1] exclusive stop */);
 __device__ void dev_publish2(unsigned long long *chain, uint32_t tile, const unsigned long long *tot /* smem [C2_SLOTS] */);
-__device__ void dev_resolve2(unsigned long long *chain, uint32_t tile, unsigned long long *tot_to_base /* in: totals; out: exclusive bases */);
+__device__ void dev_resolve2(unsigned long long *chain, uint32_t tile, unsigned long long *tot_to_base /* in: totals; out: exclusive bases */,
+                             unsigned long long *dbg /* profiling builds: two counters, else nullptr */);
+__device__ void dev_prefetch_l2(const void *p);
 __device__ void dev_warp_copy(uint8_t *dst, const uint8_t *src_smem, const uint8_t *src_glob, uint32_t len);
 __device__ void dev_copy_piece(uint8_t *dst, const uint8_t *win, uint32_t src_off, uint32_t len);
 #endif
@@ -252,6 +270,10 @@ struct Front {
     bool dirty;            /* the tile's terminator candidates are not all '\n': every line takes the exact parser */
     bool early;            /* the tile's record count was published on chain 1 before the parse finished */
     bool ranked;           /* th.rank is already set */
+    bool resolved;         /* the record base is already in scr64[S64_BASE] (looked up while the lines were parsed) */
+    Globals *g;            /* phase timing only */
+    int pbase;
+    long long tmark;
 };
 
 /* bits of mask word w that lie in the byte range this tile owns */
@@ -308,7 +330,7 @@ XM_HD bool run_head(const Reader &rd, const LineRec &L, const uint4 prev, uint64
  */
 template <class C>
 XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int score_src, uint32_t debug,
-                     bool need_prev, unsigned long long *chain1, uint32_t tile, bool skip, Front<C> &fr)
+                     bool need_prev, unsigned long long *chain1, uint32_t tile, bool skip, const SCompact *join, Front<C> &fr)
 {
     (void)th_;
     const Geo geo = fr.geo;
@@ -321,6 +343,7 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
 #else
     memcpy(T.m.win, B.p + geo.g0, (geo.wbytes + 15u) & ~15u);
 #endif
+    XM_MARK(fr, 0);
     bool exact = (debug & DBG_FORCE_GENERIC) != 0;      /* exact newline mask: the tile is dirty (or forced) */
     uint32_t tot = 0, total_lines = 0;
     bool adj = false;
@@ -335,6 +358,7 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
                 cW = is_w_byte(c) ? 1u : 0u;
                 cN = exact ? (c == '\n' ? 1u : 0u) : (cW && c != '\t' ? 1u : 0u);
             } else cW = cN = 0u;
+#pragma unroll 1
             for (int j = 0; j < C::WPT; ++j) {
                 const int w = wb + j;
                 if (w >= C::NW) break;
@@ -357,14 +381,15 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
                 aj |= W & ((W << 1) | cW);
                 tabs += (uint32_t)popc32(Tm);
                 cnt += (uint32_t)popc32(((N << 1) | cN) & own_mask<C>(geo, w));
-                cW = W >> 31; cN = N >> 31;
                 T.m.tbm[w] = Tm;
                 T.m.nlm[w] = N;
+                cW = W >> 31; cN = N >> 31;
             }
             th.sin = cnt | (tabs << 16);
             if (aj) T.m.scr[SCR_ADJ] = 1;
         XM_THREADS_END
         XM_BLOCK_SCAN(attempt & 1, tot);
+        XM_MARK(fr, 1);
         total_lines = tot & 0xffffu;
         XM_THREADS_BEGIN
             T.m.lpre[tid] = (uint16_t)(th.sout & 0xffffu);
@@ -378,6 +403,7 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
             }
         XM_THREADS_END
         XM_BARRIER();
+        XM_MARK(fr, 2);
         /* the start of owned line i, found through the per-thread counts; every terminator candidate that bounds
          * an owned line is checked to be a real '\n' on the way */
         XM_THREADS_BEGIN
@@ -420,6 +446,7 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
         XM_THREADS_END
         XM_BARRIER();
         adj = T.m.scr[SCR_ADJ] != 0;
+        XM_MARK(fr, 3);
         if (exact || !T.m.scr[SCR_FAKE]) break;
         exact = true;
     }
@@ -438,10 +465,26 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
     /* a blank line needs two touching W bytes (or a separator opening the stream): without them the tile yields
      * all its owned lines (or, skipping, the run heads among them) and can say so before the parse is over */
     fr.early = !adj && !dirty;
+    fr.resolved = false;
     if (fr.early && !skip) {
         fr.count = fr.nlines;
-#if XM_DEVICE_PASS
+#if XM_DEVICE_PASS && defined(XM_OPT_SERVICE) && !XM_OPT_SERVICE
         if (threadIdx.x == 0) dev_publish1(chain1, tile, fr.nlines, false);
+#elif XM_DEVICE_PASS
+        fr.resolved = true;
+        /* the last warp, which rarely has lines to parse, looks the record base up while the others parse, and
+         * asks for the secondary-stream records the tile will be joined with to be brought into L2 */
+        if (threadIdx.x >= C::THREADS - 32) {
+            if ((threadIdx.x & 31) == 0) dev_publish1(chain1, tile, fr.nlines, false);
+            dev_resolve1(chain1, tile, fr.nlines, false, T.m.scr64 + S64_BASE);
+            __syncwarp();
+            if (join && !T.m.scr64[S64_PSTOP]) {
+                const unsigned long long b0 = T.m.scr64[S64_BASE];
+                const uint32_t lane = threadIdx.x & 31;
+                for (uint32_t k = lane * 8u; k < fr.nlines; k += 256u) dev_prefetch_l2(join->rec + b0 + k);      /* 8 records per 128-byte line */
+                for (uint32_t k = lane * 32u; k < fr.nlines; k += 1024u) dev_prefetch_l2(join->meta + b0 + k);
+            }
+        }
 #else
         unsigned long long o_[2];
         emu_lookback1(chain1, tile, fr.nlines, false, o_);
@@ -539,6 +582,7 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
     if (split) {
         /* run heads (getReadPairs skip mode, xm.py:110-114) from the QNAMEs alone; then the rest of each line */
         XM_BARRIER();
+        XM_MARK(fr, 4);
         XM_THREADS_BEGIN
             uint32_t head = 0;
             if ((uint32_t)tid < fr.nlines) {
@@ -556,6 +600,7 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
         XM_THREADS_END
         uint32_t cnt_;
         XM_BLOCK_SCAN(0, cnt_);
+        XM_MARK(fr, 5);
         fr.count = cnt_;
         fr.ranked = true;
 #if XM_DEVICE_PASS
@@ -592,6 +637,7 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
         if (tid == 0) T.m.scr64[S64_BLANK_OFF] = fr.stop ? geo.g0 + (uint64_t)T.m.lstart[fr.n_eff] : B.len;
     XM_THREADS_END
     XM_BARRIER();      /* every thread is done with the masks: the per-line arrays may overlay them now */
+    XM_MARK(fr, 6);
 }
 
 /* Ranks among the records the tile yields: every line before the stop, or only
@@ -632,17 +678,20 @@ XM_HD uint32_t rank_lines(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B
     return tot;
 }
 
-/* record base of a tile through look-back chain 1 (count + stop flag); `early`: the count is already published */
+/* record base of a tile through look-back chain 1 (count + stop flag); `early`: the count is already published,
+ * `resolved`: the base has been looked up as well (and a barrier has been passed since) */
 #if XM_DEVICE_PASS
-#define XM_LOOKBACK1(chain, tile, count, stop, early, base, pstop) do { \
-        if (threadIdx.x < 32) { \
-            if (!(early) && threadIdx.x == 0) dev_publish1((chain), (tile), (count), (stop)); \
-            dev_resolve1((chain), (tile), (count), (stop), T.m.scr64 + S64_BASE); \
+#define XM_LOOKBACK1(chain, tile, count, stop, early, resolved, base, pstop) do { \
+        if (!(resolved)) { \
+            if (XM_LB_WARP(C)) { \
+                if (!(early) && (threadIdx.x & 31) == 0) dev_publish1((chain), (tile), (count), (stop)); \
+                dev_resolve1((chain), (tile), (count), (stop), T.m.scr64 + S64_BASE); \
+            } \
+            __syncthreads(); \
         } \
-        __syncthreads(); \
         base = T.m.scr64[S64_BASE]; pstop = T.m.scr64[S64_PSTOP]; } while (0)
 #else
-#define XM_LOOKBACK1(chain, tile, count, stop, early, base, pstop) do { \
+#define XM_LOOKBACK1(chain, tile, count, stop, early, resolved, base, pstop) do { \
         if (!(early)) { unsigned long long o_[2]; emu_lookback1((chain), (tile), (count), (stop), o_); T.m.scr64[S64_BASE] = o_[0]; T.m.scr64[S64_PSTOP] = o_[1]; } \
         base = T.m.scr64[S64_BASE]; pstop = T.m.scr64[S64_PSTOP]; } while (0)
 #endif
@@ -660,7 +709,8 @@ XM_HD void scan_tile(TileCtx<C> &T, const ScanArgs &a, uint32_t tile)
 #endif
     Front<C> fr;
     fr.geo = tile_geo<C>(a.S, tile);
-    front_end<C>(T, th_, a.S, a.score_src, a.debug, a.skip != 0, a.chain1, tile, a.skip != 0, fr);
+    XM_MARK_INIT(fr, a.g, 0);
+    front_end<C>(T, th_, a.S, a.score_src, a.debug, a.skip != 0, a.chain1, tile, a.skip != 0, nullptr, fr);
 
     if (a.skip && !fr.ranked) {
         XM_THREADS_BEGIN
@@ -671,7 +721,8 @@ XM_HD void scan_tile(TileCtx<C> &T, const ScanArgs &a, uint32_t tile)
     const uint32_t count = rank_lines<C>(T, th_, a.S, fr, a.skip != 0);
 
     unsigned long long base, pstop;
-    XM_LOOKBACK1(a.chain1, tile, count, fr.stop, fr.early, base, pstop);
+    XM_LOOKBACK1(a.chain1, tile, count, fr.stop, fr.early, fr.resolved, base, pstop);
+    XM_MARK(fr, 7);
 
     XM_THREADS_BEGIN
         if (!pstop) {
@@ -758,7 +809,8 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
     const bool paired = a.mode != MODE_SE;
     Front<C> fr;
     fr.geo = tile_geo<C>(a.P, tile);
-    front_end<C>(T, th_, a.P, a.score_src, a.debug, paired || a.skip, a.chain1, tile, a.skip != 0, fr);
+    XM_MARK_INIT(fr, a.g, 12);
+    front_end<C>(T, th_, a.P, a.score_src, a.debug, paired || a.skip, a.chain1, tile, a.skip != 0, &a.sc, fr);
 
     XM_THREADS_BEGIN
         if (tid < 36) T.m.hist[tid] = 0;
@@ -768,7 +820,9 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
     const uint32_t count = rank_lines<C>(T, th_, a.P, fr, a.skip != 0);
 
     unsigned long long base, pstop;
-    XM_LOOKBACK1(a.chain1, tile, count, fr.stop, fr.early, base, pstop);
+    XM_MARK(fr, 7);
+    XM_LOOKBACK1(a.chain1, tile, count, fr.stop, fr.early, fr.resolved, base, pstop);
+    XM_MARK(fr, 8);
     /* records at or beyond ncap are not yielded: the other stream ended first, or an error re-run cut here */
     unsigned long long ncap = a.g->n_stream[1];
     if (a.limit < ncap) ncap = a.limit;
@@ -882,12 +936,13 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
         XM_THREADS_END
     }
 
+    XM_MARK(fr, 9);
     /* byte offsets inside each bin: warp scans over the six bins, then the second look-back chain */
     XM_SCAN_BINS();
     /* publish the tile's bytes per bin now; the bases are looked up once everything that can do without them is done */
 #if XM_DEVICE_PASS
     __syncthreads();
-    if (threadIdx.x < 32) {
+    if (XM_LB_WARP(C)) {
         dev_bin_totals(T.m.scr + SCR_BINS, T.m.scr64 + S64_TSUM);
         dev_publish2(a.chain2, tile, T.m.scr64 + S64_TSUM);
     }
@@ -895,6 +950,7 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
     for (int b = 0; b < C2_SLOTS; ++b) T.m.scr64[S64_TSUM + b] = tsum[b];
 #endif
 
+    XM_MARK(fr, 10);
     /* copy items: at most two per owning line (its primary-stream part, its secondary-stream part) */
     const uint32_t nown = fr.n_eff;
     XM_THREADS_BEGIN
@@ -966,6 +1022,7 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
         }
         th.sin = v;
     XM_THREADS_END
+    XM_MARK(fr, 11);
     uint32_t rtot;
     XM_BLOCK_SCAN(0, rtot);
     const uint32_t nruns = rtot >> RUN_CB_BITS;
@@ -979,13 +1036,18 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
         if (tid == 0) T.m.run_cb[nruns] = rtot & ((1u << RUN_CB_BITS) - 1u);
     XM_THREADS_END
     XM_BARRIER();
+    XM_MARK(fr, 12);
     /* exclusive byte bases of the tile in the six bins: second look-back chain */
     unsigned long long tot[C2_SLOTS];
 #if XM_DEVICE_PASS
-    if (threadIdx.x < 32) {
-        if (threadIdx.x < C2_SLOTS) T.m.scr64[S64_TOT + threadIdx.x] = T.m.scr64[S64_TSUM + threadIdx.x];
+    if (XM_LB_WARP(C)) {
+        if ((threadIdx.x & 31) < C2_SLOTS) T.m.scr64[S64_TOT + (threadIdx.x & 31)] = T.m.scr64[S64_TSUM + (threadIdx.x & 31)];
         __syncwarp();
-        dev_resolve2(a.chain2, tile, T.m.scr64 + S64_TOT);
+#if defined(XM_PHASE_TIMING)
+        dev_resolve2(a.chain2, tile, T.m.scr64 + S64_TOT, a.g->phase + 30);
+#else
+        dev_resolve2(a.chain2, tile, T.m.scr64 + S64_TOT, nullptr);
+#endif
     }
     __syncthreads();
     for (int b = 0; b < C2_SLOTS; ++b) tot[b] = T.m.scr64[S64_TOT + b];
@@ -993,6 +1055,7 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
     for (int b = 0; b < C2_SLOTS; ++b) tot[b] = T.m.scr64[S64_TSUM + b];
     emu_lookback2(a.chain2, tile, tot);
 #endif
+    XM_MARK(fr, 13);
     /* copy the runs: each warp takes an equal share of the tile's run bytes, cutting runs where its share ends.
      * Runs that do not fit their output are dropped (the host rejects the call). */
     {
@@ -1028,6 +1091,7 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
         }
 #endif
     }
+    XM_MARK(fr, 14);
     /* and the single items: one warp each */
     {
         const uint32_t nrare = T.m.scr[SCR_NRARE];
@@ -1087,6 +1151,7 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
 
     /* category histogram and stream totals */
     XM_BARRIER();
+    XM_MARK(fr, 15);
     XM_THREADS_BEGIN
         if (tid < 36 && T.m.hist[tid]) atomic_add64(&a.g->counts[tid], (unsigned long long)T.m.hist[tid]);
         if (tid == 0) {

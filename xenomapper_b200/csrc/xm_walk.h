@@ -292,6 +292,18 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         res->ms_scan = be.elapsed(3, 1); res->ms_classify = be.elapsed(1, 2); res->ms_total += be.elapsed(0, 2);
         if (be.read(&G, sc.g, sizeof G)) { errmsg = "result read failed"; return res->status = XM_ERR_CUDA; }
 
+#ifdef XM_PHASE_TIMING
+        {
+            static const char *nm[16] = {"stage", "mask+count", "scan+trk", "select", "parse", "heads", "front-end", "pre-look1", "look1", "decide", "bins", "items", "runs", "resolve2", "copy", "rare+end"};
+            for (int k = 0; k < 2; ++k) {
+                const unsigned long long nt = k ? nt_p : nt_s;
+                fprintf(stderr, "[phases %s, cycles per tile, %llu tiles]", k ? "classify" : "scan", nt);
+                for (int q = 0; q < (k ? 16 : 8); ++q) fprintf(stderr, " %s=%.0f", nm[q], (double)G.phase[12 * k + q] / (double)nt);
+                if (k) fprintf(stderr, " | resolve2 windows/tile=%.2f polls/tile=%.1f per window: first-load=%.0f +spin=%.0f +fold=%.0f", (double)G.phase[30] / (double)nt, (double)G.phase[31] / (double)nt, (double)G.phase[32] / (double)G.phase[30], (double)G.phase[33] / (double)G.phase[30], (double)G.phase[34] / (double)G.phase[30]);
+                fprintf(stderr, "\n");
+            }
+        }
+#endif
         if (G.overflow && !small) { small = true; continue; }           /* pathologically short lines: 1 KiB tiles cannot overflow */
         if (G.n_stream[1] > sc.sc_cap) { sc_need = G.n_stream[1] + 1; continue; }
         if (G.err != NO_ERROR && limit == ~0ull) {
