@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "xm_emu.cpp")
 SO = os.path.join(HERE, "emu", "libxm_emu.so")
 DEPS = [SRC] + [os.path.join(ROOT, "xenomapper_b200", "csrc", f) for f in
-                ("xm_common.h", "xm_parse.h", "xm_tile.h", "xm_walk.h")] + [os.path.join(ROOT, "include", "xenomapper_b200.h")]
+                ("xm_common.h", "xm_parse.h", "xm_tile.h", "xm_walk.h", "xm_stream.h")] + [os.path.join(ROOT, "include", "xenomapper_b200.h")]
 
 
 class Opts(C.Structure):
@@ -37,11 +37,16 @@ def lib():
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Result),
                                          C.c_char_p, C.c_size_t]
         _lib.xm_emu_classify.restype = C.c_int
+        _lib.xm_emu_classify_stream.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(Opts), C.c_uint32, C.c_uint64,
+                                                C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Result),
+                                                C.c_char_p, C.c_size_t]
+        _lib.xm_emu_classify_stream.restype = C.c_int
     return _lib
 
 
 def classify(prim, sec, mode=0, score_src=0, skip_repeated=False, min_score=float("-inf"), enabled_bins=0x3F,
-             debug=0, cap=None):
+             debug=0, cap=None, chunk=None):
+    """chunk: run the chunked walk (xm_stream.h) with that many new bytes per stream and step"""
     L = lib()
     prim, sec = bytes(prim), bytes(sec)
     if cap is None:
@@ -52,7 +57,10 @@ def classify(prim, sec, mode=0, score_src=0, skip_repeated=False, min_score=floa
     o = Opts(mode, score_src, int(bool(skip_repeated)), enabled_bins, min_score)
     r = Result()
     err = C.create_string_buffer(512)
-    rc = L.xm_emu_classify(prim, len(prim), sec, len(sec), C.byref(o), debug, outp, caps, C.byref(r), err, 512)
+    if chunk:
+        rc = L.xm_emu_classify_stream(prim, len(prim), sec, len(sec), C.byref(o), debug, chunk, outp, caps, C.byref(r), err, 512)
+    else:
+        rc = L.xm_emu_classify(prim, len(prim), sec, len(sec), C.byref(o), debug, outp, caps, C.byref(r), err, 512)
     outs = [bufs[b].raw[:r.out_len[b]] for b in range(6)]
     return dict(status=rc, outputs=outs, counts=list(r.counts), n_records=r.n_records, err_record=r.err_record,
                 bytes_in=list(r.bytes_in), message=err.value.decode())

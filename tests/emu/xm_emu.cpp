@@ -15,6 +15,9 @@
 
 #include "../../xenomapper_b200/csrc/xm_tile.h"
 #include "../../xenomapper_b200/csrc/xm_walk.h"
+#include "../../xenomapper_b200/csrc/xm_stream.h"
+
+int64_t xm::xm_pread_all(int, void *, uint64_t, int64_t) { return -1; }     /* the emulation only streams from memory */
 
 namespace {
 
@@ -47,6 +50,9 @@ struct EmuBackend {
     int write(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
     int read(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
     int sync() { return 0; }
+    int upload(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
+    int upload_wait() { return 0; }
+    int copy_dd(void *d, const void *s, size_t n) { memmove(d, s, n); return 0; }
     void tick(int) {}
     float elapsed(int, int) { return 0.f; }
     std::string last_error() { return ""; }
@@ -83,6 +89,48 @@ extern "C" int xm_emu_classify(const void *prim, uint64_t plen, const void *sec,
     for (int b = 0; b < 6; ++b) o6[b] = (uint8_t *)out[b];
     const int rc = walk_resident(be, sc, StreamBuf{p.data(), plen}, StreamBuf{s.data(), slen}, *o, o6, cap, debug, res, msg);
     scratch_release(be, sc);
+    if (errbuf && errcap) { strncpy(errbuf, msg.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
+    return rc;
+}
+
+/* the chunked walk (xm_stream.h) over the emulated kernels: `chunk` new bytes per stream and step */
+extern "C" int xm_emu_classify_stream(const void *prim, uint64_t plen, const void *sec, uint64_t slen, const xm_opts *o,
+                                      uint32_t debug, uint64_t chunk, void *const out[6], const uint64_t cap[6], xm_result *res,
+                                      char *errbuf, size_t errcap)
+{
+    EmuBackend be;
+    Scratch sc;
+    HostIn in[2];
+    static const uint8_t nothing = 0;
+    in[0].mem = plen ? (const uint8_t *)prim : &nothing; in[0].len = plen;
+    in[1].mem = slen ? (const uint8_t *)sec : &nothing; in[1].len = slen;
+    StreamPlan plan;
+    plan.chunk = chunk;
+    const uint64_t dcap = 2 * chunk + 64;
+    std::vector<uint8_t> ibuf[2][2], obuf[2][6];
+    DevIn dev[2];
+    for (int s = 0; s < 2; ++s) {
+        for (int k = 0; k < 2; ++k) { ibuf[s][k].assign(dcap + 64, 0xEE); dev[s].buf[k] = ibuf[s][k].data(); }
+        dev[s].cap = dcap;
+    }
+    uint64_t ocap[6];
+    uint8_t *outs[2][6];
+    for (int b = 0; b < 6; ++b) {
+        ocap[b] = 4 * dcap + 64;
+        for (int k = 0; k < 2; ++k) { obuf[k][b].assign(ocap[b], 0); outs[k][b] = obuf[k][b].data(); }
+    }
+    uint64_t filled[6] = {0, 0, 0, 0, 0, 0};
+    bool overflow = false;
+    auto emit = [&](int, int b, const uint8_t *src, uint64_t n) {
+        if (filled[b] + n > cap[b]) { overflow = true; return; }
+        memcpy((uint8_t *)out[b] + filled[b], src, n);
+        filled[b] += n;
+    };
+    auto emit_wait = [&](int) {};
+    std::string msg;
+    int rc = walk_stream(be, sc, in, dev, outs, ocap, *o, debug, plan, emit, emit_wait, res, msg);
+    scratch_release(be, sc);
+    if (overflow) { rc = XM_ERR_ARG; msg = "test output buffer too small"; }
     if (errbuf && errcap) { strncpy(errbuf, msg.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
     return rc;
 }

@@ -37,3 +37,30 @@ def test_emulated_tiles_match_reference(case, variant):
     if variant.startswith("small") and case["input"]["kind"] == "synth" and case["input"]["seed"] != 1:
         pytest.skip("1 KiB-tile emulation of the large synthetic cases is covered by seed 1")
     check_case(case, VARIANTS[variant])
+
+
+@pytest.mark.parametrize("chunk", [600, 1000, 4096, 100000])
+@pytest.mark.parametrize("case", [c for c in G.CASES if not (c["input"]["kind"] == "synth" and c["input"]["n"] > 3000)],
+                         ids=lambda c: c["name"])
+def test_emulated_chunked_walk_matches_reference(case, chunk):
+    """the chunked walk (xm_stream.h: carry-over between chunks, halo record, end of walk) over the emulated kernels:
+    chunks of 600 bytes cut almost every record pair apart, 100000 bytes is a single step for most cases"""
+    p, s = G.case_records(case)
+    o = case["opts"]
+    e = case["expect"]
+    r = _emu.classify(p, s, mode=o["mode"], score_src=o["score_src"], skip_repeated=o["skip_repeated"],
+                      min_score=o["min_score"], enabled_bins=o["enabled_bins"], chunk=chunk)
+    if case["gpu"] == "unsupported":
+        assert r["status"] == 5, r["message"]
+        return
+    longest = max((len(x) for x in p.split(b"\n")), default=0)
+    if longest + 1 > chunk:
+        assert r["status"] in (5, G.ERR_CODE[e["error"]])      # a line that does not fit the staging buffer is refused, not mangled
+        if r["status"] == 5:
+            return
+    assert r["status"] == G.ERR_CODE[e["error"]], r["message"]
+    assert [len(x) for x in r["outputs"]] == e["records_len"]
+    assert [G.sha(x) for x in r["outputs"]] == e["records_sha256"]
+    if e["error"] is None:
+        assert G.counts_dict(r["counts"], o["mode"]) == e["counts"]
+        assert r["n_records"] == sum(e["counts"].values()) if o["mode"] == 0 else True

@@ -40,3 +40,13 @@ def test_cuda_matches_reference_golden(ctx, case, debug):
     if debug >= 2 and case["input"]["kind"] == "synth" and case["input"]["seed"] != 1:
         pytest.skip("covered by seed 1")
     run_case(ctx, case, debug)
+
+
+@pytest.mark.parametrize("chunk", [700, 5000])
+@pytest.mark.parametrize("case", [c for c in G.CASES if c["name"] != "adv_very_long_lines"], ids=lambda c: c["name"])
+def test_cuda_chunked_walk_matches_reference_golden(ctx, case, chunk, monkeypatch):
+    """xm_classify_host in many small steps (XM_CHUNK_BYTES): staging, carry-over, halo records and ordered bins on the device"""
+    if case["input"]["kind"] == "synth" and (case["input"]["seed"] != 1 or chunk < 5000):
+        pytest.skip("covered by seed 1 at the larger chunk")
+    monkeypatch.setenv("XM_CHUNK_BYTES", str(chunk))
+    run_case(ctx, case, 0)

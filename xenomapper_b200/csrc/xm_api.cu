@@ -21,6 +21,7 @@
 #include "xm_common.h"
 #include "xm_launch.h"
 #include "xm_walk.h"
+#include "xm_stream.h"
 
 using namespace xm;
 
@@ -28,6 +29,11 @@ static thread_local std::string g_create_error;
 
 struct DeviceBackend {
     cudaStream_t st = nullptr;
+    cudaStream_t up[2] = {nullptr, nullptr};      /* H2D lanes of the chunked walk, used alternately */
+    int up_next = 0;
+    int upload(void *d, const void *h, size_t n) { const int k = up_next; up_next ^= 1; return chk(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, up[k])); }
+    int upload_wait() { return chk(cudaStreamSynchronize(up[0])) || chk(cudaStreamSynchronize(up[1])); }
+    int copy_dd(void *d, const void *s, size_t n) { return chk(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st)) || chk(cudaStreamSynchronize(st)); }
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int chk(cudaError_t e)
@@ -76,9 +82,15 @@ struct xm_ctx {
     uint32_t debug = 0;
     std::string err;
     /* host-buffer walk: device staging and outputs, host outputs */
-    DevBuf d_in[2], d_out[6];
-    HostBuf h_out[6];
-    HostBuf h_stage[2];      /* pinned staging for pageable sources */
+    DevBuf d_in[2][2], d_out[2][6];     /* chunked walk: two input buffers per stream, two sets of six bin buffers */
+    HostBuf h_stage[2];      /* pinned staging for descriptor sources */
+    cudaStream_t dl = nullptr;          /* D2H lane */
+    /* the six bins on the host: pinned blocks filled in order; reused from call to call */
+    struct Block { uint8_t *p; uint64_t cap, len; };
+    std::vector<Block> pool;            /* free blocks */
+    std::vector<Block> bins[6];
+    std::vector<uint8_t> flat[6];       /* xm_get_output of a bin that spans several blocks */
+    uint64_t block_bytes = 0;
 };
 
 static int fail(xm_ctx *c, int code, const std::string &msg)
@@ -91,6 +103,18 @@ static int cuda_fail(xm_ctx *c, cudaError_t e, const char *what)
     return fail(c, XM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 #define XM_CUDA(c, call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail((c), e_, (what)); } while (0)
+
+int64_t xm::xm_pread_all(int fd, void *dst, uint64_t n, int64_t at)
+{
+    uint64_t got = 0;
+    while (got < n) {
+        const ssize_t r = pread(fd, (uint8_t *)dst + got, (size_t)std::min<uint64_t>(n - got, 1u << 30), (off_t)(at + (int64_t)got));
+        if (r < 0) { if (errno == EINTR) continue; return -1; }
+        if (r == 0) break;
+        got += (uint64_t)r;
+    }
+    return (int64_t)got;
+}
 
 extern "C" {
 
@@ -122,12 +146,14 @@ xm_ctx *xm_create(int device, uint32_t flags)
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->be.st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy_st[0], cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->copy_st[1], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&c->copy_st[1], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->dl, cudaStreamNonBlocking) != cudaSuccess) {
         g_create_error = "cudaStreamCreate failed";
         delete c;
         return nullptr;
     }
     for (int k = 0; k < 4; ++k) cudaEventCreate(&c->be.ev[k]);
+    c->be.up[0] = c->copy_st[0]; c->be.up[1] = c->copy_st[1];
     return c;
 }
 
@@ -137,10 +163,12 @@ void xm_destroy(xm_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->be.st);
     scratch_release(c->be, c->scratch);
-    for (auto &b : c->d_in) if (b.p) cudaFree(b.p);
-    for (auto &b : c->d_out) if (b.p) cudaFree(b.p);
-    for (auto &b : c->h_out) if (b.p) cudaFreeHost(b.p);
+    for (auto &s : c->d_in) for (auto &b : s) if (b.p) cudaFree(b.p);
+    for (auto &s : c->d_out) for (auto &b : s) if (b.p) cudaFree(b.p);
     for (auto &b : c->h_stage) if (b.p) cudaFreeHost(b.p);
+    for (auto &v : c->bins) for (auto &b : v) cudaFreeHost(b.p);
+    for (auto &b : c->pool) cudaFreeHost(b.p);
+    if (c->dl) cudaStreamDestroy(c->dl);
     for (int k = 0; k < 4; ++k) if (c->be.ev[k]) cudaEventDestroy(c->be.ev[k]);
     if (c->be.st) cudaStreamDestroy(c->be.st);
     for (auto s : c->copy_st) if (s) cudaStreamDestroy(s);
@@ -271,115 +299,178 @@ static void bin_bounds(uint64_t plen, uint64_t slen, int mode, uint32_t enabled,
     for (int k = 0; k < 6; ++k) cap[k] = ((enabled >> k) & 1u) ? b[k] : 0;
 }
 
-int xm_classify_host(xm_ctx *c, const void *prim, uint64_t prim_len, const void *sec, uint64_t sec_len,
-                     const xm_opts *opts, xm_result *res)
+/* ---- the chunked walk behind the host-buffer and the descriptor entry points ------------- */
+static uint64_t chunk_bytes()
 {
-    if (!c || !opts || !res) return XM_ERR_ARG;
+    const char *e = getenv("XM_CHUNK_BYTES");
+    if (e && *e) { const long long v = atoll(e); if (v > 0) return (uint64_t)v; }
+    e = getenv("XM_CHUNK_MB");
+    if (e && *e) { const long long v = atoll(e); if (v > 0) return (uint64_t)v << 20; }
+    return 256ull << 20;
+}
+
+static void recycle_bins(xm_ctx *c)
+{
+    for (auto &v : c->bins) { for (auto &b : v) { b.len = 0; c->pool.push_back(b); } v.clear(); }
+    for (auto &f : c->flat) f.clear();
+}
+
+/* room for n more bytes of bin b: the tail of its last block, then fresh blocks */
+static int bin_append_d2h(xm_ctx *c, int b, const uint8_t *d_src, uint64_t n)
+{
+    while (n) {
+        if (c->bins[b].empty() || c->bins[b].back().len == c->bins[b].back().cap) {
+            xm_ctx::Block blk{nullptr, 0, 0};
+            for (size_t k = 0; k < c->pool.size(); ++k)
+                if (c->pool[k].cap >= c->block_bytes) { blk = c->pool[k]; c->pool.erase(c->pool.begin() + (long)k); break; }
+            if (!blk.p) {
+                cudaError_t e = cudaHostAlloc((void **)&blk.p, c->block_bytes + 64, cudaHostAllocDefault);
+                if (e != cudaSuccess) { cudaGetLastError(); return fail(c, XM_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+                blk.cap = c->block_bytes;
+            }
+            blk.len = 0;
+            c->bins[b].push_back(blk);
+        }
+        xm_ctx::Block &k = c->bins[b].back();
+        const uint64_t m = std::min<uint64_t>(n, k.cap - k.len);
+        cudaError_t e = cudaMemcpyAsync(k.p + k.len, d_src, m, cudaMemcpyDeviceToHost, c->dl);
+        if (e != cudaSuccess) return cuda_fail(c, e, "D2H copy");
+        k.len += m; d_src += m; n -= m;
+    }
+    return XM_OK;
+}
+
+/* out_fds == nullptr: keep the bins in host blocks (xm_get_output); else append each step's bytes to the descriptors */
+static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opts *opts, xm_result *res)
+{
     cudaSetDevice(c->device);
-    for (auto &h : c->h_out) h.len = 0;
+    recycle_bins(c);
+    const uint64_t want = chunk_bytes();
+    const uint64_t longest = std::max(in[0].len, in[1].len);
+    StreamPlan plan;
+    plan.chunk = std::max<uint64_t>(std::min<uint64_t>(want, longest + 64), 64);
+    const uint64_t cap = 2 * plan.chunk + 64;
+    DevIn dev[2];
     int rc;
-    if ((rc = reserve_dev(c, c->d_in[0], prim_len)) || (rc = reserve_dev(c, c->d_in[1], sec_len))) return rc;
-    uint64_t cap[6];
-    bin_bounds(prim_len, sec_len, opts->mode, opts->enabled_bins, cap);
-    for (int b = 0; b < 6; ++b) if ((rc = reserve_dev(c, c->d_out[b], cap[b]))) return rc;
+    for (int s = 0; s < 2; ++s) {
+        for (int k = 0; k < 2; ++k) { if ((rc = reserve_dev(c, c->d_in[k][s], cap))) return rc; dev[s].buf[k] = c->d_in[k][s].p; }
+        dev[s].cap = cap;
+        if (!in[s].mem) {
+            if ((rc = reserve_host(c, c->h_stage[s], plan.chunk))) return rc;
+            in[s].stage = c->h_stage[s].p; in[s].stage_cap = plan.chunk;
+        }
+    }
+    uint64_t ocap[6];
+    bin_bounds(cap, cap, opts->mode, opts->enabled_bins, ocap);
+    uint8_t *outs[2][6];
+    for (int k = 0; k < 2; ++k)
+        for (int b = 0; b < 6; ++b) { if ((rc = reserve_dev(c, c->d_out[k][b], ocap[b]))) return rc; outs[k][b] = c->d_out[k][b].p; }
+    /* host blocks: a step's worth per block at most, small inputs get small blocks */
+    uint64_t bound[6];
+    bin_bounds(in[0].len, in[1].len, opts->mode, opts->enabled_bins, bound);
+    const uint64_t biggest = *std::max_element(bound, bound + 6);
+    c->block_bytes = std::max<uint64_t>(std::min<uint64_t>(biggest, 256ull << 20), 4096);
 
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, c->be.st);
-    /* the two record regions travel on two copy streams; the scan starts as soon as the secondary one has landed */
-    cudaEvent_t in_done[2];
-    const void *src[2] = {prim, sec};
-    const uint64_t len[2] = {prim_len, sec_len};
-    for (int k = 0; k < 2; ++k) {
-        cudaEventCreateWithFlags(&in_done[k], cudaEventDisableTiming);
-        cudaStreamWaitEvent(c->copy_st[k], e0, 0);
-        if (len[k]) {
-            cudaError_t e = cudaMemcpyAsync(c->d_in[k].p, src[k], len[k], cudaMemcpyHostToDevice, c->copy_st[k]);
-            if (e != cudaSuccess) return cuda_fail(c, e, "H2D copy");
+    int emit_rc = XM_OK;
+    auto emit = [&](int, int b, const uint8_t *d_src, uint64_t n) {
+        if (emit_rc) return;
+        emit_rc = bin_append_d2h(c, b, d_src, n);
+    };
+    auto flush_fds = [&]() -> int {
+        /* the descriptors take each step's bytes as soon as they are on the host; blocks are reused */
+        if (cudaStreamSynchronize(c->dl) != cudaSuccess) return fail(c, XM_ERR_CUDA, "D2H copy failed");
+        for (int b = 0; b < 6; ++b) {
+            for (auto &k : c->bins[b]) {
+                uint64_t done = 0;
+                while (out_fds[b] >= 0 && done < k.len) {
+                    const ssize_t w = write(out_fds[b], k.p + done, (size_t)std::min<uint64_t>(k.len - done, 1u << 30));
+                    if (w < 0) { if (errno == EINTR) continue; return fail(c, XM_ERR_IO, std::string("write: ") + strerror(errno)); }
+                    done += (uint64_t)w;
+                }
+                k.len = 0;
+                c->pool.push_back(k);
+            }
+            c->bins[b].clear();
         }
-        cudaEventRecord(in_done[k], c->copy_st[k]);
-        cudaStreamWaitEvent(c->be.st, in_done[k], 0);
-    }
-    uint8_t *o6[6];
-    for (int b = 0; b < 6; ++b) o6[b] = c->d_out[b].p;
+        return XM_OK;
+    };
+    int wait_rc = XM_OK;
+    auto emit_wait = [&](int) {
+        if (wait_rc) return;
+        if (out_fds) wait_rc = flush_fds();
+        else if (cudaStreamSynchronize(c->dl) != cudaSuccess) wait_rc = fail(c, XM_ERR_CUDA, "D2H copy failed");
+    };
     std::string msg;
-    rc = walk_resident(c->be, c->scratch, StreamBuf{c->d_in[0].p, prim_len}, StreamBuf{c->d_in[1].p, sec_len}, *opts, o6, cap, c->debug, res, msg);
+    rc = walk_stream(c->be, c->scratch, in, dev, outs, ocap, *opts, c->debug, plan, emit, emit_wait, res, msg);
     c->err = msg;
-    for (int k = 0; k < 2; ++k) cudaEventDestroy(in_done[k]);
-    if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM || rc == XM_ERR_ARG) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
-    /* bring the bins back (also after a failing record: everything before it was written) */
-    for (int b = 0; b < 6; ++b) {
-        const uint64_t n = res->out_len[b];
-        int r2 = reserve_host(c, c->h_out[b], n);
-        if (r2) return r2;
-        if (n) {
-            cudaError_t e = cudaMemcpyAsync(c->h_out[b].p, c->d_out[b].p, n, cudaMemcpyDeviceToHost, c->copy_st[b & 1]);
-            if (e != cudaSuccess) return cuda_fail(c, e, "D2H copy");
-        }
-        c->h_out[b].len = n;
+    if (emit_rc) rc = emit_rc;
+    if (wait_rc) rc = wait_rc;
+    if (rc != XM_ERR_CUDA && rc != XM_ERR_NOMEM) {
+        if (out_fds) { const int r2 = flush_fds(); if (r2) rc = r2; }
+        else if (cudaStreamSynchronize(c->dl) != cudaSuccess) rc = fail(c, XM_ERR_CUDA, "D2H copy failed");
     }
-    for (int k = 0; k < 2; ++k) XM_CUDA(c, cudaStreamSynchronize(c->copy_st[k]), "D2H copy");
     cudaEventRecord(e1, c->be.st);
     cudaEventSynchronize(e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    res->ms_total = ms;
+    res->ms_total = ms;                 /* the whole call: staging, kernels, the bins back on the host */
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
+}
+
+int xm_classify_host(xm_ctx *c, const void *prim, uint64_t prim_len, const void *sec, uint64_t sec_len,
+                     const xm_opts *opts, xm_result *res)
+{
+    if (!c || !opts || !res) return XM_ERR_ARG;
+    HostIn in[2];
+    in[0].mem = (const uint8_t *)prim; in[0].len = prim_len;
+    in[1].mem = (const uint8_t *)sec; in[1].len = sec_len;
+    static const uint8_t nothing = 0;
+    if (!in[0].mem) in[0].mem = &nothing;
+    if (!in[1].mem) in[1].mem = &nothing;
+    return stream_walk(c, in, nullptr, opts, res);
 }
 
 int xm_get_output(xm_ctx *c, int bin, const void **data, uint64_t *len)
 {
     if (!c || bin < 0 || bin > 5 || !data || !len) return XM_ERR_ARG;
-    *data = c->h_out[bin].p;
-    *len = c->h_out[bin].len;
+    auto &v = c->bins[bin];
+    if (v.empty()) { *data = nullptr; *len = 0; return XM_OK; }
+    if (v.size() == 1) { *data = v[0].p; *len = v[0].len; return XM_OK; }
+    if (c->flat[bin].empty()) {
+        uint64_t n = 0;
+        for (auto &b : v) n += b.len;
+        c->flat[bin].resize(n);
+        uint64_t at = 0;
+        for (auto &b : v) { memcpy(c->flat[bin].data() + at, b.p, b.len); at += b.len; }
+    }
+    *data = c->flat[bin].data();
+    *len = c->flat[bin].size();
     return XM_OK;
 }
 
 /* ---- file-descriptor walk ---------------------------------------------------------- */
-static int read_all(int fd, int64_t off, std::vector<uint8_t> &out, HostBuf &pinned, xm_ctx *c, uint64_t &n_out)
-{
-    const off_t end = lseek(fd, 0, SEEK_END);
-    if (end < 0) return fail(c, XM_ERR_IO, std::string("input must be seekable: ") + strerror(errno));
-    const uint64_t n = (uint64_t)end > (uint64_t)off ? (uint64_t)end - (uint64_t)off : 0;
-    int rc = reserve_host(c, pinned, n);
-    if (rc) return rc;
-    uint64_t got = 0;
-    while (got < n) {
-        ssize_t r = pread(fd, pinned.p + got, (size_t)std::min<uint64_t>(n - got, 1u << 30), (off_t)(off + (int64_t)got));
-        if (r < 0) { if (errno == EINTR) continue; return fail(c, XM_ERR_IO, std::string("pread: ") + strerror(errno)); }
-        if (r == 0) break;
-        got += (uint64_t)r;
-    }
-    (void)out;
-    n_out = got;
-    return XM_OK;
-}
-
 int xm_classify_fds(xm_ctx *c, int fd_prim, int64_t off_prim, int fd_sec, int64_t off_sec, const int out_fds[6],
                     const xm_opts *opts, xm_result *res)
 {
     if (!c || !opts || !res || !out_fds) return XM_ERR_ARG;
-    std::vector<uint8_t> unused;
-    uint64_t np = 0, ns = 0;
-    int rc;
-    if ((rc = read_all(fd_prim, off_prim, unused, c->h_stage[0], c, np)) || (rc = read_all(fd_sec, off_sec, unused, c->h_stage[1], c, ns))) return rc;
+    HostIn in[2];
+    const int fds[2] = {fd_prim, fd_sec};
+    const int64_t offs[2] = {off_prim, off_sec};
+    for (int s = 0; s < 2; ++s) {
+        const off_t end = lseek(fds[s], 0, SEEK_END);
+        if (end < 0) return fail(c, XM_ERR_IO, std::string("input must be seekable: ") + strerror(errno));
+        in[s].fd = fds[s]; in[s].off = offs[s];
+        in[s].len = (uint64_t)end > (uint64_t)offs[s] ? (uint64_t)end - (uint64_t)offs[s] : 0;
+    }
     xm_opts o = *opts;
     uint32_t en = 0;
     for (int b = 0; b < 6; ++b) if (out_fds[b] >= 0) en |= 1u << b;
     o.enabled_bins = en;
-    rc = xm_classify_host(c, c->h_stage[0].p, np, c->h_stage[1].p, ns, &o, res);
-    if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM || rc == XM_ERR_ARG) return rc;
-    for (int b = 0; b < 6; ++b) {
-        if (out_fds[b] < 0) continue;
-        uint64_t done = 0;
-        while (done < c->h_out[b].len) {
-            ssize_t w = write(out_fds[b], c->h_out[b].p + done, (size_t)std::min<uint64_t>(c->h_out[b].len - done, 1u << 30));
-            if (w < 0) { if (errno == EINTR) continue; return fail(c, XM_ERR_IO, std::string("write: ") + strerror(errno)); }
-            done += (uint64_t)w;
-        }
-    }
-    return rc;
+    return stream_walk(c, in, out_fds, &o, res);
 }
 
 /* ---- counting pass of the sharded walk ------------------------------------------------ */

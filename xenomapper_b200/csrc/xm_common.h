@@ -109,6 +109,9 @@ struct ClassifyArgs {
     long long thr;                    /* AS > min_score  <=>  AS >= thr */
     uint32_t enabled;
     uint64_t limit;                   /* records >= limit are dropped (error re-run) */
+    uint64_t *p_start;                /* [sc_cap] byte offset of every yielded primary record, or null (chunked walks carry the tail over) */
+    uint64_t p_start_cap;
+    int32_t halo;                     /* record 0 was the last record of the previous chunk: context only, not classified again */
     uint8_t *out[6];
     uint64_t out_cap[6];
     uint32_t debug;

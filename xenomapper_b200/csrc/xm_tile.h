@@ -838,6 +838,7 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
             if (gi == a.limit) a.g->limit_off = fr.geo.g0 + L.s;
             if (gi >= ncap) th.rank = NOT_YIELDED;
             else {
+                if (a.p_start && gi < a.p_start_cap) a.p_start[gi] = fr.geo.g0 + L.s;
                 const uint4 sr = a.sc.rec[gi];
                 const uint32_t smeta = a.sc.meta[gi];
                 const uint32_t sflags = smeta >> META_LEN_BITS;
@@ -851,7 +852,7 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
                 const int st = mapping_state(L.as, L.xs, (int32_t)sr.x, (int32_t)sr.y, a.thr);
                 th.sraw = L.rawbytes;
                 if (!paired) {
-                    if (!ec) {
+                    if (!ec && !(a.halo && gi == 0)) {
                         if (ev) report_error(a.g, gi, ev, evs);
                         else {
                             key = (uint32_t)st;

@@ -149,6 +149,8 @@ struct Scratch {
     uint64_t cap_tiles_s = 0, cap_tiles_p = 0;
     SCompact sc{nullptr, nullptr, nullptr};
     uint64_t sc_cap = 0;
+    uint64_t *p_start = nullptr;       /* chunked walks: byte offset of every yielded primary record */
+    uint64_t p_start_cap = 0;
     Globals *g = nullptr;
 };
 
@@ -157,7 +159,7 @@ inline void scratch_release(BE &be, Scratch &s)
 {
     be.release(s.chain1_s); be.release(s.chain1_p); be.release(s.chain2);
     be.release(s.sc.start); be.release(s.sc.rec); be.release(s.sc.meta);
-    be.release(s.g);
+    be.release(s.g); be.release(s.p_start);
     s = Scratch();
 }
 
@@ -223,6 +225,16 @@ inline uint64_t prev_line_off(BE &be, const StreamBuf &B, uint64_t off)
     return 0;
 }
 
+/* chunked walks (xm_stream.h): what the resident walk is told about its buffers and what it reports back */
+struct WalkCtl {
+    int halo = 0;                      /* record 0 of both buffers is the previous step's last record: context only */
+    bool want_tail = false;            /* report the offsets below */
+    uint64_t n_stream[2] = {0, 0};     /* records in each buffer (before its first blank line) */
+    bool stopped[2] = {false, false};  /* a blank line ends the stream inside the buffer */
+    uint64_t end_off[2] = {0, 0};      /* byte offset just past the last counted record of each buffer */
+    uint64_t last_p = 0, last_s = 0;   /* byte offset of the last yielded record in each buffer */
+};
+
 struct WalkTimes {
     float ms_scan = 0, ms_classify = 0, ms_total = 0;
     uint32_t launches = 0;
@@ -234,7 +246,8 @@ struct WalkTimes {
  */
 template <class BE>
 inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBuf &S, const xm_opts &o,
-                         uint8_t *const out[6], const uint64_t out_cap[6], uint32_t debug, xm_result *res, std::string &errmsg)
+                         uint8_t *const out[6], const uint64_t out_cap[6], uint32_t debug, xm_result *res, std::string &errmsg,
+                         WalkCtl *ctl = nullptr)
 {
     memset(res, 0, sizeof *res);
     res->err_stream = -1;
@@ -263,6 +276,12 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
             sc_need = (uint64_t)((double)S.len / mean * 1.05) + 4096;
         }
         if (!scratch_reserve(be, sc, nt_s, nt_p, sc_need)) { errmsg = "out of device memory for scratch"; return res->status = XM_ERR_NOMEM; }
+        if (ctl && ctl->want_tail && sc.p_start_cap < sc.sc_cap) {
+            be.release(sc.p_start);
+            sc.p_start = (uint64_t *)be.alloc(sc.sc_cap * 8 + 16);
+            if (!sc.p_start) { sc.p_start_cap = 0; errmsg = "out of device memory for scratch"; return res->status = XM_ERR_NOMEM; }
+            sc.p_start_cap = sc.sc_cap;
+        }
         Globals init;
         memset(&init, 0, sizeof init);
         init.err = NO_ERROR;
@@ -281,6 +300,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         ca.g = sc.g; ca.ntiles = (uint32_t)nt_p; ca.mode = o.mode; ca.score_src = o.score_src; ca.skip = sa.skip;
         ca.thr = score_threshold(o.min_score); ca.enabled = o.enabled_bins & 0x3f; ca.limit = limit; ca.debug = debug;
         for (int b = 0; b < 6; ++b) { ca.out[b] = out[b]; ca.out_cap[b] = ((ca.enabled >> b) & 1u) ? out_cap[b] : 0; }
+        if (ctl) { ca.halo = ctl->halo; if (ctl->want_tail) { ca.p_start = sc.p_start; ca.p_start_cap = sc.p_start_cap; } }
 
         be.tick(3);
         if (be.scan(sa, small)) { errmsg = "scan kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
@@ -319,6 +339,18 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
     unsigned long long n = G.n_stream[0] < G.n_stream[1] ? G.n_stream[0] : G.n_stream[1];
     if (limit < n) n = limit;
     res->n_records = n;
+    if (ctl) {
+        for (int k = 0; k < 2; ++k) {
+            ctl->n_stream[k] = G.n_stream[k];
+            ctl->end_off[k] = G.end_off[k];
+            ctl->stopped[k] = G.end_off[k] < (k ? S.len : P.len);
+        }
+        if (ctl->want_tail && n > 0) {
+            unsigned long long v = 0;
+            be.read(&v, sc.p_start + (n - 1), 8); ctl->last_p = v;
+            be.read(&v, sc.sc.start + (n - 1), 8); ctl->last_s = v;
+        }
+    }
     for (int k = 0; k < 36; ++k) res->counts[k] = G.counts[k];
     for (int b = 0; b < 6; ++b) res->out_len[b] = G.out_len[b];
     res->bytes_in[0] = G.bytes_in[0];
