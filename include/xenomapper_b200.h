@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define XM_ABI_VERSION 1
+#define XM_ABI_VERSION 2
 
 /* States and bins share one numbering: the order of the reference's output
  * arguments (xm.py:291-297).  counts[] is indexed [state] for single-end and
@@ -72,10 +72,16 @@ enum xm_status {
     XM_ERR_IO = 9
 };
 
+#define XM_READER_SKIP_REPEATED 1
+#define XM_READER_FIRST_IS_CONTEXT 2
+
 typedef struct xm_opts {
     int32_t mode;            /* enum xm_mode */
     int32_t score_src;       /* enum xm_score_src */
-    int32_t skip_repeated;   /* getReadPairs(skip_repeated_reads=...), xm.py:110; the CLI sets it for SE (xm.py:691) */
+    int32_t skip_repeated;   /* reader flags.  Bit 0 (XM_READER_SKIP_REPEATED): getReadPairs(skip_repeated_reads=True), xm.py:110;
+                                the CLI sets it for SE (xm.py:691).  Bit 1 (XM_READER_FIRST_IS_CONTEXT): record 0 of both inputs
+                                is the record before the caller's range (sharded walks): it is the predecessor the pair predicate
+                                (xm.py:402) and the run-skipping reader look at, and is neither classified nor counted. */
     uint32_t enabled_bins;   /* bit b: bin b has an output.  Disabled bins still count (xm.py:330-349) */
     double min_score;        /* --min_score; -inf default (xm.py:298) */
 } xm_opts;
@@ -141,17 +147,22 @@ int xm_classify_fds(xm_ctx *ctx, int fd_prim, int64_t off_prim, int fd_sec, int6
 
 /* ---- sharded walk (one process per GPU) -------------------------------- */
 
-/* Counting pass: how many records (after skip_repeated de-duplication if set)
- * a byte range holds, where its first record starts, and whether a blank line
- * ends the stream inside it.  Ranks exchange these 4 words (NCCL allgather in
- * bench.py / the shim) to turn byte shards into record-index shards. */
+/* Index pass over one resident byte range that starts at a record boundary:
+ * how many records it yields (after skip_repeated de-duplication if set, the
+ * reader of xm.py:95-118) and whether a blank line ends the stream inside it
+ * (xm.py:105).  Ranks exchange these words (all-gather, xenomapper_b200/
+ * sharded.py) to turn byte shards into record-index shards. */
 typedef struct xm_shard_info {
-    uint64_t n_records;      /* records that START in [begin, end) */
-    uint64_t first_start;    /* byte offset (in the whole stream) of the first of them, or end */
-    uint64_t stop_at;        /* index within this shard of the first blank line, or UINT64_MAX */
-    uint64_t reserved;
+    uint64_t n_records;      /* records the range yields */
+    uint64_t first_start;    /* 0: the range starts at a record boundary */
+    uint64_t stop_at;        /* == n_records when a blank line ends the stream inside the range, else UINT64_MAX */
+    uint64_t end_off;        /* byte offset just past the last counted record (the blank line's offset when the stream stops) */
 } xm_shard_info;
 int xm_count_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repeated, xm_shard_info *info);
+/* Byte offsets (in the buffer) at which the records with the given indices start; `len` for indices at or past
+ * the buffer's record count.  With the counts above this turns record-index partition points into byte ranges. */
+int xm_locate_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repeated, uint32_t n_queries,
+                     const uint64_t *record_index, uint64_t *byte_offset);
 
 /* ---- device memory helpers (so bindings need no CUDA of their own) ----- */
 int xm_dev_alloc(xm_ctx *ctx, uint64_t bytes, void **d_ptr);

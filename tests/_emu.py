@@ -23,6 +23,10 @@ class Result(C.Structure):
                 ("ms_total", C.c_float), ("n_launches", C.c_uint32)]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("first_start", C.c_uint64), ("stop_at", C.c_uint64), ("end_off", C.c_uint64)]
+
+
 _lib = None
 
 
@@ -41,11 +45,29 @@ def lib():
                                                 C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Result),
                                                 C.c_char_p, C.c_size_t]
         _lib.xm_emu_classify_stream.restype = C.c_int
+        _lib.xm_emu_index.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_uint64), C.POINTER(ShardInfo), C.c_char_p, C.c_size_t]
+        _lib.xm_emu_index.restype = C.c_int
     return _lib
 
 
+def index(buf, record_indices=(), skip_repeated=False, debug=0):
+    """index pass of the sharded walk: (ShardInfo, byte offsets of the queried records)"""
+    L = lib()
+    buf = bytes(buf)
+    n = len(record_indices)
+    q = (C.c_uint64 * max(1, n))(*record_indices)
+    off = (C.c_uint64 * max(1, n))()
+    info = ShardInfo()
+    err = C.create_string_buffer(512)
+    rc = L.xm_emu_index(buf, len(buf), int(bool(skip_repeated)), debug, n, q, off, C.byref(info), err, 512)
+    if rc:
+        raise RuntimeError("xm_emu_index failed (%d): %s" % (rc, err.value.decode()))
+    return info, list(off)[:n]
+
+
 def classify(prim, sec, mode=0, score_src=0, skip_repeated=False, min_score=float("-inf"), enabled_bins=0x3F,
-             debug=0, cap=None, chunk=None):
+             debug=0, cap=None, chunk=None, first_is_context=False):
     """chunk: run the chunked walk (xm_stream.h) with that many new bytes per stream and step"""
     L = lib()
     prim, sec = bytes(prim), bytes(sec)
@@ -54,7 +76,7 @@ def classify(prim, sec, mode=0, score_src=0, skip_repeated=False, min_score=floa
     bufs = [C.create_string_buffer(cap) for _ in range(6)]
     outp = (C.c_void_p * 6)(*[C.cast(b, C.c_void_p) for b in bufs])
     caps = (C.c_uint64 * 6)(*([cap] * 6))
-    o = Opts(mode, score_src, int(bool(skip_repeated)), enabled_bins, min_score)
+    o = Opts(mode, score_src, int(bool(skip_repeated)) | (2 if first_is_context else 0), enabled_bins, min_score)
     r = Result()
     err = C.create_string_buffer(512)
     if chunk:

@@ -87,7 +87,13 @@ extern "C" int xm_emu_classify(const void *prim, uint64_t plen, const void *sec,
     std::string msg;
     uint8_t *o6[6];
     for (int b = 0; b < 6; ++b) o6[b] = (uint8_t *)out[b];
-    const int rc = walk_resident(be, sc, StreamBuf{p.data(), plen}, StreamBuf{s.data(), slen}, *o, o6, cap, debug, res, msg);
+    /* bit 1 of the reader flags: record 0 is context (sharded walks), exactly as xm_classify_device decodes it */
+    WalkCtl ctl;
+    ctl.halo = (o->skip_repeated >> 1) & 1;
+    xm_opts oo = *o;
+    oo.skip_repeated &= 1;
+    const int rc = walk_resident(be, sc, StreamBuf{p.data(), plen}, StreamBuf{s.data(), slen}, oo, o6, cap, debug, res, msg, &ctl);
+    if (ctl.halo && res->n_records) res->n_records -= 1;
     scratch_release(be, sc);
     if (errbuf && errcap) { strncpy(errbuf, msg.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
     return rc;
@@ -131,6 +137,22 @@ extern "C" int xm_emu_classify_stream(const void *prim, uint64_t plen, const voi
     int rc = walk_stream(be, sc, in, dev, outs, ocap, *o, debug, plan, emit, emit_wait, res, msg);
     scratch_release(be, sc);
     if (overflow) { rc = XM_ERR_ARG; msg = "test output buffer too small"; }
+    if (errbuf && errcap) { strncpy(errbuf, msg.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
+    return rc;
+}
+
+
+/* the index pass of the sharded walk (xm_walk.h index_resident) over the emulated scan kernel */
+extern "C" int xm_emu_index(const void *buf, uint64_t len, int skip, uint32_t debug, uint32_t nq, const uint64_t *q, uint64_t *off,
+                            xm_shard_info *info, char *errbuf, size_t errcap)
+{
+    std::vector<uint8_t> b(len + 64, 0xEE);
+    if (len) memcpy(b.data(), buf, len);
+    EmuBackend be;
+    Scratch sc;
+    std::string msg;
+    const int rc = index_resident(be, sc, StreamBuf{b.data(), len}, skip != 0, debug, nq, q, off, info, msg);
+    scratch_release(be, sc);
     if (errbuf && errcap) { strncpy(errbuf, msg.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
     return rc;
 }

@@ -21,7 +21,7 @@ DEBUG_FORCE_GENERIC, DEBUG_SMALL_TILES = 1, 2
 EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_classify_device",
            "xm_classify_host", "xm_get_output", "xm_classify_fds", "xm_count_device", "xm_dev_alloc",
            "xm_dev_free", "xm_host_alloc_pinned", "xm_host_free_pinned", "xm_memcpy_h2d", "xm_memcpy_d2h",
-           "xm_memcpy_d2d", "xm_dev_mem_info", "xm_set_debug")
+           "xm_memcpy_d2d", "xm_dev_mem_info", "xm_set_debug", "xm_locate_device")
 
 
 class Opts(C.Structure):
@@ -38,7 +38,7 @@ class Result(C.Structure):
 
 class ShardInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("first_start", C.c_uint64), ("stop_at", C.c_uint64),
-                ("reserved", C.c_uint64)]
+                ("end_off", C.c_uint64)]
 
 
 class XenomapperLibraryError(RuntimeError):
@@ -74,6 +74,7 @@ def load():
     L.xm_get_output.argtypes = [vp, i, C.POINTER(vp), C.POINTER(u64)]
     L.xm_classify_fds.argtypes = [vp, i, C.c_int64, i, C.c_int64, C.POINTER(i), C.POINTER(Opts), C.POINTER(Result)]
     L.xm_count_device.argtypes = [vp, vp, u64, i, C.POINTER(ShardInfo)]
+    L.xm_locate_device.argtypes = [vp, vp, u64, i, C.c_uint32, C.POINTER(u64), C.POINTER(u64)]
     L.xm_dev_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     L.xm_dev_free.argtypes = [vp, vp]
     L.xm_host_alloc_pinned.argtypes = [vp, u64, C.POINTER(vp)]
@@ -168,8 +169,9 @@ class Context:
 
     # ---- walks --------------------------------------------------------------
     @staticmethod
-    def opts(mode=MODE_SE, score_src=SCORE_AS_XS, skip_repeated=False, min_score=float("-inf"), enabled_bins=0x3F):
-        return Opts(mode, score_src, int(bool(skip_repeated)), enabled_bins, min_score)
+    def opts(mode=MODE_SE, score_src=SCORE_AS_XS, skip_repeated=False, min_score=float("-inf"), enabled_bins=0x3F,
+             first_is_context=False):
+        return Opts(mode, score_src, int(bool(skip_repeated)) | (2 if first_is_context else 0), enabled_bins, min_score)
 
     def classify_device(self, d_prim, prim_len, d_sec, sec_len, opts, d_out, out_cap):
         res = Result()
@@ -207,6 +209,13 @@ class Context:
         info = ShardInfo()
         self._check(self.lib.xm_count_device(self.h, d_buf, n, int(bool(skip_repeated)), C.byref(info)), "xm_count_device")
         return info
+
+
+    def locate_device(self, d_buf, n, record_indices, skip_repeated=False):
+        q = (C.c_uint64 * len(record_indices))(*record_indices)
+        out = (C.c_uint64 * len(record_indices))()
+        self._check(self.lib.xm_locate_device(self.h, d_buf, n, int(bool(skip_repeated)), len(record_indices), q, out), "xm_locate_device")
+        return list(out)
 
 
 _default_ctx = None

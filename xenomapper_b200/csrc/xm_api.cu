@@ -260,8 +260,13 @@ int xm_classify_device(xm_ctx *c, const void *d_prim, uint64_t prim_len, const v
     uint64_t cap6[6];
     for (int b = 0; b < 6; ++b) { o6[b] = d_out ? (uint8_t *)d_out[b] : nullptr; cap6[b] = (out_cap && o6[b]) ? out_cap[b] : 0; }
     std::string msg;
+    WalkCtl ctl;
+    ctl.halo = (opts->skip_repeated >> 1) & 1;
+    xm_opts o = *opts;
+    o.skip_repeated &= 1;
     const int rc = walk_resident(c->be, c->scratch, StreamBuf{(const uint8_t *)d_prim, prim_len}, StreamBuf{(const uint8_t *)d_sec, sec_len},
-                                 *opts, o6, cap6, c->debug, res, msg);
+                                 o, o6, cap6, c->debug, res, msg, &ctl);
+    if (ctl.halo && res->n_records) res->n_records -= 1;
     c->err = msg;
     return rc;
 }
@@ -404,7 +409,9 @@ static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opt
         else if (cudaStreamSynchronize(c->dl) != cudaSuccess) wait_rc = fail(c, XM_ERR_CUDA, "D2H copy failed");
     };
     std::string msg;
-    rc = walk_stream(c->be, c->scratch, in, dev, outs, ocap, *opts, c->debug, plan, emit, emit_wait, res, msg);
+    xm_opts o = *opts;
+    o.skip_repeated &= 1;
+    rc = walk_stream(c->be, c->scratch, in, dev, outs, ocap, o, c->debug, plan, emit, emit_wait, res, msg, (opts->skip_repeated >> 1) & 1);
     c->err = msg;
     if (emit_rc) rc = emit_rc;
     if (wait_rc) rc = wait_rc;
@@ -473,36 +480,27 @@ int xm_classify_fds(xm_ctx *c, int fd_prim, int64_t off_prim, int fd_sec, int64_
     return stream_walk(c, in, out_fds, &o, res);
 }
 
-/* ---- counting pass of the sharded walk ------------------------------------------------ */
+/* ---- index pass of the sharded walk (xm_walk.h index_resident) ---------------------------- */
 int xm_count_device(xm_ctx *c, const void *d_buf, uint64_t len, int skip_repeated, xm_shard_info *info)
 {
     if (!c || !info) return XM_ERR_ARG;
     cudaSetDevice(c->device);
-    memset(info, 0, sizeof *info);
-    info->stop_at = ~0ull;
-    info->first_start = 0;
-    if (!len) return XM_OK;
-    const bool small = (c->debug & DBG_SMALL_TILES) != 0;
-    const uint64_t tile = tile_bytes(small);
-    const uint64_t nt = (len + tile - 1) / tile;
-    if (!scratch_reserve(c->be, c->scratch, nt, 0, 0)) return fail(c, XM_ERR_NOMEM, "out of device memory for scratch");
-    Globals init;
-    memset(&init, 0, sizeof init);
-    init.err = NO_ERROR;
-    if (c->be.write(c->scratch.g, &init, sizeof init) || c->be.zero(c->scratch.chain1_s, nt * 8)) return fail(c, XM_ERR_CUDA, c->be.err);
-    ScanArgs sa;
-    memset(&sa, 0, sizeof sa);
-    sa.S = StreamBuf{(const uint8_t *)d_buf, len};
-    sa.sc = c->scratch.sc; sa.sc_cap = 0;
-    sa.chain1 = c->scratch.chain1_s; sa.g = c->scratch.g; sa.ntiles = (uint32_t)nt;
-    sa.skip = skip_repeated ? 1 : 0; sa.stream_id = 1; sa.debug = c->debug;
-    if (c->be.scan(sa, small) || c->be.sync()) return fail(c, XM_ERR_CUDA, "count kernel failed: " + c->be.err);
-    Globals G;
-    if (c->be.read(&G, c->scratch.g, sizeof G)) return fail(c, XM_ERR_CUDA, c->be.err);
-    if (G.overflow) return fail(c, XM_ERR_UNSUPPORTED, "lines shorter than 64 bytes on average: count with XM_DEBUG_SMALL_TILES");
-    info->n_records = G.n_stream[1];
-    if (G.end_off[1] < len) info->stop_at = G.n_stream[1];
-    return XM_OK;
+    std::string msg;
+    const int rc = index_resident(c->be, c->scratch, StreamBuf{(const uint8_t *)d_buf, len}, skip_repeated != 0, c->debug, 0, nullptr, nullptr, info, msg);
+    c->err = msg;
+    return rc;
+}
+
+int xm_locate_device(xm_ctx *c, const void *d_buf, uint64_t len, int skip_repeated, uint32_t n_queries,
+                     const uint64_t *record_index, uint64_t *byte_offset)
+{
+    if (!c || (n_queries && (!record_index || !byte_offset))) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    xm_shard_info info;
+    std::string msg;
+    const int rc = index_resident(c->be, c->scratch, StreamBuf{(const uint8_t *)d_buf, len}, skip_repeated != 0, c->debug, n_queries, record_index, byte_offset, &info, msg);
+    c->err = msg;
+    return rc;
 }
 
 }  // extern "C"

@@ -79,13 +79,13 @@ int64_t xm_pread_all(int fd, void *dst, uint64_t n, int64_t at);      /* xm_api.
 template <class BE, class Emit, class EmitWait>
 inline int walk_stream(BE &be, Scratch &sc, HostIn in[2], DevIn dev[2], uint8_t *const outs[2][6], const uint64_t out_cap[6],
                        const xm_opts &o, uint32_t debug, const StreamPlan &plan, Emit emit, EmitWait emit_wait,
-                       xm_result *res, std::string &errmsg)
+                       xm_result *res, std::string &errmsg, int first_is_context = 0)
 {
     memset(res, 0, sizeof *res);
     res->err_stream = -1;
     uint64_t carry_off[2] = {0, 0}, carry_len[2] = {0, 0};      /* in the previous buffer */
     bool final_sent[2] = {false, false};
-    int halo = 0;
+    int halo = first_is_context ? 1 : 0;                      /* sharded walks: the caller's buffers open with the record before its range */
     for (uint64_t step = 0;; ++step) {
         const int cur = (int)(step & 1), prev = cur ^ 1;
         /* stage: carry to the front, new bytes behind it */

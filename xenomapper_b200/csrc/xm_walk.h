@@ -395,4 +395,56 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
     return res->status = status;
 }
 
+/*
+ * Index pass of the sharded walk: scans one resident byte range that starts at a record boundary and reports how
+ * many records it yields (run heads only with skip), whether a blank line ends the stream inside it, and -- for
+ * each queried record index -- the byte offset at which that record starts (the offset just past the last
+ * counted record for indices at or beyond the count).
+ */
+template <class BE>
+inline int index_resident(BE &be, Scratch &sc, const StreamBuf &B, bool skip, uint32_t debug, uint32_t n_queries,
+                          const uint64_t *record_index, uint64_t *byte_offset, xm_shard_info *info, std::string &errmsg)
+{
+    memset(info, 0, sizeof *info);
+    info->stop_at = ~0ull;
+    for (uint32_t q = 0; q < n_queries; ++q) byte_offset[q] = 0;
+    if (!B.len) return XM_OK;
+    bool small = (debug & DBG_SMALL_TILES) != 0;
+    uint64_t need = n_queries ? B.len / 64 + 4096 : 0;         /* per-record arrays are only needed to answer queries */
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        const uint64_t tile = small ? (uint64_t)CfgSmall::TILE : (uint64_t)CfgBig::TILE;
+        const uint64_t nt = (B.len + tile - 1) / tile;
+        if (nt > 0xffffffffull) { errmsg = "stream too large for one call"; return XM_ERR_ARG; }
+        if (!scratch_reserve(be, sc, nt, 0, need)) { errmsg = "out of device memory for scratch"; return XM_ERR_NOMEM; }
+        Globals init;
+        memset(&init, 0, sizeof init);
+        init.err = NO_ERROR;
+        if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt * 8)) { errmsg = "scratch init failed: " + be.last_error(); return XM_ERR_CUDA; }
+        ScanArgs sa;
+        memset(&sa, 0, sizeof sa);
+        sa.S = B; sa.sc = sc.sc; sa.sc_cap = n_queries ? sc.sc_cap : 0;
+        sa.chain1 = sc.chain1_s; sa.g = sc.g; sa.ntiles = (uint32_t)nt;
+        sa.skip = skip ? 1 : 0; sa.stream_id = 1; sa.debug = debug;
+        if (be.scan(sa, small) || be.sync()) { errmsg = "index kernel failed: " + be.last_error(); return XM_ERR_CUDA; }
+        Globals G;
+        if (be.read(&G, sc.g, sizeof G)) { errmsg = "result read failed: " + be.last_error(); return XM_ERR_CUDA; }
+        if (G.overflow && !small) { small = true; continue; }
+        if (n_queries && G.n_stream[1] > sc.sc_cap) { need = G.n_stream[1] + 1; continue; }
+        info->n_records = G.n_stream[1];
+        info->first_start = 0;
+        info->end_off = G.end_off[1];
+        if (G.end_off[1] < B.len) info->stop_at = G.n_stream[1];
+        for (uint32_t q = 0; q < n_queries; ++q) {
+            if (record_index[q] < G.n_stream[1]) {
+                unsigned long long v = 0;
+                if (be.read(&v, sc.sc.start + record_index[q], 8)) { errmsg = "result read failed: " + be.last_error(); return XM_ERR_CUDA; }
+                byte_offset[q] = v;
+            } else byte_offset[q] = G.end_off[1];
+        }
+        return XM_OK;
+    }
+    errmsg = "record arrays could not be sized";
+    return XM_ERR_NOMEM;
+}
+
 }  // namespace xm
