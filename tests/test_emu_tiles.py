@@ -64,3 +64,33 @@ def test_emulated_chunked_walk_matches_reference(case, chunk):
     if e["error"] is None:
         assert G.counts_dict(r["counts"], o["mode"]) == e["counts"]
         assert r["n_records"] == sum(e["counts"].values()) if o["mode"] == 0 else True
+
+
+def _fixed_width_pair(n, width, first=0):
+    """n records per stream, every primary line exactly `width` bytes (secondary width-8): tiles of 32 KiB then
+    hold exactly 32768/width lines"""
+    P, S = [], []
+    for i in range(first, first + n):
+        q = "r%07d" % (i // 2 if i % 5 == 0 else i)
+        a1, a2 = 40 + (i * 7) % 60, 40 + (i * 11) % 60
+        for out, a, w in ((P, a1, width), (S, a2, width - 8)):
+            head = "%s\t0\tchr1\t%d\t42\t50M\t*\t0\t0\t" % (q, 1000 + i)
+            tail = "\tAS:i:%d\tXS:i:%d\tNM:i:%d\n" % (a, a - (i % 3), i % 4)
+            fill = w - len(head) - len(tail) - 1
+            out.append(head + "A" * (fill // 2) + "\t" + "I" * (fill - fill // 2) + tail)
+            assert len(out[-1]) == w
+    return "".join(P).encode(), "".join(S).encode()
+
+
+@pytest.mark.parametrize("width", [256, 128, 264, 248])
+@pytest.mark.parametrize("skip", [False, True])
+def test_tiles_with_exactly_half_the_threads_in_lines(width, skip):
+    """a 32 KiB tile that owns exactly THREADS/2 = 128 lines (and its neighbours 127, 129): the two-threads-per-line
+    parse must leave the last thread to the halo line"""
+    from oracle import oracle
+    p, s = _fixed_width_pair(700, width)
+    ref = oracle.classify(p, s, skip_repeated=skip)
+    r = _emu.classify(p, s, skip_repeated=skip)
+    assert r["status"] == 0, r["message"]
+    assert r["counts"] == ref["counts"]
+    assert r["outputs"] == ref["outputs"]

@@ -50,3 +50,34 @@ def test_cuda_chunked_walk_matches_reference_golden(ctx, case, chunk, monkeypatc
         pytest.skip("covered by seed 1 at the larger chunk")
     monkeypatch.setenv("XM_CHUNK_BYTES", str(chunk))
     run_case(ctx, case, 0)
+
+
+@pytest.mark.parametrize("width", [256, 128, 264, 248])
+@pytest.mark.parametrize("mode,skip", [(0, False), (0, True), (1, False)])
+def test_cuda_fixed_width_lines_match_oracle(ctx, width, mode, skip):
+    """32 KiB tiles that own exactly 128, 127, 129 or 256 lines (tests/test_emu_tiles.py has the CPU twin)"""
+    from oracle import oracle
+    from tests.test_emu_tiles import _fixed_width_pair
+    from xenomapper_b200 import _lib
+    ctx.set_debug(0)
+    p, s = _fixed_width_pair(3000, width)
+    ref = oracle.classify(p, s, mode=mode, skip_repeated=skip)
+    rc, res, outs = ctx.classify_host(p, s, _lib.Context.opts(mode, 0, skip))
+    assert rc == 0, ctx.error()
+    assert list(res.counts) == ref["counts"]
+    assert outs == ref["outputs"]
+
+
+@pytest.mark.parametrize("style,mode,skip", [(0, 0, True), (1, 1, False), (2, 2, False)])
+def test_cuda_large_synthetic_matches_oracle(ctx, style, mode, skip):
+    """300 k records (about 130 MB per stream: thousands of tiles, look-back across several waves of CTAs)"""
+    from oracle import oracle
+    from xenomapper_b200 import _lib, synth
+    ctx.set_debug(0)
+    p, s = synth.generate(300000, seed=77, style=style)
+    score = 1 if style == 2 else 0
+    ref = oracle.classify(p, s, mode=mode, score_src=score, skip_repeated=skip, min_score=-18.0 if style == 2 else float("-inf"))
+    rc, res, outs = ctx.classify_host(p, s, _lib.Context.opts(mode, score, skip, -18.0 if style == 2 else float("-inf")))
+    assert rc == 0, ctx.error()
+    assert list(res.counts) == ref["counts"]
+    assert outs == ref["outputs"]

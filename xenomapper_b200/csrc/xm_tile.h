@@ -492,12 +492,12 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
 #endif
     }
 
-    /* Parse the owned lines.  In a clean tile with at most THREADS/2 lines two threads share a line: thread i
+    /* Parse the owned lines.  In a clean tile with fewer than THREADS/2 lines two threads share a line: thread i
      * does the checks and the QNAME (fast_head), thread THREADS/2+i the aux tokens (fast_tail) and leaves its
-     * result in qx[THREADS/2+1+i].  The last thread owns no line: it parses the line before the first owned one
+     * result in qx[THREADS/2+1+i] (so at most THREADS/2-1 lines).  The last thread owns no line: it parses the line before the first owned one
      * when the walk needs it. */
     constexpr int HALF = C::THREADS / 2;
-    const bool pair = fr.early && fr.nlines <= (uint32_t)HALF;
+    const bool pair = fr.early && fr.nlines < (uint32_t)HALF;     /* thread THREADS-1 serves the halo line, not line HALF-1's aux half */
     const bool split = pair && skip;
     if (skip && !split) fr.early = false;
     XM_THREADS_BEGIN
