@@ -133,17 +133,21 @@ struct Cfg {
     static_assert(WIN + 1 < 65535, "line starts are kept as 16-bit window offsets");
     static_assert(THREADS <= 512 && THREADS % 32 == 0, "per-warp scratch holds 16 warps");
 };
+/* Production geometry, from the sweeps in profiles/r01_geometry_sweep.md: the time a tile takes is dominated by
+ * latencies that do not depend on its size (look-back waits, one line per thread in the parse), so throughput grows
+ * with the bytes a SM holds in flight: the largest window three CTAs fit into 227 KB of shared memory, and enough
+ * threads that a tile of ~125 lines still has two threads per line. */
 #ifndef XM_BIG_THREADS
-#define XM_BIG_THREADS 256
+#define XM_BIG_THREADS 320
 #endif
 #ifndef XM_BIG_TILE
-#define XM_BIG_TILE 32768
+#define XM_BIG_TILE 47104
 #endif
 #ifndef XM_BIG_HALO
-#define XM_BIG_HALO 2048
+#define XM_BIG_HALO 1024
 #endif
 #ifndef XM_BIG_OCC
-#define XM_BIG_OCC 4
+#define XM_BIG_OCC 3
 #endif
 using CfgBig = Cfg<XM_BIG_TILE, XM_BIG_HALO, XM_BIG_THREADS>;
 using CfgSmall = Cfg<480, 512, 256>;          /* LCAP >= TILE/2: cannot lose the stop (non-blank lines need 2 bytes) */
