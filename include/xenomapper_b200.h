@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define XM_ABI_VERSION 2
+#define XM_ABI_VERSION 3
 
 /* States and bins share one numbering: the order of the reference's output
  * arguments (xm.py:291-297).  counts[] is indexed [state] for single-end and
@@ -163,6 +163,32 @@ int xm_count_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repea
  * the buffer's record count.  With the counts above this turns record-index partition points into byte ranges. */
 int xm_locate_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repeated, uint32_t n_queries,
                      const uint64_t *record_index, uint64_t *byte_offset);
+
+/* ---- BAM input ---------------------------------------------------------- */
+
+/* Replaces the two `samtools view` pipes of xm.py:48-64 (get_bam_header,
+ * bam_lines) and getBamReadPairs (xm.py:66-93).  The BGZF blocks are inflated
+ * on the host (zlib, a pool of threads), the GPU renders the alignment records
+ * as the SAM text lines `samtools view` prints, in device memory, and the
+ * walk runs on them; the six bins come back as with xm_classify_host.
+ * Float aux values (types f, B:f) are refused with XM_ERR_UNSUPPORTED. */
+int xm_classify_bam_host(xm_ctx *ctx, const void *prim_bam, uint64_t prim_len,
+                         const void *sec_bam, uint64_t sec_len, const xm_opts *opts, xm_result *res);
+/* The header text stored in a BAM file (l_text bytes; what `samtools view -H`
+ * of xm.py:49 printed before samtools 1.10 began to append its own @PG line).
+ * *needed receives its length; it is copied to dst when cap suffices.
+ * No context needed; errors are reported through xm_last_error(NULL). */
+int xm_bam_header_text(const void *bam, uint64_t len, char *dst, uint64_t cap, uint64_t *needed);
+/* All records of one BAM file as SAM text on the host (library-owned, valid
+ * until the next BAM call): what iterating getBamReadPairs needs. */
+int xm_bam_render_host(xm_ctx *ctx, const void *bam, uint64_t len, const void **text, uint64_t *text_len);
+typedef struct xm_bam_stats {
+    double inflate_s;        /* host wall time: BGZF scan + inflate + record chain */
+    float render_ms;         /* device time of the three BAM kernels */
+    uint32_t n_launches;
+    uint64_t bam_bytes, inflated_bytes, text_bytes, records;
+} xm_bam_stats;
+int xm_bam_get_stats(xm_ctx *ctx, xm_bam_stats *out, int reset);
 
 /* ---- device memory helpers (so bindings need no CUDA of their own) ----- */
 int xm_dev_alloc(xm_ctx *ctx, uint64_t bytes, void **d_ptr);

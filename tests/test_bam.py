@@ -1,0 +1,107 @@
+"""BAM input (BASELINE configs[4]): host BGZF inflate + GPU record rendering + the walk.
+
+The reference cannot run its own BAM path here (samtools is absent, xm.py:48-93 are `# pragma: no cover`); the pin
+is the fixture twins: paired_end_testdata_{human,mouse}.bam decode to exactly the .sam files next to them, so the
+expected outputs are the SAM goldens (which the unmodified reference produced)."""
+import io
+
+import pytest
+
+from tests import _bamwriter
+from tests import _golden as G
+
+
+def test_bam_header_text_needs_no_gpu():
+    from xenomapper_b200 import _lib
+    for which in ("primary", "secondary"):
+        bam = G.fixture_bytes("pe", which, "bam")
+        header, _ = G.split_header(G.fixture_bytes("pe", which, "sam"))
+        assert _lib.bam_header_text(bam) == header
+
+
+def test_bam_writer_round_trips_the_fixture_through_the_header_reader():
+    from xenomapper_b200 import _lib
+    header, records = G.split_header(G.fixture_bytes("pe", "primary", "sam"))
+    bam = _bamwriter.sam_to_bam(header, records + b"\n", block=3000)
+    assert _lib.bam_header_text(bam) == header
+
+
+def test_corrupt_bam_is_refused():
+    from xenomapper_b200 import _lib
+    bam = bytearray(G.fixture_bytes("pe", "primary", "bam"))
+    with pytest.raises(_lib.XenomapperLibraryError):
+        _lib.bam_header_text(bytes(bam[:100]))
+    bam[40] ^= 0x55
+    with pytest.raises(_lib.XenomapperLibraryError):
+        _lib.bam_header_text(bytes(bam))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from xenomapper_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["primary", "secondary"])
+def test_gpu_renders_fixture_bam_as_its_sam_twin(ctx, which):
+    _, records = G.split_header(G.fixture_bytes("pe", which, "sam"))
+    if not records.endswith(b"\n"):
+        records += b"\n"                       # the fixture's last line is unterminated; samtools view prints whole lines
+    assert ctx.bam_render_host(G.fixture_bytes("pe", which, "bam")) == records
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("style", [0, 1, 2])
+@pytest.mark.parametrize("block", [0xff00, 777])
+def test_gpu_renders_synthetic_bam_back_to_its_sam(ctx, style, block):
+    """records that straddle BGZF blocks (777-byte blocks cut every record), every aux type the writer emits"""
+    from xenomapper_b200 import synth
+    p, _ = synth.generate(4000 if block > 1000 else 400, seed=31 + style, style=style)
+    extra = b"rX\t4\t*\t0\t0\t*\t*\t0\t0\t*\t*\tXA:A:q\tXB:B:c,-1,2,3\tXC:B:S,65535,0\tXH:H:1AE301\tXI:i:-70000\tXJ:i:4000000000\tXS:i:-200\tXZ:Z:a b\n"
+    text = bytes(p) + extra + b"*\t4\t*\t0\t0\t*\t*\t0\t0\tACGTN\t*\n"
+    bam = _bamwriter.sam_to_bam(synth.HEADER_PRIMARY, text, block=block)
+    assert ctx.bam_render_host(bam) == text
+    st = ctx.bam_stats()
+    assert st.records == text.count(b"\n") and st.text_bytes == len(text)
+
+
+@pytest.mark.gpu
+def test_float_aux_is_refused_not_misprinted(ctx):
+    import struct
+    from xenomapper_b200 import _lib, synth
+    rec = _bamwriter.record("r1\t4\t*\t0\t0\t*\t*\t0\t0\tAC\tII", {})
+    body = rec[4:] + b"XFf" + struct.pack("<f", 1.5)
+    raw = b"BAM\1" + struct.pack("<i", 0) + struct.pack("<i", 0) + struct.pack("<i", len(body)) + body
+    with pytest.raises(_lib.UnsupportedInput):
+        ctx.bam_render_host(_bamwriter.bgzf(raw))
+
+
+FIXTURE_CASES = [c for c in G.CASES if c["input"]["kind"] == "fixture" and c["input"]["key"] == "pe" and c["header"]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", FIXTURE_CASES, ids=[c["name"] for c in FIXTURE_CASES])
+def test_bam_walk_equals_the_sam_goldens(case):
+    """process_headers(bam=True) + getBamReadPairs + the walks on the fixture BAMs: the six outputs, headers
+    included, and the counts are those the reference produced from the SAM twins"""
+    from xenomapper_b200 import xenomapper as xm
+    o = case["opts"]
+    walk = (xm.main_single_end, xm.main_paired_end, xm.conservative_main_paired_end)[o["mode"]]
+    tag_func = (xm.get_tag, xm.get_tag_with_ZS_as_XS, xm.get_cigarbased_AS_tag)[o["score_src"]]
+    f1, f2 = io.BytesIO(G.fixture_bytes("pe", "primary", "bam")), io.BytesIO(G.fixture_bytes("pe", "secondary", "bam"))
+    outs = [io.StringIO() if (o["enabled_bins"] >> b) & 1 else None for b in range(6)]
+    names = ("primary_specific", "secondary_specific", "primary_multi", "secondary_multi", "unassigned", "unresolved")
+    kw = dict(zip(names, outs))
+    if kw["primary_specific"] is None:
+        pytest.skip("the reference always writes the primary_specific header")
+    xm.process_headers(f1, f2, bam=True, **kw)
+    counts = walk(xm.getBamReadPairs(f1, f2, skip_repeated_reads=o["skip_repeated"]), min_score=o["min_score"], tag_func=tag_func, **kw)
+    e = case["expect"]
+    got = [x.getvalue().encode() if x is not None else b"" for x in outs]
+    assert [len(x) for x in got] == e["full_len"]
+    assert [G.sha(x) for x in got] == e["full_sha256"]
+    key = (lambda k: k) if o["mode"] == 0 else (lambda k: k[0] + "|" + k[1])
+    assert {key(k): v for k, v in counts.items()} == e["counts"]

@@ -82,10 +82,11 @@ def _fixed_width_pair(n, width, first=0):
     return "".join(P).encode(), "".join(S).encode()
 
 
-@pytest.mark.parametrize("width", [256, 128, 264, 248])
+@pytest.mark.parametrize("width", [256, 128, 264, 248, 292, 294, 296])
 @pytest.mark.parametrize("skip", [False, True])
 def test_tiles_with_exactly_half_the_threads_in_lines(width, skip):
-    """a 32 KiB tile that owns exactly THREADS/2 = 128 lines (and its neighbours 127, 129): the two-threads-per-line
+    """tiles that own exactly THREADS/2 lines and one more or less (128 lines of 256 bytes in 32 KiB tiles, 160 lines of
+    294 bytes in 46 KiB tiles): the two-threads-per-line
     parse must leave the last thread to the halo line"""
     from oracle import oracle
     p, s = _fixed_width_pair(700, width)

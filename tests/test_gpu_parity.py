@@ -52,7 +52,7 @@ def test_cuda_chunked_walk_matches_reference_golden(ctx, case, chunk, monkeypatc
     run_case(ctx, case, 0)
 
 
-@pytest.mark.parametrize("width", [256, 128, 264, 248])
+@pytest.mark.parametrize("width", [256, 128, 264, 248, 292, 294, 296])
 @pytest.mark.parametrize("mode,skip", [(0, False), (0, True), (1, False)])
 def test_cuda_fixed_width_lines_match_oracle(ctx, width, mode, skip):
     """32 KiB tiles that own exactly 128, 127, 129 or 256 lines (tests/test_emu_tiles.py has the CPU twin)"""

@@ -21,7 +21,8 @@ DEBUG_FORCE_GENERIC, DEBUG_SMALL_TILES = 1, 2
 EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_classify_device",
            "xm_classify_host", "xm_get_output", "xm_classify_fds", "xm_count_device", "xm_dev_alloc",
            "xm_dev_free", "xm_host_alloc_pinned", "xm_host_free_pinned", "xm_memcpy_h2d", "xm_memcpy_d2h",
-           "xm_memcpy_d2d", "xm_dev_mem_info", "xm_set_debug", "xm_locate_device")
+           "xm_memcpy_d2d", "xm_dev_mem_info", "xm_set_debug", "xm_locate_device", "xm_classify_bam_host",
+           "xm_bam_header_text", "xm_bam_render_host", "xm_bam_get_stats")
 
 
 class Opts(C.Structure):
@@ -39,6 +40,11 @@ class Result(C.Structure):
 class ShardInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("first_start", C.c_uint64), ("stop_at", C.c_uint64),
                 ("end_off", C.c_uint64)]
+
+
+class BamStats(C.Structure):
+    _fields_ = [("inflate_s", C.c_double), ("render_ms", C.c_float), ("n_launches", C.c_uint32), ("bam_bytes", C.c_uint64),
+                ("inflated_bytes", C.c_uint64), ("text_bytes", C.c_uint64), ("records", C.c_uint64)]
 
 
 class XenomapperLibraryError(RuntimeError):
@@ -84,6 +90,10 @@ def load():
     L.xm_memcpy_d2d.argtypes = [vp, vp, vp, u64]
     L.xm_dev_mem_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.xm_set_debug.argtypes = [vp, C.c_uint32]
+    L.xm_classify_bam_host.argtypes = [vp, vp, u64, vp, u64, C.POINTER(Opts), C.POINTER(Result)]
+    L.xm_bam_header_text.argtypes = [vp, u64, vp, u64, C.POINTER(u64)]
+    L.xm_bam_render_host.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
+    L.xm_bam_get_stats.argtypes = [vp, C.POINTER(BamStats), i]
     for name in EXPORTS:
         if name not in ("xm_create", "xm_destroy", "xm_last_error", "xm_abi_version"):
             getattr(L, name).restype = i
@@ -198,6 +208,39 @@ class Context:
         del pk, sk
         return rc, res, outs
 
+    def classify_bam_host(self, prim_bam, sec_bam, opts, want_outputs=True):
+        """prim_bam / sec_bam: bytes-like BAM files (BGZF): inflated on the host, rendered and walked on the device"""
+        pa, pn, pk = _host_ptr(prim_bam)
+        sa, sn, sk = _host_ptr(sec_bam)
+        res = Result()
+        rc = self.lib.xm_classify_bam_host(self.h, pa, pn, sa, sn, C.byref(opts), C.byref(res))
+        self._check(rc, "xm_classify_bam_host")
+        outs = None
+        if want_outputs:
+            outs = []
+            for b in range(6):
+                p, n = C.c_void_p(), C.c_uint64()
+                self.lib.xm_get_output(self.h, b, C.byref(p), C.byref(n))
+                outs.append(C.string_at(p.value, n.value) if n.value else b"")
+        del pk, sk
+        return rc, res, outs
+
+    def bam_render_host(self, bam):
+        """all records of a BAM file as SAM text (what `samtools view` prints), rendered on the device"""
+        a, n, keep = _host_ptr(bam)
+        p, ln = C.c_void_p(), C.c_uint64()
+        rc = self.lib.xm_bam_render_host(self.h, a, n, C.byref(p), C.byref(ln))
+        self._check(rc, "xm_bam_render_host")
+        if rc == XM_ERR_UNSUPPORTED:
+            raise UnsupportedInput(self.error())
+        del keep
+        return C.string_at(p.value, ln.value) if ln.value else b""
+
+    def bam_stats(self, reset=True):
+        st = BamStats()
+        self.lib.xm_bam_get_stats(self.h, C.byref(st), int(reset))
+        return st
+
     def classify_fds(self, fd_prim, off_prim, fd_sec, off_sec, out_fds, opts):
         res = Result()
         fds = (C.c_int * 6)(*out_fds)
@@ -228,3 +271,17 @@ def default_context():
         dev = int(os.environ.get("XENOMAPPER_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         _default_ctx = Context(dev)
     return _default_ctx
+
+
+def bam_header_text(bam):
+    """header text stored in a BAM file (no device needed: host inflate of the leading BGZF blocks)"""
+    L = load()
+    a, n, keep = _host_ptr(bam)
+    need = C.c_uint64()
+    rc = L.xm_bam_header_text(a, n, None, 0, C.byref(need))
+    if rc:
+        raise XenomapperLibraryError("xm_bam_header_text failed (%d): %s" % (rc, L.xm_last_error(None).decode()))
+    buf = C.create_string_buffer(max(1, need.value))
+    L.xm_bam_header_text(a, n, buf, need.value, C.byref(need))
+    del keep
+    return buf.raw[:need.value]

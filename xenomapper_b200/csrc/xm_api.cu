@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,7 @@
 #include "xm_launch.h"
 #include "xm_walk.h"
 #include "xm_stream.h"
+#include "xm_bam.h"
 
 using namespace xm;
 
@@ -91,6 +93,11 @@ struct xm_ctx {
     std::vector<Block> bins[6];
     std::vector<uint8_t> flat[6];       /* xm_get_output of a bin that spans several blocks */
     uint64_t block_bytes = 0;
+    /* BAM input: inflated streams (pinned), device copies, record tables, rendered SAM text */
+    HostBuf h_bam[2];
+    DevBuf d_bam[2], d_bam_rec[2], d_bam_ref[2], d_bam_len[2], d_bam_sum[2], d_bam_text[2];
+    std::vector<uint8_t> bam_text_host;
+    xm_bam_stats bam_stats{};
 };
 
 static int fail(xm_ctx *c, int code, const std::string &msg)
@@ -166,6 +173,8 @@ void xm_destroy(xm_ctx *c)
     for (auto &s : c->d_in) for (auto &b : s) if (b.p) cudaFree(b.p);
     for (auto &s : c->d_out) for (auto &b : s) if (b.p) cudaFree(b.p);
     for (auto &b : c->h_stage) if (b.p) cudaFreeHost(b.p);
+    for (auto &b : c->h_bam) if (b.p) cudaFreeHost(b.p);
+    for (auto *arr : {c->d_bam, c->d_bam_rec, c->d_bam_ref, c->d_bam_len, c->d_bam_sum, c->d_bam_text}) for (int k = 0; k < 2; ++k) if (arr[k].p) cudaFree(arr[k].p);
     for (auto &v : c->bins) for (auto &b : v) cudaFreeHost(b.p);
     for (auto &b : c->pool) cudaFreeHost(b.p);
     if (c->dl) cudaStreamDestroy(c->dl);
@@ -478,6 +487,173 @@ int xm_classify_fds(xm_ctx *c, int fd_prim, int64_t off_prim, int fd_sec, int64_
     for (int b = 0; b < 6; ++b) if (out_fds[b] >= 0) en |= 1u << b;
     o.enabled_bins = en;
     return stream_walk(c, in, out_fds, &o, res);
+}
+
+/* ---- BAM input (xm_bam.h) ------------------------------------------------------------------ */
+static int host_threads()
+{
+    const char *e = getenv("XM_HOST_THREADS");
+    if (e && *e) { const int v = atoi(e); if (v > 0) return v; }
+    const unsigned h = std::thread::hardware_concurrency();
+    return (int)std::min<unsigned>(h ? h : 1, 32);
+}
+
+/* inflate, index, upload and render one BAM file: its records as SAM text in device memory (slot s) */
+static int bam_to_device_text(xm_ctx *c, const void *bam, uint64_t len, int s, uint8_t **d_text, uint64_t *text_len)
+{
+    *d_text = nullptr; *text_len = 0;
+    std::string err;
+    std::vector<BgzfBlock> blocks;
+    uint64_t total = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!bgzf_scan((const uint8_t *)bam, len, blocks, total, err)) return fail(c, XM_ERR_IO, "BAM input: " + err);
+    int rc;
+    if ((rc = reserve_host(c, c->h_bam[s], total))) return rc;
+    if (!bgzf_inflate((const uint8_t *)bam, blocks, 0, blocks.size(), c->h_bam[s].p, host_threads(), err)) return fail(c, XM_ERR_IO, "BAM input: " + err);
+    BamIndex ix;
+    if (!bam_index(c->h_bam[s].p, total, ix, false, err)) return fail(c, XM_ERR_IO, "BAM input: " + err);
+    c->bam_stats.inflate_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    c->bam_stats.bam_bytes += len;
+    c->bam_stats.inflated_bytes += total;
+    const uint64_t n = ix.rec.size();
+    c->bam_stats.records += n;
+    if (!n) return XM_OK;
+    const uint64_t nb = (n + 1023) / 1024;
+    const uint64_t ref_bytes = ix.ref_off.size() * 4 + ix.ref_names.size() + 16;
+    if ((rc = reserve_dev(c, c->d_bam[s], total)) || (rc = reserve_dev(c, c->d_bam_rec[s], n * 8)) || (rc = reserve_dev(c, c->d_bam_ref[s], ref_bytes)) ||
+        (rc = reserve_dev(c, c->d_bam_len[s], n * 8 + 16)) || (rc = reserve_dev(c, c->d_bam_sum[s], nb * 8 + 16))) return rc;
+    cudaStream_t st = c->be.st;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    XM_CUDA(c, cudaMemcpyAsync(c->d_bam[s].p, c->h_bam[s].p, total, cudaMemcpyHostToDevice, st), "H2D copy");
+    XM_CUDA(c, cudaMemcpyAsync(c->d_bam_rec[s].p, ix.rec.data(), n * 8, cudaMemcpyHostToDevice, st), "H2D copy");
+    XM_CUDA(c, cudaMemcpyAsync(c->d_bam_ref[s].p, ix.ref_off.data(), ix.ref_off.size() * 4, cudaMemcpyHostToDevice, st), "H2D copy");
+    uint8_t *d_names = c->d_bam_ref[s].p + ix.ref_off.size() * 4;
+    if (!ix.ref_names.empty()) XM_CUDA(c, cudaMemcpyAsync(d_names, ix.ref_names.data(), ix.ref_names.size(), cudaMemcpyHostToDevice, st), "H2D copy");
+    unsigned long long *d_err = (unsigned long long *)(c->d_bam_sum[s].p + nb * 8);
+    const unsigned long long no_err = BAM_NO_ERROR;
+    XM_CUDA(c, cudaMemcpyAsync(d_err, &no_err, 8, cudaMemcpyHostToDevice, st), "H2D copy");
+    BamDev B;
+    B.data = c->d_bam[s].p; B.rec = (const uint64_t *)c->d_bam_rec[s].p; B.n = n;
+    B.ref_off = (const uint32_t *)c->d_bam_ref[s].p; B.ref_names = d_names; B.n_ref = (uint32_t)ix.ref_off.size() - 1;
+    uint32_t *d_len = (uint32_t *)c->d_bam_len[s].p, *d_loff = d_len + n + (n & 1);
+    cudaEventRecord(e0, st);
+    k_bam_len<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(B, d_len, d_err);
+    k_bam_scan_blocks<<<(unsigned)nb, 1024, 0, st>>>(d_len, n, d_loff, (unsigned long long *)c->d_bam_sum[s].p);
+    std::vector<unsigned long long> sums(nb + 1);
+    XM_CUDA(c, cudaMemcpyAsync(sums.data(), c->d_bam_sum[s].p, (nb + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H copy");
+    XM_CUDA(c, cudaStreamSynchronize(st), "BAM length kernels");
+    if (sums[nb] != BAM_NO_ERROR) {
+        const unsigned long long rec = sums[nb] >> 8;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if ((sums[nb] & 0xff) == BAM_E_FLOAT) return fail(c, XM_ERR_UNSUPPORTED, "BAM record " + std::to_string(rec) + " has a float aux value (f or B:f): not rendered on the device");
+        return fail(c, XM_ERR_IO, "BAM record " + std::to_string(rec) + " is corrupt");
+    }
+    unsigned long long run = 0;
+    for (uint64_t k = 0; k < nb; ++k) { const unsigned long long v = sums[k]; sums[k] = run; run += v; }
+    if ((rc = reserve_dev(c, c->d_bam_text[s], run))) return rc;
+    XM_CUDA(c, cudaMemcpyAsync(c->d_bam_sum[s].p, sums.data(), nb * 8, cudaMemcpyHostToDevice, st), "H2D copy");
+    k_bam_render<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(B, d_loff, (const unsigned long long *)c->d_bam_sum[s].p, c->d_bam_text[s].p);
+    cudaEventRecord(e1, st);
+    XM_CUDA(c, cudaStreamSynchronize(st), "BAM render kernel");
+    XM_CUDA(c, cudaGetLastError(), "BAM render kernel");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->bam_stats.render_ms += ms;
+    c->bam_stats.text_bytes += run;
+    c->bam_stats.n_launches += 3;
+    *d_text = c->d_bam_text[s].p;
+    *text_len = run;
+    return XM_OK;
+}
+
+int xm_bam_header_text(const void *bam, uint64_t len, char *dst, uint64_t cap, uint64_t *needed)
+{
+    if (!bam || !needed) return XM_ERR_ARG;
+    std::string err;
+    std::vector<BgzfBlock> blocks;
+    uint64_t total = 0;
+    if (!bgzf_scan((const uint8_t *)bam, len, blocks, total, err)) { g_create_error = "BAM input: " + err; return XM_ERR_IO; }
+    /* inflate leading blocks until the header is complete */
+    for (size_t take = std::min<size_t>(blocks.size(), 4);; take = std::min(blocks.size(), take * 4)) {
+        const uint64_t bytes = take < blocks.size() ? blocks[take].out_off : total;
+        std::vector<uint8_t> buf(bytes + 16);
+        if (!bgzf_inflate((const uint8_t *)bam, blocks, 0, take, buf.data(), 1, err)) { g_create_error = "BAM input: " + err; return XM_ERR_IO; }
+        BamIndex ix;
+        if (bam_index(buf.data(), bytes, ix, true, err)) {
+            *needed = ix.text.size();
+            if (dst && cap >= ix.text.size()) memcpy(dst, ix.text.data(), ix.text.size());
+            return XM_OK;
+        }
+        if (take == blocks.size()) { g_create_error = "BAM input: " + err; return XM_ERR_IO; }
+    }
+}
+
+int xm_bam_render_host(xm_ctx *c, const void *bam, uint64_t len, const void **text, uint64_t *text_len)
+{
+    if (!c || !bam || !text || !text_len) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    uint8_t *d = nullptr;
+    uint64_t n = 0;
+    const int rc = bam_to_device_text(c, bam, len, 0, &d, &n);
+    if (rc) return rc;
+    c->bam_text_host.resize(n);
+    if (n) {
+        XM_CUDA(c, cudaMemcpyAsync(c->bam_text_host.data(), d, n, cudaMemcpyDeviceToHost, c->be.st), "D2H copy");
+        XM_CUDA(c, cudaStreamSynchronize(c->be.st), "D2H copy");
+    }
+    *text = c->bam_text_host.data();
+    *text_len = n;
+    return XM_OK;
+}
+
+int xm_classify_bam_host(xm_ctx *c, const void *prim_bam, uint64_t prim_len, const void *sec_bam, uint64_t sec_len,
+                         const xm_opts *opts, xm_result *res)
+{
+    if (!c || !opts || !res || !prim_bam || !sec_bam) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    recycle_bins(c);
+    memset(res, 0, sizeof *res);
+    uint8_t *d_txt[2] = {nullptr, nullptr};
+    uint64_t n_txt[2] = {0, 0};
+    int rc;
+    if ((rc = bam_to_device_text(c, prim_bam, prim_len, 0, &d_txt[0], &n_txt[0]))) return res->status = rc;
+    if ((rc = bam_to_device_text(c, sec_bam, sec_len, 1, &d_txt[1], &n_txt[1]))) return res->status = rc;
+    xm_opts o = *opts;
+    o.skip_repeated &= 1;
+    std::string msg;
+    /* sizing pass (nothing is written), then the walk into exactly sized bins */
+    uint8_t *none[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t cap[6] = {0, 0, 0, 0, 0, 0};
+    xm_result dry;
+    rc = walk_resident(c->be, c->scratch, StreamBuf{d_txt[0], n_txt[0]}, StreamBuf{d_txt[1], n_txt[1]}, o, none, cap, c->debug, &dry, msg);
+    if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM) { c->err = msg; return res->status = rc; }
+    uint8_t *outs[6];
+    for (int b = 0; b < 6; ++b) {
+        cap[b] = ((o.enabled_bins >> b) & 1u) ? dry.out_len[b] : 0;
+        if ((rc = reserve_dev(c, c->d_out[0][b], cap[b] + 16))) return res->status = rc;
+        outs[b] = c->d_out[0][b].p;
+    }
+    rc = walk_resident(c->be, c->scratch, StreamBuf{d_txt[0], n_txt[0]}, StreamBuf{d_txt[1], n_txt[1]}, o, outs, cap, c->debug, res, msg);
+    c->err = msg;
+    res->n_launches += dry.n_launches + c->bam_stats.n_launches;
+    if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM) return rc;
+    uint64_t biggest = 4096;
+    for (int b = 0; b < 6; ++b) biggest = std::max<uint64_t>(biggest, res->out_len[b]);
+    c->block_bytes = std::min<uint64_t>(biggest, 256ull << 20);
+    for (int b = 0; b < 6; ++b)
+        if (((o.enabled_bins >> b) & 1u) && res->out_len[b]) { const int r2 = bin_append_d2h(c, b, outs[b], res->out_len[b]); if (r2) return r2; }
+    if (cudaStreamSynchronize(c->dl) != cudaSuccess) return fail(c, XM_ERR_CUDA, "D2H copy failed");
+    return rc;
+}
+
+int xm_bam_get_stats(xm_ctx *c, xm_bam_stats *out, int reset)
+{
+    if (!c || !out) return XM_ERR_ARG;
+    *out = c->bam_stats;
+    if (reset) c->bam_stats = xm_bam_stats{};
+    return XM_OK;
 }
 
 /* ---- index pass of the sharded walk (xm_walk.h index_resident) ---------------------------- */

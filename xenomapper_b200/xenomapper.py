@@ -265,7 +265,12 @@ def _walk(mode, readpairs, outputs, min_score, tag_func):
         raise NotImplementedError(
             "tag_func must be get_tag, get_tag_with_ZS_as_XS or get_cigarbased_AS_tag: scores are parsed "
             "inside the CUDA kernels, arbitrary Python callables cannot run there")
-    if isinstance(readpairs, ReadPairs):
+    bam_inputs = None
+    if isinstance(readpairs, ReadPairs) and readpairs.bam:
+        from . import bam
+        bam_inputs = (bam._all_bytes(readpairs.sam1), bam._all_bytes(readpairs.sam2))
+        skip = readpairs.skip_repeated_reads
+    elif isinstance(readpairs, ReadPairs):
         prim, sec = readpairs.record_regions()
         skip = readpairs.skip_repeated_reads
     else:
@@ -277,7 +282,10 @@ def _walk(mode, readpairs, outputs, min_score, tag_func):
             enabled |= 1 << b
     ctx = _lib.default_context()
     opts = ctx.opts(mode, score_src, skip, float(min_score), enabled)
-    rc, res, outs = ctx.classify_host(prim, sec, opts)
+    if bam_inputs:
+        rc, res, outs = ctx.classify_bam_host(bam_inputs[0], bam_inputs[1], opts)      # inflate on the host, decode + walk on the GPU
+    else:
+        rc, res, outs = ctx.classify_host(prim, sec, opts)
     # everything before a failing record is written, like the reference's streaming prints
     for b, out in enumerate(outputs):
         if out and outs[b]:
