@@ -62,7 +62,8 @@ def test_gpu_renders_synthetic_bam_back_to_its_sam(ctx, style, block):
     p, _ = synth.generate(4000 if block > 1000 else 400, seed=31 + style, style=style)
     extra = b"rX\t4\t*\t0\t0\t*\t*\t0\t0\t*\t*\tXA:A:q\tXB:B:c,-1,2,3\tXC:B:S,65535,0\tXH:H:1AE301\tXI:i:-70000\tXJ:i:4000000000\tXS:i:-200\tXZ:Z:a b\n"
     text = bytes(p) + extra + b"*\t4\t*\t0\t0\t*\t*\t0\t0\tACGTN\t*\n"
-    bam = _bamwriter.sam_to_bam(synth.HEADER_PRIMARY, text, block=block)
+    bam = _bamwriter.sam_to_bam(FULL_HEADER, text, block=block)
+    ctx.bam_stats(reset=True)
     assert ctx.bam_render_host(bam) == text
     st = ctx.bam_stats()
     assert st.records == text.count(b"\n") and st.text_bytes == len(text)
@@ -78,6 +79,10 @@ def test_float_aux_is_refused_not_misprinted(ctx):
     with pytest.raises(_lib.UnsupportedInput):
         ctx.bam_render_host(_bamwriter.bgzf(raw))
 
+
+# every reference name the synthetic generator uses (its own header lists two)
+FULL_HEADER = "@HD\tVN:1.0\tSO:unsorted\n" + "".join("@SQ\tSN:%s\tLN:1000000000\n" % n for n in
+                                                     ("chr1", "chr2", "chr7", "chr11", "chr17", "chr19", "chrX", "chrM")) + "@PG\tID:bowtie2\tPN:bowtie2\n"
 
 FIXTURE_CASES = [c for c in G.CASES if c["input"]["kind"] == "fixture" and c["input"]["key"] == "pe" and c["header"]]
 
@@ -105,3 +110,20 @@ def test_bam_walk_equals_the_sam_goldens(case):
     assert [G.sha(x) for x in got] == e["full_sha256"]
     key = (lambda k: k) if o["mode"] == 0 else (lambda k: k[0] + "|" + k[1])
     assert {key(k): v for k, v in counts.items()} == e["counts"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("style,mode,score,skip,min_score", [(0, 0, 0, True, float("-inf")), (1, 1, 2, False, -40.0), (2, 2, 1, False, -18.0)],
+                         ids=["se_skip", "pe_cigar", "pe_conservative_zs"])
+def test_bam_walk_on_synthetic_pairs_equals_the_oracle(ctx, style, mode, score, skip, min_score):
+    """configs[4]-shaped inputs (--cigar_scores on BAM among them): the walk on BAM input against the oracle on the SAM text"""
+    from oracle import oracle
+    from xenomapper_b200 import _lib, synth
+    p, s = synth.generate(20000, seed=41, style=style)
+    hdr2 = FULL_HEADER.replace("SN:chr", "SN:").replace("SN:M\t", "SN:MT\t")
+    bam_p, bam_s = _bamwriter.sam_to_bam(FULL_HEADER, bytes(p)), _bamwriter.sam_to_bam(hdr2, bytes(s))
+    ref = oracle.classify(p, s, mode=mode, score_src=score, skip_repeated=skip, min_score=min_score)
+    rc, res, outs = ctx.classify_bam_host(bam_p, bam_s, _lib.Context.opts(mode, score, skip, min_score))
+    assert rc == 0, ctx.error()
+    assert list(res.counts) == ref["counts"]
+    assert outs == ref["outputs"]
