@@ -71,8 +71,6 @@ def bgzf(data, block=0xff00, level=1):
     out = bytearray()
     for k in list(range(0, len(data), block)) + [len(data)]:
         chunk = data[k:k + block] if k < len(data) else b""
-        if k == len(data) and len(data) and False:
-            break
         c = zlib.compressobj(level, zlib.DEFLATED, -15)
         comp = c.compress(chunk) + c.flush()
         out += struct.pack("<BBBBIBBHBBHH", 31, 139, 8, 4, 0, 0, 255, 6, 66, 67, 2, len(comp) + 25)
@@ -80,7 +78,7 @@ def bgzf(data, block=0xff00, level=1):
     return bytes(out)
 
 
-def sam_to_bam(header_text, record_text, block=0xff00):
+def sam_to_bam(header_text, record_text, block=0xff00, level=1):
     """header_text: '@' lines; record_text: SAM records (bytes or str).  Returns BAM file bytes."""
     if isinstance(header_text, bytes):
         header_text = header_text.decode()
@@ -99,4 +97,4 @@ def sam_to_bam(header_text, record_text, block=0xff00):
     for line in record_text.split("\n"):
         if line:
             raw += record(line, ref_ids)
-    return bgzf(bytes(raw), block)
+    return bgzf(bytes(raw), block, level)

@@ -168,3 +168,29 @@ def test_sharded_cli_equals_single_process_cli(tmp_path, flags):
                         {"XENOMAPPER_DIST_BACKEND": "gloo", "XENOMAPPER_DEVICE": "0"})
     assert two == one
     assert summary1[summary1.index("Read Count"):].strip() in summary2
+
+
+@pytest.mark.gpu
+def test_sharded_cli_over_nccl_on_two_gpus(tmp_path):
+    """one process per GPU, NCCL for the words exchanged (needs two devices: `gpurun --gpus 2`)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    p, s = synth.generate(200000, seed=23, style=synth.STYLE_PE_BOWTIE2)
+    open(tmp_path / "p.sam", "wb").write(synth.HEADER_PRIMARY.encode() + bytes(p))
+    open(tmp_path / "s.sam", "wb").write(synth.HEADER_SECONDARY.encode() + bytes(s))
+    names = ["primary_specific", "secondary_specific", "primary_multi", "secondary_multi", "unassigned", "unresolved"]
+    outs = []
+    for n in names:
+        outs += ["--" + n, str(tmp_path / (n + ".sam"))]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), "-m", "xenomapper_b200.xenomapper", "--primary_sam", str(tmp_path / "p.sam"),
+           "--secondary_sam", str(tmp_path / "s.sam"), "--paired"] + outs
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, timeout=900)
+    assert r.returncode == 0, r.stderr.decode()[-3000:]
+    ref = oracle.classify(p, s, mode=1)
+    for b, n in enumerate(names):
+        data = open(tmp_path / (n + ".sam"), "rb").read()
+        body = data[data.index(b"\n@CO") + 1:]
+        body = body[body.index(b"\n") + 1:]
+        assert body == ref["outputs"][b], n
