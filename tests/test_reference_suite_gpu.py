@@ -109,3 +109,31 @@ def test_cli_end_to_end(tmp_path):
     assert G.sha(r.stdout) == e["full_sha256"][0]
     assert G.sha(un.read_bytes()) == e["full_sha256"][5]
     assert G.sha(r.stderr) == e["summary_sha256"]
+
+
+@pytest.mark.parametrize("name,flags", [("fixture_se_mode0_src0_skip1_min-inf", []), ("fixture_pe_mode1_src0_skip0_min-inf", ["--paired"]),
+                                        ("fixture_pe_mode1_src2_skip0_min-inf", ["--paired", "--cigar_scores"])])
+@pytest.mark.parametrize("chunk", [None, "3000"])
+def test_cli_on_real_files_streams_through_descriptors(tmp_path, name, flags, chunk):
+    """every input and output a regular file: the walk goes through xm_classify_fds (pinned staging, write(2) per bin);
+    with XM_CHUNK_BYTES=3000 in dozens of steps.  Expected: the reference CLI's six files, headers included."""
+    import os
+    import subprocess
+    import sys
+    if name not in G.BY_NAME:
+        pytest.skip("no such golden")
+    case = G.BY_NAME[name]
+    key = case["input"]["key"]
+    p, s = tmp_path / "h.sam", tmp_path / "m.sam"
+    p.write_bytes(G.fixture_bytes(key, "primary")); s.write_bytes(G.fixture_bytes(key, "secondary"))
+    outs = [tmp_path / (b + ".sam") for b in G.BINS]
+    cmd = [sys.executable, "-m", "xenomapper_b200.xenomapper", "--primary_sam", str(p), "--secondary_sam", str(s)] + flags
+    for b, o in zip(G.BINS, outs):
+        cmd += ["--" + b, str(o)]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **({"XM_CHUNK_BYTES": chunk} if chunk else {}))
+    r = subprocess.run(cmd, cwd=root, capture_output=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr.decode()
+    e = case["expect"]
+    assert [G.sha(o.read_bytes()) for o in outs] == e["full_sha256"]
+    assert G.sha(r.stderr) == e["summary_sha256"]

@@ -265,14 +265,16 @@ def _walk(mode, readpairs, outputs, min_score, tag_func):
         raise NotImplementedError(
             "tag_func must be get_tag, get_tag_with_ZS_as_XS or get_cigarbased_AS_tag: scores are parsed "
             "inside the CUDA kernels, arbitrary Python callables cannot run there")
-    bam_inputs = None
+    bam_inputs = fds = None
     if isinstance(readpairs, ReadPairs) and readpairs.bam:
         from . import bam
         bam_inputs = (bam._all_bytes(readpairs.sam1), bam._all_bytes(readpairs.sam2))
         skip = readpairs.skip_repeated_reads
     elif isinstance(readpairs, ReadPairs):
-        prim, sec = readpairs.record_regions()
         skip = readpairs.skip_repeated_reads
+        fds = _descriptors(readpairs, outputs)      # before anything is read from the inputs
+        if not fds:
+            prim, sec = readpairs.record_regions()
     else:
         prim, sec = _serialise_pairs(readpairs)
         skip = False
@@ -282,6 +284,14 @@ def _walk(mode, readpairs, outputs, min_score, tag_func):
             enabled |= 1 << b
     ctx = _lib.default_context()
     opts = ctx.opts(mode, score_src, skip, float(min_score), enabled)
+    if fds:
+        # real files on both sides (the CLI): the library streams them through pinned staging and appends each bin to
+        # its descriptor in record order (xm_classify_fds); nothing passes through Python
+        (fd1, off1), (fd2, off2), out_fds = fds
+        rc, res = ctx.classify_fds(fd1, off1, fd2, off2, out_fds, opts)
+        if rc != _lib.XM_OK:
+            _raise_for(rc, ctx, res)
+        return _counter(res, mode != _lib.MODE_SE)
     if bam_inputs:
         rc, res, outs = ctx.classify_bam_host(bam_inputs[0], bam_inputs[1], opts)      # inflate on the host, decode + walk on the GPU
     else:
@@ -293,6 +303,40 @@ def _walk(mode, readpairs, outputs, min_score, tag_func):
     if rc != _lib.XM_OK:
         _raise_for(rc, ctx, res)
     return _counter(res, mode != _lib.MODE_SE)
+
+
+def _descriptors(readpairs, outputs):
+    """((fd, byte offset) of both inputs, six output descriptors) when every file involved is a real one, else None.
+    Text inputs must sit where only whole lines were read (after process_headers): then tell() is the byte offset
+    of the first record, which is checked against the raw bytes."""
+    import stat
+    ins = []
+    for f in (readpairs.sam1, readpairs.sam2):
+        try:
+            fd = f.fileno()
+            if not stat.S_ISREG(os.fstat(fd).st_mode):
+                return None
+            pos = f.tell()
+        except (AttributeError, OSError, ValueError):
+            return None
+        if not isinstance(pos, int) or pos < 0 or pos > os.fstat(fd).st_size:
+            return None
+        if pos > 0 and os.pread(fd, 1, pos - 1) != b"\n":
+            return None                      # not at a line start: a decoder-state cookie, not an offset
+        if getattr(f, "newlines", None) not in (None, "\n"):
+            return None                      # universal newlines already translated something: let the text layer decide
+        ins.append((fd, pos))
+    out_fds = []
+    for out in outputs:
+        if not out:
+            out_fds.append(-1)
+            continue
+        try:
+            out.flush()                      # header lines written by process_headers
+            out_fds.append(out.fileno())
+        except (AttributeError, OSError, ValueError):
+            return None
+    return ins[0], ins[1], out_fds
 
 
 def main_single_end(readpairs, primary_specific=sys.stdout, secondary_specific=None, primary_multi=None,
