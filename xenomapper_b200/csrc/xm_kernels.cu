@@ -15,20 +15,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#ifndef XM_OPT_BACKOFF_NS
-#define XM_OPT_BACKOFF_NS 0
-#endif
-#if XM_OPT_BACKOFF_NS
-#define XM_BACKOFF() __nanosleep(XM_OPT_BACKOFF_NS)      /* polling a descriptor that is not there yet: do not hammer L2 */
-#else
-#define XM_BACKOFF() ((void)0)
-#endif
-#ifndef XM_OPT_LASTWARP
-#define XM_OPT_LASTWARP 0
-#endif
-#ifndef XM_OPT_SERVICE
-#define XM_OPT_SERVICE 0
-#endif
 #include "xm_tile.h"
 #include "xm_launch.h"
 
@@ -201,7 +187,7 @@ __device__ void dev_resolve1(unsigned long long *desc, uint32_t tile, unsigned l
             if (done) break;
             const long long idx = j - 32 * q - lane;
             if (idx >= 0)
-                while ((d[q] >> 62) == 0) { XM_BACKOFF(); d[q] = ld_volatile64(desc + idx); }
+                while ((d[q] >> 62) == 0) { d[q] = ld_volatile64(desc + idx); }
             const unsigned incmask = __ballot_sync(0xffffffffu, (d[q] >> 62) == 2);
             const int L = incmask ? __ffs((int)incmask) - 1 : 31;  /* nearest inclusive prefix */
             const bool part = lane <= L;
@@ -264,7 +250,6 @@ __device__ void dev_resolve2(unsigned long long *chain, uint32_t tile, unsigned 
                 if (!((pending >> b) & 1u)) continue;
                 if (idx >= 0)
                     while ((d[q][b] >> 62) == 0) {
-                        XM_BACKOFF();
                         d[q][b] = ld_volatile64(chain + (size_t)idx * C2_SLOTS + b);
 #ifdef XM_PHASE_TIMING
                         ++n_spin;
@@ -292,11 +277,6 @@ __device__ void dev_resolve2(unsigned long long *chain, uint32_t tile, unsigned 
     }
 #endif
     __syncwarp();
-}
-
-__device__ void dev_prefetch_l2(const void *p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 /* ---- warp copy engine ------------------------------------------------------- */

@@ -174,12 +174,8 @@ XM_HD uint32_t shl_pack(uint32_t outlen, int state, int evalerr, int evalstream,
 #define XM_SMEM_INC(p, result) do { result = (*(p))++; } while (0)
 #endif
 
-/* which warp runs the serial look-back sections */
-#if defined(XM_OPT_LASTWARP) && XM_OPT_LASTWARP
-#define XM_LB_WARP(C) (threadIdx.x >= C::THREADS - 32)
-#else
+/* the warp that runs the serial look-back sections */
 #define XM_LB_WARP(C) (threadIdx.x < 32)
-#endif
 
 /* phase timing (profiling builds only): thread 0 adds the cycles since the previous mark to Globals::phase[k] */
 #if XM_DEVICE_PASS && defined(XM_PHASE_TIMING)
@@ -204,7 +200,6 @@ __device__ void dev_resolve1(unsigned long long *desc, uint32_t tile, unsigned l
 __device__ void dev_publish2(unsigned long long *chain, uint32_t tile, const unsigned long long *tot /* smem [C2_SLOTS] */);
 __device__ void dev_resolve2(unsigned long long *chain, uint32_t tile, unsigned long long *tot_to_base /* in: totals; out: exclusive bases */,
                              unsigned long long *dbg /* profiling builds: two counters, else nullptr */);
-__device__ void dev_prefetch_l2(const void *p);
 __device__ void dev_warp_copy(uint8_t *dst, const uint8_t *src_smem, const uint8_t *src_glob, uint32_t len);
 __device__ void dev_copy_piece(uint8_t *dst, const uint8_t *win, uint32_t src_off, uint32_t len);
 #endif
@@ -270,7 +265,6 @@ struct Front {
     bool dirty;            /* the tile's terminator candidates are not all '\n': every line takes the exact parser */
     bool early;            /* the tile's record count was published on chain 1 before the parse finished */
     bool ranked;           /* th.rank is already set */
-    bool resolved;         /* the record base is already in scr64[S64_BASE] (looked up while the lines were parsed) */
     Globals *g;            /* phase timing only */
     int pbase;
     long long tmark;
@@ -330,7 +324,7 @@ XM_HD bool run_head(const Reader &rd, const LineRec &L, const uint4 prev, uint64
  */
 template <class C>
 XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int score_src, uint32_t debug,
-                     bool need_prev, unsigned long long *chain1, uint32_t tile, bool skip, const SCompact *join, Front<C> &fr)
+                     bool need_prev, unsigned long long *chain1, uint32_t tile, bool skip, Front<C> &fr)
 {
     (void)th_;
     const Geo geo = fr.geo;
@@ -465,26 +459,10 @@ XM_HD void front_end(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B, int
     /* a blank line needs two touching W bytes (or a separator opening the stream): without them the tile yields
      * all its owned lines (or, skipping, the run heads among them) and can say so before the parse is over */
     fr.early = !adj && !dirty;
-    fr.resolved = false;
     if (fr.early && !skip) {
         fr.count = fr.nlines;
-#if XM_DEVICE_PASS && defined(XM_OPT_SERVICE) && !XM_OPT_SERVICE
+#if XM_DEVICE_PASS
         if (threadIdx.x == 0) dev_publish1(chain1, tile, fr.nlines, false);
-#elif XM_DEVICE_PASS
-        fr.resolved = true;
-        /* the last warp, which rarely has lines to parse, looks the record base up while the others parse, and
-         * asks for the secondary-stream records the tile will be joined with to be brought into L2 */
-        if (threadIdx.x >= C::THREADS - 32) {
-            if ((threadIdx.x & 31) == 0) dev_publish1(chain1, tile, fr.nlines, false);
-            dev_resolve1(chain1, tile, fr.nlines, false, T.m.scr64 + S64_BASE);
-            __syncwarp();
-            if (join && !T.m.scr64[S64_PSTOP]) {
-                const unsigned long long b0 = T.m.scr64[S64_BASE];
-                const uint32_t lane = threadIdx.x & 31;
-                for (uint32_t k = lane * 8u; k < fr.nlines; k += 256u) dev_prefetch_l2(join->rec + b0 + k);      /* 8 records per 128-byte line */
-                for (uint32_t k = lane * 32u; k < fr.nlines; k += 1024u) dev_prefetch_l2(join->meta + b0 + k);
-            }
-        }
 #else
         unsigned long long o_[2];
         emu_lookback1(chain1, tile, fr.nlines, false, o_);
@@ -678,20 +656,17 @@ XM_HD uint32_t rank_lines(TileCtx<C> &T, ThreadState<C> &th_, const StreamBuf &B
     return tot;
 }
 
-/* record base of a tile through look-back chain 1 (count + stop flag); `early`: the count is already published,
- * `resolved`: the base has been looked up as well (and a barrier has been passed since) */
+/* record base of a tile through look-back chain 1 (count + stop flag); `early`: the count is already published */
 #if XM_DEVICE_PASS
-#define XM_LOOKBACK1(chain, tile, count, stop, early, resolved, base, pstop) do { \
-        if (!(resolved)) { \
-            if (XM_LB_WARP(C)) { \
-                if (!(early) && (threadIdx.x & 31) == 0) dev_publish1((chain), (tile), (count), (stop)); \
-                dev_resolve1((chain), (tile), (count), (stop), T.m.scr64 + S64_BASE); \
-            } \
-            __syncthreads(); \
+#define XM_LOOKBACK1(chain, tile, count, stop, early, base, pstop) do { \
+        if (XM_LB_WARP(C)) { \
+            if (!(early) && (threadIdx.x & 31) == 0) dev_publish1((chain), (tile), (count), (stop)); \
+            dev_resolve1((chain), (tile), (count), (stop), T.m.scr64 + S64_BASE); \
         } \
+        __syncthreads(); \
         base = T.m.scr64[S64_BASE]; pstop = T.m.scr64[S64_PSTOP]; } while (0)
 #else
-#define XM_LOOKBACK1(chain, tile, count, stop, early, resolved, base, pstop) do { \
+#define XM_LOOKBACK1(chain, tile, count, stop, early, base, pstop) do { \
         if (!(early)) { unsigned long long o_[2]; emu_lookback1((chain), (tile), (count), (stop), o_); T.m.scr64[S64_BASE] = o_[0]; T.m.scr64[S64_PSTOP] = o_[1]; } \
         base = T.m.scr64[S64_BASE]; pstop = T.m.scr64[S64_PSTOP]; } while (0)
 #endif
@@ -710,7 +685,7 @@ XM_HD void scan_tile(TileCtx<C> &T, const ScanArgs &a, uint32_t tile)
     Front<C> fr;
     fr.geo = tile_geo<C>(a.S, tile);
     XM_MARK_INIT(fr, a.g, 0);
-    front_end<C>(T, th_, a.S, a.score_src, a.debug, a.skip != 0, a.chain1, tile, a.skip != 0, nullptr, fr);
+    front_end<C>(T, th_, a.S, a.score_src, a.debug, a.skip != 0, a.chain1, tile, a.skip != 0, fr);
 
     if (a.skip && !fr.ranked) {
         XM_THREADS_BEGIN
@@ -721,7 +696,7 @@ XM_HD void scan_tile(TileCtx<C> &T, const ScanArgs &a, uint32_t tile)
     const uint32_t count = rank_lines<C>(T, th_, a.S, fr, a.skip != 0);
 
     unsigned long long base, pstop;
-    XM_LOOKBACK1(a.chain1, tile, count, fr.stop, fr.early, fr.resolved, base, pstop);
+    XM_LOOKBACK1(a.chain1, tile, count, fr.stop, fr.early, base, pstop);
     XM_MARK(fr, 7);
 
     XM_THREADS_BEGIN
@@ -810,7 +785,7 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
     Front<C> fr;
     fr.geo = tile_geo<C>(a.P, tile);
     XM_MARK_INIT(fr, a.g, 12);
-    front_end<C>(T, th_, a.P, a.score_src, a.debug, paired || a.skip, a.chain1, tile, a.skip != 0, &a.sc, fr);
+    front_end<C>(T, th_, a.P, a.score_src, a.debug, paired || a.skip, a.chain1, tile, a.skip != 0, fr);
 
     XM_THREADS_BEGIN
         if (tid < 36) T.m.hist[tid] = 0;
@@ -821,7 +796,7 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
 
     unsigned long long base, pstop;
     XM_MARK(fr, 7);
-    XM_LOOKBACK1(a.chain1, tile, count, fr.stop, fr.early, fr.resolved, base, pstop);
+    XM_LOOKBACK1(a.chain1, tile, count, fr.stop, fr.early, base, pstop);
     XM_MARK(fr, 8);
     /* records at or beyond ncap are not yielded: the other stream ended first, or an error re-run cut here */
     unsigned long long ncap = a.g->n_stream[1];
