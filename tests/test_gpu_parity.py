@@ -81,3 +81,42 @@ def test_cuda_large_synthetic_matches_oracle(ctx, style, mode, skip):
     assert rc == 0, ctx.error()
     assert list(res.counts) == ref["counts"]
     assert outs == ref["outputs"]
+
+
+@pytest.mark.parametrize("style,mode", [(0, 0), (1, 1)], ids=["single_end", "paired"])
+def test_cuda_size_independent_properties(ctx, style, mode):
+    """1.5 M records per stream (1.2 GB, beyond what the oracle is asked to chew in a test): properties that hold
+    at any size.  (1) the walk of a concatenation is the concatenation of the walks (cut at a pair boundary);
+    (2) every bin holds as many lines as its categories counted (xm.py:330-350; unresolved emits both streams);
+    (3) the bytes read are the bytes given."""
+    from xenomapper_b200 import _lib, synth
+    import numpy as np
+    ctx.set_debug(0)
+    n = 1_500_000
+    p, s = synth.generate(n, seed=5, style=style)
+    half = n // 2
+    pa, sa = synth.generate(half, seed=5, style=style)
+    o = _lib.Context.opts(mode, 0, False)
+    rc, res, outs = ctx.classify_host(p, s, o)
+    assert rc == 0, ctx.error()
+    assert int(res.bytes_in[0]) == p.nbytes and int(res.bytes_in[1]) == s.nbytes and int(res.n_records) == n
+    rc1, r1, o1 = ctx.classify_host(pa, sa, o)
+    rc2, r2, o2 = ctx.classify_host(p[pa.nbytes:], s[sa.nbytes:], o)
+    assert rc1 == 0 and rc2 == 0
+    assert [a + b for a, b in zip(o1, o2)] == outs
+    assert [a + b for a, b in zip(r1.counts, r2.counts)] == list(res.counts)
+    lines = [np.count_nonzero(np.frombuffer(x, dtype=np.uint8) == 10) for x in outs]
+    c = list(res.counts)
+    if mode == 0:
+        expect = [c[0], c[1], c[2], c[3], c[4], 2 * c[5]]
+        assert sum(c) == n
+    else:
+        # liberal chain xm.py:423-448: the better ranked of (fwd, rev) in PS > SS > PM > SM > UR > UA; 2 lines per unit, 4 for UR
+        rank = {0: 0, 1: 1, 2: 2, 3: 3, 5: 4, 4: 5}
+        expect = [0] * 6
+        for f in range(6):
+            for r in range(6):
+                b = f if rank[f] <= rank[r] else r
+                expect[b] += c[f * 6 + r] * (4 if b == 5 else 2)
+        assert sum(c) == n // 2                     # every record pair is one unit in the interlaced synthetic data
+    assert lines == expect
