@@ -69,6 +69,8 @@ struct EmuBackend {
         for (uint32_t k = 0; k < a.ntiles; ++k) { t.reset(); classify_tile<C>(t.ctx, a, k); }
     }
     int scan(const ScanArgs &a, bool small) { if (small) scan_t<CfgSmall>(a); else scan_t<CfgBig>(a); return 0; }
+    int scan2(const ScanArgs &) { return -1; }      /* the warp-synchronous scan exists on the device only */
+    uint64_t scan2_tiles(uint64_t) { return 0; }
     int classify(const ClassifyArgs &a, bool small) { if (small) classify_t<CfgSmall>(a); else classify_t<CfgBig>(a); return 0; }
 };
 

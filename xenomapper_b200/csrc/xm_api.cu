@@ -64,6 +64,14 @@ struct DeviceBackend {
     }
     std::string last_error() { return err; }
     int scan(const ScanArgs &a, bool small) { return chk(launch_scan(a, small, st)); }
+    /* the barrier-free scan of clean inputs: 0 launched, -1 not to be used (XM_SCAN2=0), 1 launch error */
+    int scan2(const ScanArgs &a)
+    {
+        static const bool off = [] { const char *e = getenv("XM_SCAN2"); return e && e[0] == '0'; }();
+        if (off) return -1;
+        return chk(launch_scan2(a, st));
+    }
+    uint64_t scan2_tiles(uint64_t len) { const uint64_t t = scan2_tile_bytes(); return (len + t - 1) / t; }
     int classify(const ClassifyArgs &a, bool small) { return chk(launch_classify(a, small, st)); }
 };
 

@@ -368,6 +368,10 @@ __device__ void dev_copy_piece(uint8_t *dst, const uint8_t *win, uint32_t src_of
     }
 }
 
+}  // namespace xm
+#include "xm_scan2.cuh"
+namespace xm {
+
 /* ---- kernels ------------------------------------------------------------------ */
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, (C::THREADS == XM_BIG_THREADS ? XM_BIG_OCC : 4)) k_scan(const ScanArgs a)

@@ -259,6 +259,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
     uint64_t limit = ~0ull;
     uint64_t sc_need = 0;
     Globals G;
+    bool no_scan2 = false;
     int code_first = 0;
     unsigned long long err_first = NO_ERROR;
     for (int attempt = 0; attempt < 6; ++attempt) {
@@ -275,7 +276,9 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
             const double mean = nl ? (double)n / (double)nl : (double)n;
             sc_need = (uint64_t)((double)S.len / mean * 1.05) + 4096;
         }
-        if (!scratch_reserve(be, sc, nt_s, nt_p, sc_need)) { errmsg = "out of device memory for scratch"; return res->status = XM_ERR_NOMEM; }
+        const uint64_t nt_s2 = small ? 0 : be.scan2_tiles(S.len);               /* the barrier-free scan has its own tiling */
+        const uint64_t nt_sc = nt_s > nt_s2 ? nt_s : nt_s2;
+        if (!scratch_reserve(be, sc, nt_sc, nt_p, sc_need)) { errmsg = "out of device memory for scratch"; return res->status = XM_ERR_NOMEM; }
         if (ctl && ctl->want_tail && sc.p_start_cap < sc.sc_cap) {
             be.release(sc.p_start);
             sc.p_start = (uint64_t *)be.alloc(sc.sc_cap * 8 + 16);
@@ -287,7 +290,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         init.err = NO_ERROR;
         init.limit_off = ~0ull;
         be.tick(0);                                  /* the step starts here: scratch init is part of it */
-        if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_s * 8) || be.zero(sc.chain1_p, nt_p * 8) ||
+        if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_sc * 8) || be.zero(sc.chain1_p, nt_p * 8) ||
             be.zero(sc.chain2, nt_p * 8 * C2_SLOTS)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
 
         ScanArgs sa;
@@ -303,12 +306,34 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         if (ctl) { ca.halo = ctl->halo; if (ctl->want_tail) { ca.p_start = sc.p_start; ca.p_start_cap = sc.p_start_cap; } }
 
         be.tick(3);
-        if (be.scan(sa, small)) { errmsg = "scan kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+        /* clean inputs take the barrier-free scan (xm_scan2.cuh); it says so when a span needs the exact kernel */
+        bool scanned = false;
+        if (!small && !(debug & DBG_FORCE_GENERIC) && !no_scan2) {
+            ScanArgs s2 = sa;
+            s2.ntiles = (uint32_t)be.scan2_tiles(S.len);
+            const int r2 = s2.ntiles ? be.scan2(s2) : -1;
+            if (r2 > 0) { errmsg = "scan kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            if (r2 == 0) {
+                Globals G2;
+                if (be.read(&G2, sc.g, sizeof G2)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+                res->n_launches += 1;
+                if (!G2.pad) scanned = true;
+                else {
+                    no_scan2 = true;            /* and for the re-runs of this call */
+                    if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_sc * 8)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
+                    be.tick(3);
+                }
+            }
+        }
+        if (!scanned) {
+            if (be.scan(sa, small)) { errmsg = "scan kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            res->n_launches += 1;
+        }
         be.tick(1);
         if (be.classify(ca, small)) { errmsg = "classify kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
         be.tick(2);
         if (be.sync()) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
-        res->n_launches += 2;
+        res->n_launches += 1;
         res->ms_scan = be.elapsed(3, 1); res->ms_classify = be.elapsed(1, 2); res->ms_total += be.elapsed(0, 2);
         if (be.read(&G, sc.g, sizeof G)) { errmsg = "result read failed"; return res->status = XM_ERR_CUDA; }
 
