@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define XM_ABI_VERSION 3
+#define XM_ABI_VERSION 4
 
 /* States and bins share one numbering: the order of the reference's output
  * arguments (xm.py:291-297).  counts[] is indexed [state] for single-end and
@@ -189,6 +189,15 @@ typedef struct xm_bam_stats {
     uint64_t bam_bytes, inflated_bytes, text_bytes, records;
 } xm_bam_stats;
 int xm_bam_get_stats(xm_ctx *ctx, xm_bam_stats *out, int reset);
+
+/* Which kernels the last resident walk (the last step of a chunked one) ran:
+ * clean, error-free inputs take the barrier-free pair; anything else the exact
+ * pair.  For benchmarks and tests. */
+#define XM_KERNEL_SCAN2 1u
+#define XM_KERNEL_CLASSIFY2 2u
+#define XM_KERNEL_SCAN 4u
+#define XM_KERNEL_CLASSIFY 8u
+int xm_get_walk_kernels(xm_ctx *ctx, uint32_t *mask);
 
 /* ---- device memory helpers (so bindings need no CUDA of their own) ----- */
 int xm_dev_alloc(xm_ctx *ctx, uint64_t bytes, void **d_ptr);

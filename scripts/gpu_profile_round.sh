@@ -6,6 +6,6 @@ python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail 
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 CMD="python bench.py --records 2000000 --steps 2 --warmup 3 --no-cpu --no-e2e"
 $CMD > gpurun_out/prof_plain.json 2>/dev/null && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_ -s 6 -c 2 -o gpurun_out/r01_prof_final -f $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches2.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_ -s 6 -c 2 -o gpurun_out/r01_prof_final2 -f $CMD > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | tail -8

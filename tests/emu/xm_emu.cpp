@@ -71,6 +71,7 @@ struct EmuBackend {
     int scan(const ScanArgs &a, bool small) { if (small) scan_t<CfgSmall>(a); else scan_t<CfgBig>(a); return 0; }
     int scan2(const ScanArgs &) { return -1; }      /* the warp-synchronous scan exists on the device only */
     uint64_t scan2_tiles(uint64_t) { return 0; }
+    int classify2(const ClassifyArgs &) { return -1; }
     int classify(const ClassifyArgs &a, bool small) { if (small) classify_t<CfgSmall>(a); else classify_t<CfgBig>(a); return 0; }
 };
 

@@ -120,3 +120,39 @@ def test_cuda_size_independent_properties(ctx, style, mode):
                 expect[b] += c[f * 6 + r] * (4 if b == 5 else 2)
         assert sum(c) == n // 2                     # every record pair is one unit in the interlaced synthetic data
     assert lines == expect
+
+
+def test_cuda_kernel_selection_and_fallback(ctx):
+    """clean, error-free input runs the barrier-free pair (k_scan2 / k_classify2); anything they do not handle --
+    here a space inside a record, then a duplicated AS tag -- sends the walk through the exact pair, with the
+    reference's result either way"""
+    from oracle import oracle
+    from xenomapper_b200 import _lib, synth
+    ctx.set_debug(0)
+    p, s = synth.generate(50000, seed=9, style=0)
+    o = _lib.Context.opts(0, 0, True)
+    rc, res, outs = ctx.classify_host(p, s, o)
+    assert rc == 0 and ctx.walk_kernels() == ["k_scan2", "k_classify2"]
+    ref = oracle.classify(p, s, skip_repeated=True)
+    assert outs == ref["outputs"] and list(res.counts) == ref["counts"]
+    # a space in the secondary stream: k_scan2 declines, k_scan runs; the primary stream is still clean
+    sd = bytes(s).replace(b"\tXM:i:", b" XM:i:", 1)
+    rc, res, outs = ctx.classify_host(p, sd, o)
+    ref = oracle.classify(p, sd, skip_repeated=True)
+    assert rc == 0 and "k_scan" in ctx.walk_kernels()
+    assert outs == ref["outputs"] and list(res.counts) == ref["counts"]
+    # a space in the primary stream: k_classify2 declines
+    pd = bytes(p).replace(b"\tXM:i:", b" XM:i:", 1)
+    rc, res, outs = ctx.classify_host(pd, s, o)
+    ref = oracle.classify(pd, s, skip_repeated=True)
+    assert rc == 0 and "k_classify" in ctx.walk_kernels()
+    assert outs == ref["outputs"] and list(res.counts) == ref["counts"]
+    # an input error (two AS tags): reported by the exact kernels, outputs up to the failing record
+    pe = bytes(p)
+    cut = pe.index(b"\n", len(pe) // 2) + 1
+    line_end = pe.index(b"\n", cut)
+    pe = pe[:line_end] + b"\tAS:i:1" + pe[line_end:]
+    rc, res, outs = ctx.classify_host(pe, s, o)
+    ref = oracle.classify(pe, s, skip_repeated=True)
+    assert ERR[rc] == "ValueError" and ref["err"] == 2
+    assert outs == ref["outputs"]

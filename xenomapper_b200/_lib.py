@@ -22,7 +22,7 @@ EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_cla
            "xm_classify_host", "xm_get_output", "xm_classify_fds", "xm_count_device", "xm_dev_alloc",
            "xm_dev_free", "xm_host_alloc_pinned", "xm_host_free_pinned", "xm_memcpy_h2d", "xm_memcpy_d2h",
            "xm_memcpy_d2d", "xm_dev_mem_info", "xm_set_debug", "xm_locate_device", "xm_classify_bam_host",
-           "xm_bam_header_text", "xm_bam_render_host", "xm_bam_get_stats")
+           "xm_bam_header_text", "xm_bam_render_host", "xm_bam_get_stats", "xm_get_walk_kernels")
 
 
 class Opts(C.Structure):
@@ -94,6 +94,7 @@ def load():
     L.xm_bam_header_text.argtypes = [vp, u64, vp, u64, C.POINTER(u64)]
     L.xm_bam_render_host.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
     L.xm_bam_get_stats.argtypes = [vp, C.POINTER(BamStats), i]
+    L.xm_get_walk_kernels.argtypes = [vp, C.POINTER(C.c_uint32)]
     for name in EXPORTS:
         if name not in ("xm_create", "xm_destroy", "xm_last_error", "xm_abi_version"):
             getattr(L, name).restype = i
@@ -235,6 +236,12 @@ class Context:
             raise UnsupportedInput(self.error())
         del keep
         return C.string_at(p.value, ln.value) if ln.value else b""
+
+    def walk_kernels(self):
+        """names of the kernels the last resident walk ran"""
+        m = C.c_uint32()
+        self.lib.xm_get_walk_kernels(self.h, C.byref(m))
+        return [n for b, n in enumerate(("k_scan2", "k_classify2", "k_scan", "k_classify")) if (m.value >> b) & 1]
 
     def bam_stats(self, reset=True):
         st = BamStats()

@@ -71,6 +71,12 @@ struct DeviceBackend {
         if (off) return -1;
         return chk(launch_scan2(a, st));
     }
+    int classify2(const ClassifyArgs &a)
+    {
+        static const bool off = [] { const char *e = getenv("XM_CLASSIFY2"); return e && e[0] == '0'; }();
+        if (off) return -1;
+        return chk(launch_classify2(a, st));
+    }
     uint64_t scan2_tiles(uint64_t len) { const uint64_t t = scan2_tile_bytes(); return (len + t - 1) / t; }
     int classify(const ClassifyArgs &a, bool small) { return chk(launch_classify(a, small, st)); }
 };
@@ -654,6 +660,13 @@ int xm_classify_bam_host(xm_ctx *c, const void *prim_bam, uint64_t prim_len, con
         if (((o.enabled_bins >> b) & 1u) && res->out_len[b]) { const int r2 = bin_append_d2h(c, b, outs[b], res->out_len[b]); if (r2) return r2; }
     if (cudaStreamSynchronize(c->dl) != cudaSuccess) return fail(c, XM_ERR_CUDA, "D2H copy failed");
     return rc;
+}
+
+int xm_get_walk_kernels(xm_ctx *c, uint32_t *mask)
+{
+    if (!c || !mask) return XM_ERR_ARG;
+    *mask = c->scratch.last_kernels;
+    return XM_OK;
 }
 
 int xm_bam_get_stats(xm_ctx *c, xm_bam_stats *out, int reset)

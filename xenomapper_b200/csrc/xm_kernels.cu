@@ -368,6 +368,46 @@ __device__ void dev_copy_piece(uint8_t *dst, const uint8_t *win, uint32_t src_of
     }
 }
 
+/*
+ * Copies len bytes between arbitrarily aligned global addresses, called by a full warp: unaligned head and tail
+ * bytes by single lanes, the 16-byte aligned body of the destination as vector stores assembled from two aligned
+ * source vectors with funnel shifts (the shift is the same for the whole piece).  The source was read by this
+ * kernel a few hundred tiles ago and normally still sits in L2; it is readable up to the next multiple of 16.
+ */
+__device__ void dev_copy_global(uint8_t *dst, const uint8_t *src, uint32_t len)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+    if (head > len) head = len;
+    const uint32_t rest = len - head, nchunk = rest >> 4, tail = rest & 15u;
+    const uint8_t *so = src + head;
+    const uint32_t u = (uint32_t)((uintptr_t)so & 15u);
+    const uint8_t *sa = so - u;
+    uint8_t *body = dst + head;
+    if (lane < head) dst[lane] = src[lane];
+    if (lane < tail) body[16u * nchunk + lane] = so[16u * nchunk + lane];
+    const uint32_t bsh = (u & 3u) * 8u;
+    if (u == 0) {
+#pragma unroll 4
+        for (uint32_t c = lane; c < nchunk; c += 32u)
+            __stcs((uint4 *)(body + 16u * c), ld_src16(sa + 16u * c, false));
+        return;
+    }
+#pragma unroll 2
+    for (uint32_t c = lane; c < nchunk; c += 32u) {
+        const uint4 q0 = ld_src16(sa + 16u * c, false);
+        const uint4 q1 = ld_src16(sa + 16u * c + 16u, false);
+        uint4 o;
+        switch (u >> 2) {
+        case 0: o.x = __funnelshift_r(q0.x, q0.y, bsh); o.y = __funnelshift_r(q0.y, q0.z, bsh); o.z = __funnelshift_r(q0.z, q0.w, bsh); o.w = __funnelshift_r(q0.w, q1.x, bsh); break;
+        case 1: o.x = __funnelshift_r(q0.y, q0.z, bsh); o.y = __funnelshift_r(q0.z, q0.w, bsh); o.z = __funnelshift_r(q0.w, q1.x, bsh); o.w = __funnelshift_r(q1.x, q1.y, bsh); break;
+        case 2: o.x = __funnelshift_r(q0.z, q0.w, bsh); o.y = __funnelshift_r(q0.w, q1.x, bsh); o.z = __funnelshift_r(q1.x, q1.y, bsh); o.w = __funnelshift_r(q1.y, q1.z, bsh); break;
+        default: o.x = __funnelshift_r(q0.w, q1.x, bsh); o.y = __funnelshift_r(q1.x, q1.y, bsh); o.z = __funnelshift_r(q1.y, q1.z, bsh); o.w = __funnelshift_r(q1.z, q1.w, bsh); break;
+        }
+        __stcs((uint4 *)(body + 16u * c), o);
+    }
+}
+
 }  // namespace xm
 #include "xm_scan2.cuh"
 namespace xm {

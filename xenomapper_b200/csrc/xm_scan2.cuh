@@ -35,39 +35,45 @@ struct Scan2Cfg {
 #define XM_SCAN2_WARPS 8
 #endif
 #ifndef XM_SCAN2_SPAN
-#define XM_SCAN2_SPAN 10240
+#define XM_SCAN2_SPAN 12288
 #endif
 #ifndef XM_SCAN2_OCC
 #define XM_SCAN2_OCC 4
 #endif
 using Scan2Big = Scan2Cfg<XM_SCAN2_WARPS, XM_SCAN2_SPAN, 1024, 2048>;
 
-template <class C>
-__global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const ScanArgs a)
-{
-    __shared__ uint32_t s_tbm[C::WARPS][C::NWW], s_nlm[C::WARPS][C::NWW];
-    __shared__ uint16_t s_trk[C::WARPS][C::NWW];
-    __shared__ uint16_t s_start[C::WARPS][C::LQ];
-    __shared__ uint32_t s_cnt[C::WARPS];
-    __shared__ unsigned long long s_base[2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x;
-    const uint64_t span_lo = ((uint64_t)tile * C::WARPS + (uint64_t)warp) * (uint64_t)C::SPAN;
-    const bool live = span_lo < a.S.len;
-    const bool skip = a.skip != 0;
-    bool bad = false;                                 /* this span needs the exact kernel */
+/* what a warp knows about its span once the masks are built and the line starts are listed */
+struct SpanInfo {
+    uint64_t win0, wend;       /* the window [win0, wend) in the stream */
+    uint32_t hoff, wbytes;     /* the span's first byte inside the window; bytes in the window */
+    uint32_t j0, nown;         /* index (in starts[]) of the first owned line; owned lines */
+    bool live, bad;            /* the span lies inside the stream; it needs the exact kernel */
+};
 
-    uint32_t *tbm = s_tbm[warp], *nlm = s_nlm[warp];
-    uint16_t *trk = s_trk[warp], *starts = s_start[warp];
+/* masks (tbm, nlm, trk: this warp's private shared memory), line starts and the owned range of one span.
+ * need_prev: the line before the first owned one will be looked at (run heads, pair units). */
+template <class C>
+__device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span_lo, bool need_prev, uint32_t *tbm, uint32_t *nlm, uint16_t *trk, uint16_t *starts)
+{
+    const int lane = threadIdx.x & 31;
+    SpanInfo si;
+    si.live = span_lo < B.len;
+    si.bad = false;
     /* window: [win0, win0 + wbytes); the span's first byte sits at hoff.  The bytes before it are looked at for the
-     * line that precedes the span (its last newline decides whether the span opens a line; skipping needs its QNAME) */
-    const uint64_t win0 = live ? (span_lo >= (uint64_t)C::BACK ? span_lo - C::BACK : 0) : 0;
-    const uint32_t hoff = (uint32_t)(span_lo - win0);
-    uint64_t wend = span_lo + C::SPAN + C::EXT;
-    if (wend > a.S.len) wend = a.S.len;
-    const uint32_t wbytes = live ? (uint32_t)(wend - win0) : 0u;
+     * line that precedes the span (its last newline decides whether the span opens a line) */
+    si.win0 = si.live ? (span_lo >= (uint64_t)C::BACK ? span_lo - C::BACK : 0) : 0;
+    si.hoff = (uint32_t)(span_lo - si.win0);
+    si.wend = span_lo + C::SPAN + C::EXT;
+    if (si.wend > B.len) si.wend = B.len;
+    si.wbytes = si.live ? (uint32_t)(si.wend - si.win0) : 0u;
+    si.j0 = 0; si.nown = 0;
+    const uint64_t win0 = si.win0, wend = si.wend;
+    const uint32_t hoff = si.hoff, wbytes = si.wbytes;
+    const bool live = si.live;
+    const bool skip = need_prev;
+    bool bad = false;
     const uint32_t own_hi = hoff + C::SPAN < wbytes ? hoff + (uint32_t)C::SPAN : wbytes;     /* owned starts lie in [hoff, own_hi) */
-    const uint8_t *win = a.S.p + win0;          /* read through L1/L2: no staged copy, so a SM holds 32 of these warps */
+    const uint8_t *win = B.p + win0;          /* read through L1/L2: no staged copy, so a SM holds 32 of these warps */
 
     /* ---- masks and line starts ------------------------------------------------------------------ */
     uint32_t nst = 0;                                 /* line starts listed so far (uniform) */
@@ -151,13 +157,38 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
         if (j1 > j0) {
             if (j1 >= nst) bad = true;
         }
-        if (wend == a.S.len && !bad) {
+        if (wend == B.len && !bad) {
             const uint32_t last = nst ? (uint32_t)starts[nst - 1] : 0xffffffffu;
             if (last != wbytes && own_hi == wbytes) bad = true;       /* unterminated last line */
         }
         if (skip && j1 > j0 && j0 == 0 && win0 + starts[0] != 0) bad = true;      /* the line before the span is not in the window */
     }
-    const uint32_t nown = (live && !bad) ? j1 - j0 : 0u;
+    si.bad = bad;
+    si.j0 = j0;
+    si.nown = (live && !bad) ? j1 - j0 : 0u;
+    return si;
+}
+
+
+template <class C>
+__global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const ScanArgs a)
+{
+    __shared__ uint32_t s_tbm[C::WARPS][C::NWW], s_nlm[C::WARPS][C::NWW];
+    __shared__ uint16_t s_trk[C::WARPS][C::NWW];
+    __shared__ uint16_t s_start[C::WARPS][C::LQ];
+    __shared__ uint32_t s_cnt[C::WARPS];
+    __shared__ unsigned long long s_base[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint64_t span_lo = ((uint64_t)tile * C::WARPS + (uint64_t)warp) * (uint64_t)C::SPAN;
+    const bool skip = a.skip != 0;
+    uint32_t *tbm = s_tbm[warp], *nlm = s_nlm[warp];
+    uint16_t *trk = s_trk[warp], *starts = s_start[warp];
+    const SpanInfo si = span_front<C>(a.S, span_lo, skip, tbm, nlm, trk, starts);
+    bool bad = si.bad;                                /* this span needs the exact kernel */
+    const uint64_t win0 = si.win0;
+    const uint32_t wbytes = si.wbytes, j0 = si.j0, nown = si.nown;
+    const uint8_t *win = a.S.p + win0;
 
     /* ---- parse: one line per lane ---------------------------------------------------------------- */
     /* skipping walks also parse the head of the line before the first owned one (lane 0 of the first batch) */
@@ -242,6 +273,294 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
         if (a.sc.start && n <= a.sc_cap) a.sc.start[n] = a.S.len;
     }
 }
+
+/* =========================================================================
+ * k_classify2: the primary-stream walk in the same barrier-free style.
+ * Each warp parses the lines of its span, joins them with the secondary
+ * stream's compact rows by record index, decides the categories, sizes its
+ * part of the six bins with warp scans and copies its lines global -> global
+ * (the span was read from HBM microseconds earlier and is still in L2).  The
+ * warps of a CTA meet four times per tile: record counts, record base (chain
+ * 1), byte totals per bin, byte bases (chain 2).  Clean inputs without errors
+ * only; everything else raises the fallback flag and k_classify runs.
+ * ========================================================================= */
+#ifndef XM_CLS2_OCC
+#define XM_CLS2_OCC 3
+#endif
+constexpr int CLS2_LINES = 64;            /* lines (with the context line) a span may hold: two batches */
+
+template <class C>
+struct Cls2Smem {
+    uint32_t tbm[C::WARPS][C::NWW], nlm[C::WARPS][C::NWW];
+    uint16_t trk[C::WARPS][C::NWW];
+    uint16_t starts[C::WARPS][C::LQ];
+    /* per parsed line */
+    int32_t as[C::WARPS][CLS2_LINES], xs[C::WARPS][CLS2_LINES];
+    uint32_t h1[C::WARPS][CLS2_LINES], h2[C::WARPS][CLS2_LINES];
+    uint32_t so[C::WARPS][CLS2_LINES];          /* start (16) | emitted length (16) */
+    uint32_t q[C::WARPS][CLS2_LINES];           /* QNAME start (16) | QNAME length (16) */
+    uint16_t rank[C::WARPS][CLS2_LINES];        /* rank among the span's yielded records, 0xffff none */
+    uint32_t cnt[C::WARPS];
+    uint32_t wtot[C::WARPS][8];                 /* bytes per bin (6), raw bytes (slot 6) of each warp */
+    unsigned long long tot[8], keep[8];
+    unsigned long long base1[2];
+    uint32_t hist[36];
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const ClassifyArgs a)
+{
+    extern __shared__ uint4 xm_smem_c2[];
+    Cls2Smem<C> &S = *reinterpret_cast<Cls2Smem<C> *>(xm_smem_c2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint64_t span_lo = ((uint64_t)tile * C::WARPS + (uint64_t)warp) * (uint64_t)C::SPAN;
+    const bool skip = a.skip != 0, paired = a.mode != MODE_SE;
+    const bool need_prev = skip || paired;
+    uint32_t *tbm = S.tbm[warp], *nlm = S.nlm[warp];
+    uint16_t *trk = S.trk[warp], *starts = S.starts[warp];
+    /* copy items (primary part and secondary part of what line k emits) overlay the warp's tab mask, which is dead
+     * once the lines are parsed: dst | src (16) + len (16) | dst | len, then bin and line count bytes */
+    static_assert(C::NWW * 4 >= CLS2_LINES * 18, "the copy items overlay the tab mask");
+    uint32_t *it_dst = tbm, *it_sl = tbm + CLS2_LINES, *is_dst = tbm + 2 * CLS2_LINES, *is_len = tbm + 3 * CLS2_LINES;
+    uint8_t *it_bin = (uint8_t *)(tbm + 4 * CLS2_LINES), *is_nl = it_bin + CLS2_LINES;
+    if (threadIdx.x < 36) S.hist[threadIdx.x] = 0;
+    const SpanInfo si = span_front<C>(a.P, span_lo, need_prev, tbm, nlm, trk, starts);
+    bool bad = si.bad;
+    const uint64_t win0 = si.win0;
+    const uint32_t wbytes = si.wbytes, j0 = si.j0, nown = si.nown;
+    const uint8_t *win = a.P.p + win0;
+    const WinMasks M_{win, tbm, nlm, trk, wbytes, false};
+    const Reader rd_{win, a.P.p, win0, wbytes, a.P.len};
+
+    /* ---- parse: one line per lane; line 0 is the line before the span when the walk looks at predecessors ---- */
+    const bool ctx = need_prev && nown > 0 && (win0 + starts[j0]) != 0;
+    const uint32_t first = ctx ? j0 - 1u : j0;
+    const uint32_t nparse = nown + (ctx ? 1u : 0u);
+    if (nparse > (uint32_t)CLS2_LINES) bad = true;
+    uint32_t count = 0;
+    {
+        uint32_t prev_qlen = 0, prev_h1 = 0, prev_h2 = 0, prev_qs = 0;
+        for (uint32_t kb = 0; kb < nparse && !bad; kb += 32u) {
+            const uint32_t k = kb + (uint32_t)lane;
+            const bool mine = k < nparse;
+            bool ok = true;
+            LineRec L;
+            L.qlen = 0; L.h1 = 0; L.h2 = 0; L.qs = 0; L.flags = 0; L.as = SCORE_ABSENT; L.xs = SCORE_ABSENT; L.s = 0; L.outlen = 0; L.rawbytes = 0;
+            if (mine) {
+                const int s = (int)starts[first + k], e = (int)starts[first + k + 1] - 1;
+                FastCtx fc;
+                ok = fast_head(M_, s, e, L, fc);
+                if (ok && (paired || !(ctx && k == 0))) fast_tail(M_, s, e, a.score_src, fc, L);
+                if (L.flags) ok = false;                      /* score errors are reported by the exact kernel */
+            }
+            if (__any_sync(0xffffffffu, !ok)) { bad = true; break; }
+            uint32_t pq = __shfl_up_sync(0xffffffffu, L.qlen, 1), p1 = __shfl_up_sync(0xffffffffu, L.h1, 1),
+                     p2 = __shfl_up_sync(0xffffffffu, L.h2, 1), ps = __shfl_up_sync(0xffffffffu, L.qs, 1);
+            if (lane == 0) { pq = prev_qlen; p1 = prev_h1; p2 = prev_h2; ps = prev_qs; }
+            prev_qlen = __shfl_sync(0xffffffffu, L.qlen, 31); prev_h1 = __shfl_sync(0xffffffffu, L.h1, 31);
+            prev_h2 = __shfl_sync(0xffffffffu, L.h2, 31); prev_qs = __shfl_sync(0xffffffffu, L.qs, 31);
+            bool yield = mine && !(ctx && k == 0);
+            /* does this line carry the QNAME of the line before it?  (run heads xm.py:110-114, pair units xm.py:402) */
+            bool same = false;
+            if (mine && k > 0 && pq == L.qlen && p1 == L.h1 && p2 == L.h2) same = names_equal(rd_, win0 + ps, pq, win0 + L.qs, L.qlen);
+            if (skip && same) yield = false;
+            const uint32_t ym = __ballot_sync(0xffffffffu, yield);
+            if (mine) {
+                S.as[warp][k] = L.as; S.xs[warp][k] = L.xs; S.h1[warp][k] = L.h1; S.h2[warp][k] = L.h2;
+                S.so[warp][k] = L.s | (L.outlen << 16);
+                S.q[warp][k] = (same ? 1u : 0u);              /* all later phases need of the QNAME */
+                S.rank[warp][k] = yield ? (uint16_t)(count + (uint32_t)__popc(ym & ((1u << lane) - 1u))) : (uint16_t)0xffff;
+            }
+            count += (uint32_t)__popc(ym);
+        }
+    }
+    if (bad) { count = 0; if (lane == 0) a.g->pad = 1u; }
+
+    /* ---- record base: chain 1 ------------------------------------------------------------------- */
+    if (lane == 0) S.cnt[warp] = count;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < C::WARPS; ++w) { const uint32_t c = S.cnt[w]; if (w < warp) wbase += c; total += c; }
+    if (warp == 0) {
+        if (lane == 0) dev_publish1(a.chain1, tile, total, false);
+        dev_resolve1(a.chain1, tile, total, false, S.base1);
+    }
+    __syncthreads();
+    const unsigned long long base = S.base1[0] + wbase;        /* record index of this span's first yielded record */
+    unsigned long long ncap = a.g->n_stream[1];
+    if (a.limit < ncap) ncap = a.limit;
+
+    /* ---- join, decide, size ------------------------------------------------------------------------ */
+    uint32_t wtot[7] = {0, 0, 0, 0, 0, 0, 0};
+    {
+        int pst_carry = 0;                       /* state, emitted lengths and validity of the line before lane 0's */
+        uint32_t pout_carry = 0, pslen_carry = 0, pso_carry = 0;
+        bool pvalid_carry = false;
+        for (uint32_t kb = 0; kb < nparse && !bad; kb += 32u) {
+            const uint32_t k = kb + (uint32_t)lane;
+            const bool mine = k < nparse;
+            const uint32_t rk = mine ? (uint32_t)S.rank[warp][k] : 0xffffu;
+            /* record index: yielded lines by their rank; the context line is the record before the span's first */
+            bool valid = false;
+            unsigned long long gi = 0;
+            if (mine) {
+                if (rk != 0xffffu) { gi = base + rk; valid = gi < ncap; }
+                else if (ctx && k == 0 && !skip && base > 0) { gi = base - 1; valid = gi < ncap; }
+            }
+            int st = UA;
+            uint32_t slen = 0, so = 0;
+            bool mismatch = false;
+            if (valid) {
+                const uint4 sr = a.sc.rec[gi];
+                const uint32_t smeta = a.sc.meta[gi];
+                if ((smeta >> META_LEN_BITS) || sr.z != S.h1[warp][k] || sr.w != S.h2[warp][k]) mismatch = true;     /* dirty / failing secondary line, QNAME assert: exact kernel */
+                slen = smeta & META_LEN_MASK;
+                st = mapping_state(S.as[warp][k], S.xs[warp][k], (int32_t)sr.x, (int32_t)sr.y, a.thr);
+                so = S.so[warp][k];
+                if (rk != 0xffffu && a.p_start && gi < a.p_start_cap) a.p_start[gi] = win0 + (so & 0xffffu);
+            }
+            if (__any_sync(0xffffffffu, mismatch)) { bad = true; break; }
+            const uint32_t outlen = so >> 16;
+            /* the line before, for pair units */
+            int pst = __shfl_up_sync(0xffffffffu, st, 1);
+            uint32_t pout = __shfl_up_sync(0xffffffffu, outlen, 1), pslen = __shfl_up_sync(0xffffffffu, slen, 1), pso = __shfl_up_sync(0xffffffffu, so, 1);
+            bool pvalid = __shfl_up_sync(0xffffffffu, (int)valid, 1) != 0;
+            if (lane == 0) { pst = pst_carry; pout = pout_carry; pslen = pslen_carry; pso = pso_carry; pvalid = pvalid_carry; }
+            pst_carry = __shfl_sync(0xffffffffu, st, 31); pout_carry = __shfl_sync(0xffffffffu, outlen, 31);
+            pslen_carry = __shfl_sync(0xffffffffu, slen, 31); pso_carry = __shfl_sync(0xffffffffu, so, 31);
+            pvalid_carry = __shfl_sync(0xffffffffu, (int)valid, 31) != 0;
+
+            uint32_t key = 36, bin = NO_BIN, plen = 0, sbytes = 0, src = 0, raw = 0;
+            int nl = 1;
+            if (valid && rk != 0xffffu) {
+                raw = outlen;
+                if (!paired) {
+                    if (!(a.halo && gi == 0)) {
+                        key = (uint32_t)st; bin = (uint32_t)st;
+                        const bool pside = st == PS || st == PM || st == UA || st == UR, sside = st == SS || st == SM || st == UR;
+                        plen = pside ? outlen : 0u; sbytes = sside ? slen : 0u; src = so & 0xffffu;
+                    }
+                } else if (!skip && S.q[warp][k] && pvalid && gi > 0) {
+                    key = (uint32_t)(pst * 6 + st);
+                    bin = (uint32_t)(a.mode == MODE_PE_CONSERVATIVE ? pair_bin_conservative(pst, st) : pair_bin_liberal(pst, st));
+                    const bool pside = bin == PS || bin == PM || bin == UA || bin == UR, sside = bin == SS || bin == SM || bin == UR;
+                    plen = pside ? pout + outlen : 0u; sbytes = sside ? pslen + slen : 0u; src = pso & 0xffffu; nl = 2;
+                }
+                if (bin != NO_BIN && !((a.enabled >> bin) & 1u)) { plen = 0; sbytes = 0; }
+            }
+            dev_hist_add(S.hist, key);
+            /* offsets inside the warp's part of each bin */
+            const uint32_t bytes = plen + sbytes;
+            uint32_t off = 0;
+#pragma unroll
+            for (uint32_t b = 0; b < 6; ++b) {
+                const uint32_t v = bin == b ? bytes : 0u;
+                if (__any_sync(0xffffffffu, v != 0u)) {
+                    uint32_t x = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                    if (bin == b) off = wtot[b] + x - v;
+                    wtot[b] += __shfl_sync(0xffffffffu, x, 31);
+                }
+            }
+            wtot[6] += __reduce_add_sync(0xffffffffu, raw);
+            /* copy items; neighbouring primary parts that continue each other in the input and in the bin are merged */
+            const uint32_t pend_src = src + plen, pend_dst = off + plen;
+            const uint32_t q_src = __shfl_up_sync(0xffffffffu, pend_src, 1), q_dst = __shfl_up_sync(0xffffffffu, pend_dst, 1),
+                           q_bin = __shfl_up_sync(0xffffffffu, bin, 1), q_len = __shfl_up_sync(0xffffffffu, plen, 1);
+            const bool head = plen && !(lane > 0 && q_len && q_bin == bin && q_src == src && q_dst == off);
+            const uint32_t heads = __ballot_sync(0xffffffffu, head || !plen);          /* lanes that end the run before them */
+            const uint32_t above = heads & (lane == 31 ? 0u : (0xffffffffu << (lane + 1)));
+            const int last = above ? __ffs((int)above) - 2 : 31;                        /* last lane of this lane's run */
+            const uint32_t run_end = __shfl_sync(0xffffffffu, pend_src, last);
+            if (mine) {
+                it_dst[k] = off; it_bin[k] = (uint8_t)bin;
+                it_sl[k] = head ? (src | ((run_end - src) << 16)) : 0u;
+                is_dst[k] = off + plen; is_len[k] = sbytes; is_nl[k] = (uint8_t)nl;
+            }
+        }
+    }
+    if (bad) {
+        if (lane == 0) a.g->pad = 1u;
+#pragma unroll
+        for (int b = 0; b < 7; ++b) wtot[b] = 0;
+    }
+
+    /* ---- byte bases: chain 2 ------------------------------------------------------------------------- */
+    if (lane < 8) S.wtot[warp][lane] = 0;
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < 7; ++b) S.wtot[warp][b] = wtot[b];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane < 8) {
+            unsigned long long t = 0;
+            for (int w = 0; w < C::WARPS; ++w) t += S.wtot[w][lane];
+            S.tot[lane] = t; S.keep[lane] = t;
+        }
+        __syncwarp();
+        dev_publish2(a.chain2, tile, S.tot);
+        dev_resolve2(a.chain2, tile, S.tot, nullptr);
+    }
+    __syncthreads();
+
+    /* ---- copy -------------------------------------------------------------------------------------------- */
+    if (!bad) {
+        unsigned long long wb[6];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            unsigned long long t = S.tot[b];
+            for (int w = 0; w < warp; ++w) t += S.wtot[w][b];
+            wb[b] = t;
+        }
+        for (uint32_t k = 0; k < nparse; ++k) {
+            const uint32_t sl = it_sl[k], slen = is_len[k];
+            if (!sl && !slen) continue;
+            const uint32_t bin = it_bin[k];
+            unsigned long long bb = 0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) if ((int)bin == b) bb = wb[b];
+            if (sl) {
+                const uint32_t len = sl >> 16;
+                const unsigned long long doff = bb + it_dst[k];
+                if (doff + len <= a.out_cap[bin]) dev_copy_global(a.out[bin] + doff, win + (sl & 0xffffu), len);
+            }
+            if (slen) {
+                const unsigned long long doff = bb + is_dst[k];
+                const unsigned long long gi = base + S.rank[warp][k];
+                const uint64_t ss = a.sc.start[is_nl[k] == 2 ? gi - 1 : gi];
+                if (doff + slen <= a.out_cap[bin]) dev_copy_global(a.out[bin] + doff, a.S.p + ss, slen);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 36 && S.hist[threadIdx.x]) atomicAdd(&a.g->counts[threadIdx.x], (unsigned long long)S.hist[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        if (S.keep[6]) atomicAdd(&a.g->bytes_in[0], S.keep[6]);
+        if (tile + 1 == a.ntiles) {
+            a.g->n_stream[0] = S.base1[0] + total;
+            a.g->end_off[0] = a.P.len;
+            for (int b = 0; b < 6; ++b) a.g->out_len[b] = S.tot[b] + S.keep[b];
+        }
+    }
+}
+
+template <class C>
+static cudaError_t launch_classify2_t(ClassifyArgs a, cudaStream_t st)
+{
+    const uint64_t nt = (a.P.len + C::TILE - 1) / C::TILE;
+    a.ntiles = (uint32_t)nt;
+    const size_t smem = sizeof(Cls2Smem<C>);
+    cudaError_t e = cudaFuncSetAttribute(k_classify2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_classify2<C><<<(unsigned)nt, C::WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_classify2(const ClassifyArgs &a, cudaStream_t st) { return launch_classify2_t<Scan2Big>(a, st); }
 
 template <class C>
 static cudaError_t launch_scan2_t(ScanArgs a, cudaStream_t st)

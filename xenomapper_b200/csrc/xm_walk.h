@@ -152,6 +152,7 @@ struct Scratch {
     uint64_t *p_start = nullptr;       /* chunked walks: byte offset of every yielded primary record */
     uint64_t p_start_cap = 0;
     Globals *g = nullptr;
+    uint32_t last_kernels = 0;       /* bit 0 k_scan2, bit 1 k_classify2, bit 2 k_scan, bit 3 k_classify ran in the last resident walk */
 };
 
 template <class BE>
@@ -256,10 +257,11 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
     if (P.len == 0 || S.len == 0) return res->status = XM_OK;       /* readline() == '' on the first call: nothing is yielded */
 
     bool small = (debug & DBG_SMALL_TILES) != 0;
+    sc.last_kernels = 0;
     uint64_t limit = ~0ull;
     uint64_t sc_need = 0;
     Globals G;
-    bool no_scan2 = false;
+    bool no_scan2 = false, no_cls2 = false;
     int code_first = 0;
     unsigned long long err_first = NO_ERROR;
     for (int attempt = 0; attempt < 6; ++attempt) {
@@ -307,7 +309,8 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
 
         be.tick(3);
         /* clean inputs take the barrier-free scan (xm_scan2.cuh); it says so when a span needs the exact kernel */
-        bool scanned = false;
+        bool scanned = false, have_gs = false;
+        Globals Gs;
         if (!small && !(debug & DBG_FORCE_GENERIC) && !no_scan2) {
             ScanArgs s2 = sa;
             s2.ntiles = (uint32_t)be.scan2_tiles(S.len);
@@ -317,7 +320,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
                 Globals G2;
                 if (be.read(&G2, sc.g, sizeof G2)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
                 res->n_launches += 1;
-                if (!G2.pad) scanned = true;
+                if (!G2.pad) { scanned = true; Gs = G2; have_gs = true; sc.last_kernels |= 1u; }
                 else {
                     no_scan2 = true;            /* and for the re-runs of this call */
                     if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_sc * 8)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
@@ -326,16 +329,40 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
             }
         }
         if (!scanned) {
+            sc.last_kernels |= 4u;
             if (be.scan(sa, small)) { errmsg = "scan kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
             res->n_launches += 1;
         }
         be.tick(1);
-        if (be.classify(ca, small)) { errmsg = "classify kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
-        be.tick(2);
-        if (be.sync()) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
-        res->n_launches += 1;
+        /* and the barrier-free classify (k_classify2) when nothing but clean, error-free input has been seen so far */
+        bool classified = false;
+        if (!small && !(debug & DBG_FORCE_GENERIC) && !no_cls2 && limit == ~0ull) {
+            if (!have_gs && be.read(&Gs, sc.g, sizeof Gs)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            const int r3 = be.classify2(ca);
+            if (r3 > 0) { errmsg = "classify kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            if (r3 == 0) {
+                be.tick(2);
+                if (be.read(&G, sc.g, sizeof G)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+                res->n_launches += 1;
+                if (!G.pad) { classified = true; sc.last_kernels |= 2u; }
+                else {
+                    /* back to the state the scan left, and the exact kernel */
+                    no_cls2 = true;
+                    Gs.pad = 0;
+                    if (be.write(sc.g, &Gs, sizeof Gs) || be.zero(sc.chain1_p, nt_p * 8) || be.zero(sc.chain2, nt_p * 8 * C2_SLOTS)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
+                    be.tick(1);
+                }
+            }
+        }
+        if (!classified) {
+            sc.last_kernels |= 8u;
+            if (be.classify(ca, small)) { errmsg = "classify kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            be.tick(2);
+            if (be.sync()) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            res->n_launches += 1;
+            if (be.read(&G, sc.g, sizeof G)) { errmsg = "result read failed"; return res->status = XM_ERR_CUDA; }
+        }
         res->ms_scan = be.elapsed(3, 1); res->ms_classify = be.elapsed(1, 2); res->ms_total += be.elapsed(0, 2);
-        if (be.read(&G, sc.g, sizeof G)) { errmsg = "result read failed"; return res->status = XM_ERR_CUDA; }
 
 #ifdef XM_PHASE_TIMING
         {
