@@ -27,7 +27,7 @@ struct Scan2Cfg {
     static constexpr int WARPS = WARPS_, SPAN = SPAN_, BACK = BACK_, EXT = EXT_;
     static constexpr int TILE = WARPS * SPAN;             /* bytes of the stream one CTA owns */
     static constexpr int WINB = BACK + SPAN + EXT;          /* bytes a warp may look at */
-    static constexpr int NWW = WINB / 32 + 1;               /* mask words per warp */
+    static constexpr int NWW = WINB / 32 + 2;               /* mask words per warp (an even count and one spare) */
     static constexpr int LQ = 160;                          /* line starts a warp can list */
     static_assert(SPAN % 1024 == 0 && BACK % 1024 == 0 && EXT % 1024 == 0 && WINB < 65535, "geometry");
 };
@@ -40,7 +40,11 @@ struct Scan2Cfg {
 #ifndef XM_SCAN2_OCC
 #define XM_SCAN2_OCC 4
 #endif
-using Scan2Big = Scan2Cfg<XM_SCAN2_WARPS, XM_SCAN2_SPAN, 1024, 2048>;
+#ifndef XM_SCAN2_SPAN_S
+#define XM_SCAN2_SPAN_S 11264
+#endif
+using Scan2Big = Scan2Cfg<XM_SCAN2_WARPS, XM_SCAN2_SPAN, 1024, 2048>;        /* k_classify2: ~28 primary lines of 440 bytes per span */
+using Scan2Sec = Scan2Cfg<XM_SCAN2_WARPS, XM_SCAN2_SPAN_S, 1024, 2048>;      /* k_scan2: ~30 secondary lines of 378 bytes (one parse batch) */
 
 /* what a warp knows about its span once the masks are built and the line starts are listed */
 struct SpanInfo {
@@ -81,62 +85,70 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
     bool adj = false;
     if (live) {
         if (win0 == 0) { if (lane == 0) starts[0] = 0; nst = 1; }      /* the stream's first byte opens a line */
-        const uint32_t w_first = skip ? 0u : (hoff >= 32u ? hoff / 32u - 1u : 0u);
+        /* two consecutive 32-byte words per lane and step (2 KiB per warp), so the scan, the shuffles and the loop
+         * control below are paid once per 64 bytes; the first word looked at is the one before the span (its last
+         * byte decides whether the span opens a line), or word 0 when the line before the span matters */
+        const uint32_t w_first = skip ? 0u : ((hoff >= 32u ? hoff / 32u - 1u : 0u) & ~1u);
         const uint32_t nwords = (wbytes + 31u) >> 5;
-        uint32_t carryW = 0;                          /* was the byte before this word a separator? (lane 0's view) */
+        uint32_t carryW = 0;                          /* was the byte before this lane's first word a separator? (lane 0's view) */
         bool done = false;
         const uint32_t lim16 = (wbytes + 15u) & ~15u;      /* the buffer is readable up to the next multiple of 16 */
         const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-        uint4 va = filler, vb = filler, na = filler, nb = filler;
-        if (w_first + (uint32_t)lane < nwords) {
-            const uint32_t off = (w_first + (uint32_t)lane) * 32u;
-            va = ld_src16(win + off, false);
-            if (off + 16u < lim16) vb = ld_src16(win + off + 16u, false);
-        }
-        for (uint32_t wb = w_first; wb < nwords && !done; wb += 32u) {
-            const uint32_t w = wb + (uint32_t)lane;
-            /* the next step's bytes are requested before this step's are looked at */
-            if (w + 32u < nwords) {
-                const uint32_t off = (w + 32u) * 32u;
-                na = ld_src16(win + off, false);
-                nb = off + 16u < lim16 ? ld_src16(win + off + 16u, false) : filler;
-            }
-            uint32_t W = 0, Tm = 0;
+        const uint32_t lastp = own_hi - 1u;
+        for (uint32_t wb = w_first; wb < nwords && !done; wb += 64u) {
+            const uint32_t w = wb + 2u * (uint32_t)lane;           /* this lane's words: w, w + 1 */
+            uint32_t W0 = 0, T0 = 0, W1 = 0, T1 = 0;
             if (w < nwords) {
                 const uint32_t off = w * 32u;
+                const uint4 v0 = ld_src16(win + off, false);
+                const uint4 v1 = off + 16u < lim16 ? ld_src16(win + off + 16u, false) : filler;
+                const uint4 v2 = off + 32u < lim16 ? ld_src16(win + off + 32u, false) : filler;
+                const uint4 v3 = off + 48u < lim16 ? ld_src16(win + off + 48u, false) : filler;
                 uint32_t Wa, Ta, Wb, Tb;
-                masks16(va, Wa, Ta);
-                masks16(vb, Wb, Tb);
-                W = Wa | (Wb << 16);
-                Tm = Ta | (Tb << 16);
-                const uint32_t valid = wbytes - off;
-                if (valid < 32u) { const uint32_t k = (1u << valid) - 1u; W &= k; Tm &= k; }
+                masks16(v0, Wa, Ta);
+                masks16(v1, Wb, Tb);
+                W0 = Wa | (Wb << 16); T0 = Ta | (Tb << 16);
+                masks16(v2, Wa, Ta);
+                masks16(v3, Wb, Tb);
+                W1 = Wa | (Wb << 16); T1 = Ta | (Tb << 16);
+                if (off + 64u > wbytes) {                      /* the window's last words: bytes past its end do not count */
+                    const uint32_t valid = wbytes - off;       /* 1..63 */
+                    const uint32_t k0 = valid >= 32u ? 0xffffffffu : (1u << valid) - 1u;
+                    const uint32_t k1 = valid > 32u ? (1u << (valid - 32u)) - 1u : 0u;
+                    W0 &= k0; T0 &= k0; W1 &= k1; T1 &= k1;
+                }
             }
-            const uint32_t N = W & ~Tm;
-            uint32_t prevW = __shfl_up_sync(0xffffffffu, W >> 31, 1);
+            const uint32_t N0 = W0 & ~T0, N1 = W1 & ~T1;
+            uint32_t prevW = __shfl_up_sync(0xffffffffu, W1 >> 31, 1);
             if (lane == 0) prevW = carryW;
-            carryW = __shfl_sync(0xffffffffu, W >> 31, 31);
-            if (W & ((W << 1) | prevW)) adj = true;
-            /* tabs and line ends before each lane's word: one packed warp scan */
-            const uint32_t x = (uint32_t)__popc(Tm) | ((uint32_t)__popc(N) << 16);
+            carryW = __shfl_sync(0xffffffffu, W1 >> 31, 31);
+            if ((W0 & ((W0 << 1) | prevW)) | (W1 & ((W1 << 1) | (W0 >> 31)))) adj = true;
+            /* tabs and line ends before each lane's words: one packed warp scan */
+            const uint32_t x0 = (uint32_t)__popc(T0) | ((uint32_t)__popc(N0) << 16);
+            const uint32_t x = x0 + ((uint32_t)__popc(T1) | ((uint32_t)__popc(N1) << 16));
             uint32_t inc = x;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
             const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
             const uint32_t exc = inc - x;
-            if (w < (uint32_t)C::NWW) { tbm[w] = Tm; nlm[w] = N; trk[w] = (uint16_t)(tab_run + (exc & 0xffffu)); }
+            if (w + 1u < (uint32_t)C::NWW) {
+                tbm[w] = T0; nlm[w] = N0; trk[w] = (uint16_t)(tab_run + (exc & 0xffffu));
+                tbm[w + 1] = T1; nlm[w + 1] = N1; trk[w + 1] = (uint16_t)(tab_run + ((exc + x0) & 0xffffu));
+            }
             uint32_t idx = nst + (exc >> 16);
-            for (uint32_t m = N; m; m &= m - 1) {
-                const uint32_t p = w * 32u + (uint32_t)__ffs((int)m);          /* the byte after the terminator */
-                if (idx < (uint32_t)C::LQ) starts[idx] = (uint16_t)p;
+            for (uint32_t m = N0; m; m &= m - 1) {
+                if (idx < (uint32_t)C::LQ) starts[idx] = (uint16_t)(w * 32u + (uint32_t)__ffs((int)m));     /* the byte after the terminator */
+                ++idx;
+            }
+            for (uint32_t m = N1; m; m &= m - 1) {
+                if (idx < (uint32_t)C::LQ) starts[idx] = (uint16_t)(w * 32u + 32u + (uint32_t)__ffs((int)m));
                 ++idx;
             }
             tab_run += tot & 0xffffu;
             nst += tot >> 16;
-            va = na; vb = nb;
             /* the last owned line is closed once a terminator at or beyond the span's last byte has been seen */
-            const uint32_t lastp = own_hi - 1u;
-            const bool closed = N && ((w * 32u + 31u - (uint32_t)__clz((int)N)) >= lastp);
+            const bool closed = (N1 && (w * 32u + 63u - (uint32_t)__clz((int)N1)) >= lastp) ||
+                                (N0 && (w * 32u + 31u - (uint32_t)__clz((int)N0)) >= lastp);
             done = __any_sync(0xffffffffu, closed);
         }
         adj = __any_sync(0xffffffffu, adj);
@@ -570,7 +582,7 @@ static cudaError_t launch_scan2_t(ScanArgs a, cudaStream_t st)
     k_scan2<C><<<(unsigned)nt, C::WARPS * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
-cudaError_t launch_scan2(const ScanArgs &a, cudaStream_t st) { return launch_scan2_t<Scan2Big>(a, st); }
-uint32_t scan2_tile_bytes() { return Scan2Big::TILE; }
+cudaError_t launch_scan2(const ScanArgs &a, cudaStream_t st) { return launch_scan2_t<Scan2Sec>(a, st); }
+uint32_t scan2_tile_bytes() { return Scan2Sec::TILE; }
 
 }  // namespace xm
