@@ -97,6 +97,7 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
         const uint32_t lastp = own_hi - 1u;
         for (uint32_t wb = w_first; wb < nwords && !done; wb += 64u) {
             const uint32_t w = wb + 2u * (uint32_t)lane;           /* this lane's words: w, w + 1 */
+            if (w + 64u < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(win + (size_t)(w + 64u) * 32u));      /* the next step's bytes */
             uint32_t W0 = 0, T0 = 0, W1 = 0, T1 = 0;
             if (w < nwords) {
                 const uint32_t off = w * 32u;
@@ -229,8 +230,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
         if (mine) {
             const int s = (int)starts[first + k], e = (int)starts[first + k + 1] - 1;
             FastCtx fc;
-            ok = fast_head(M_, s, e, L, fc);
-            if (ok && !(ctx && k == 0)) fast_tail(M_, s, e, a.score_src, fc, L);
+            ok = fast_head(M_, s, e, L, fc);                  /* the aux tokens come after the record count is out */
         }
         if (__any_sync(0xffffffffu, !ok)) { bad = true; continue; }
         /* run heads (xm.py:110-114): a line is yielded when its QNAME differs from the line before */
@@ -258,10 +258,26 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
     uint32_t wbase = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < C::WARPS; ++w) { const uint32_t c = s_cnt[w]; if (w < warp) wbase += c; total += c; }
-    if (warp == 0) {
-        if (lane == 0) dev_publish1(a.chain1, tile, total, false);
-        dev_resolve1(a.chain1, tile, total, false, s_base);
+    /* the tile's count goes out now; its base is looked up after the aux tokens are parsed, when the tiles before
+     * this one have long published theirs */
+    if (threadIdx.x == 0) dev_publish1(a.chain1, tile, total, false);
+    if (!bad) {
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) {
+            const uint32_t k = (uint32_t)(32 * b + lane);
+            if (k >= nparse || (ctx && k == 0)) continue;
+            const int s = (int)starts[first + k], e = (int)starts[first + k + 1] - 1;
+            FastCtx fc;
+            fc.r0 = tabs_before(M_, s);
+            fc.ntab = tabs_before(M_, e) - fc.r0;
+            LineRec X;
+            X.flags = 0; X.as = SCORE_ABSENT; X.xs = SCORE_ABSENT;
+            fast_tail(M_, s, e, a.score_src, fc, X);
+            Rrec[b].x = (uint32_t)X.as; Rrec[b].y = (uint32_t)X.xs;
+            Rmeta[b] |= (X.flags & 0x3fu) << META_LEN_BITS;
+        }
     }
+    if (warp == 0) dev_resolve1(a.chain1, tile, total, false, s_base);
     __syncthreads();
     const unsigned long long base = s_base[0] + wbase;
 
@@ -315,8 +331,8 @@ struct Cls2Smem {
     uint32_t cnt[C::WARPS];
     uint32_t wtot[C::WARPS][8];                 /* bytes per bin (6), raw bytes (slot 6) of each warp */
     unsigned long long tot[8], keep[8];
+    unsigned long long wbase[C::WARPS][6];       /* where each warp's bytes start in the six bins */
     unsigned long long base1[2];
-    uint32_t hist[36];
 };
 
 template <class C>
@@ -336,7 +352,6 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
     static_assert(C::NWW * 4 >= CLS2_LINES * 18, "the copy items overlay the tab mask");
     uint32_t *it_dst = tbm, *it_sl = tbm + CLS2_LINES, *is_dst = tbm + 2 * CLS2_LINES, *is_len = tbm + 3 * CLS2_LINES;
     uint8_t *it_bin = (uint8_t *)(tbm + 4 * CLS2_LINES), *is_nl = it_bin + CLS2_LINES;
-    if (threadIdx.x < 36) S.hist[threadIdx.x] = 0;
     const SpanInfo si = span_front<C>(a.P, span_lo, need_prev, tbm, nlm, trk, starts);
     bool bad = si.bad;
     const uint64_t win0 = si.win0;
@@ -362,9 +377,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
             if (mine) {
                 const int s = (int)starts[first + k], e = (int)starts[first + k + 1] - 1;
                 FastCtx fc;
-                ok = fast_head(M_, s, e, L, fc);
-                if (ok && (paired || !(ctx && k == 0))) fast_tail(M_, s, e, a.score_src, fc, L);
-                if (L.flags) ok = false;                      /* score errors are reported by the exact kernel */
+                ok = fast_head(M_, s, e, L, fc);              /* the aux tokens come after the record count is out */
             }
             if (__any_sync(0xffffffffu, !ok)) { bad = true; break; }
             uint32_t pq = __shfl_up_sync(0xffffffffu, L.qlen, 1), p1 = __shfl_up_sync(0xffffffffu, L.h1, 1),
@@ -395,17 +408,32 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
     uint32_t wbase = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < C::WARPS; ++w) { const uint32_t c = S.cnt[w]; if (w < warp) wbase += c; total += c; }
-    if (warp == 0) {
-        if (lane == 0) dev_publish1(a.chain1, tile, total, false);
-        dev_resolve1(a.chain1, tile, total, false, S.base1);
+    if (threadIdx.x == 0) dev_publish1(a.chain1, tile, total, false);
+    /* the aux tokens (scores), while the tiles before this one publish their counts */
+    for (uint32_t kb = 0; kb < nparse && !bad; kb += 32u) {
+        const uint32_t k = kb + (uint32_t)lane;
+        bool ok = true;
+        if (k < nparse && (paired || !(ctx && k == 0))) {
+            const int s = (int)starts[first + k], e = (int)starts[first + k + 1] - 1;
+            FastCtx fc;
+            fc.r0 = tabs_before(M_, s);
+            fc.ntab = tabs_before(M_, e) - fc.r0;
+            LineRec X;
+            X.flags = 0; X.as = SCORE_ABSENT; X.xs = SCORE_ABSENT;
+            fast_tail(M_, s, e, a.score_src, fc, X);
+            S.as[warp][k] = X.as; S.xs[warp][k] = X.xs;
+            if (X.flags) ok = false;                          /* score errors are reported by the exact kernel */
+        }
+        if (__any_sync(0xffffffffu, !ok)) { bad = true; if (lane == 0) a.g->pad = 1u; }
     }
+    if (warp == 0) dev_resolve1(a.chain1, tile, total, false, S.base1);
     __syncthreads();
     const unsigned long long base = S.base1[0] + wbase;        /* record index of this span's first yielded record */
     unsigned long long ncap = a.g->n_stream[1];
     if (a.limit < ncap) ncap = a.limit;
 
     /* ---- join, decide, size ------------------------------------------------------------------------ */
-    uint32_t wtot[7] = {0, 0, 0, 0, 0, 0, 0};
+    uint32_t wtot_l = 0;                     /* lane b < 7 carries the warp's running total of slot b (six bins, raw bytes) */
     {
         int pst_carry = 0;                       /* state, emitted lengths and validity of the line before lane 0's */
         uint32_t pout_carry = 0, pslen_carry = 0, pso_carry = 0;
@@ -462,7 +490,11 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
                 }
                 if (bin != NO_BIN && !((a.enabled >> bin) & 1u)) { plen = 0; sbytes = 0; }
             }
-            dev_hist_add(S.hist, key);
+            {
+                /* one global atomic per distinct category in the warp */
+                const unsigned peers = __match_any_sync(0xffffffffu, key);
+                if (key < 36u && lane == __ffs((int)peers) - 1) atomicAdd(&a.g->counts[key], (unsigned long long)__popc(peers));
+            }
             /* offsets inside the warp's part of each bin */
             const uint32_t bytes = plen + sbytes;
             uint32_t off = 0;
@@ -473,11 +505,13 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
                     uint32_t x = v;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-                    if (bin == b) off = wtot[b] + x - v;
-                    wtot[b] += __shfl_sync(0xffffffffu, x, 31);
+                    const uint32_t run = __shfl_sync(0xffffffffu, wtot_l, (int)b);
+                    if (bin == b) off = run + x - v;
+                    const uint32_t add = __shfl_sync(0xffffffffu, x, 31);
+                    if (lane == (int)b) wtot_l += add;
                 }
             }
-            wtot[6] += __reduce_add_sync(0xffffffffu, raw);
+            { const uint32_t add = __reduce_add_sync(0xffffffffu, raw); if (lane == 6) wtot_l += add; }
             /* copy items; neighbouring primary parts that continue each other in the input and in the bin are merged */
             const uint32_t pend_src = src + plen, pend_dst = off + plen;
             const uint32_t q_src = __shfl_up_sync(0xffffffffu, pend_src, 1), q_dst = __shfl_up_sync(0xffffffffu, pend_dst, 1),
@@ -496,17 +530,11 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
     }
     if (bad) {
         if (lane == 0) a.g->pad = 1u;
-#pragma unroll
-        for (int b = 0; b < 7; ++b) wtot[b] = 0;
+        wtot_l = 0;
     }
 
     /* ---- byte bases: chain 2 ------------------------------------------------------------------------- */
-    if (lane < 8) S.wtot[warp][lane] = 0;
-    __syncwarp();
-    if (lane == 0) {
-#pragma unroll
-        for (int b = 0; b < 7; ++b) S.wtot[warp][b] = wtot[b];
-    }
+    if (lane < 8) S.wtot[warp][lane] = lane < 7 ? wtot_l : 0u;
     __syncthreads();
     if (warp == 0) {
         if (lane < 8) {
@@ -522,20 +550,17 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
 
     /* ---- copy -------------------------------------------------------------------------------------------- */
     if (!bad) {
-        unsigned long long wb[6];
-#pragma unroll
-        for (int b = 0; b < 6; ++b) {
-            unsigned long long t = S.tot[b];
-            for (int w = 0; w < warp; ++w) t += S.wtot[w][b];
-            wb[b] = t;
+        if (lane < 6) {
+            unsigned long long t = S.tot[lane];
+            for (int w = 0; w < warp; ++w) t += S.wtot[w][lane];
+            S.wbase[warp][lane] = t;
         }
+        __syncwarp();
         for (uint32_t k = 0; k < nparse; ++k) {
             const uint32_t sl = it_sl[k], slen = is_len[k];
             if (!sl && !slen) continue;
             const uint32_t bin = it_bin[k];
-            unsigned long long bb = 0;
-#pragma unroll
-            for (int b = 0; b < 6; ++b) if ((int)bin == b) bb = wb[b];
+            const unsigned long long bb = S.wbase[warp][bin < 6u ? bin : 0u];
             if (sl) {
                 const uint32_t len = sl >> 16;
                 const unsigned long long doff = bb + it_dst[k];
@@ -549,8 +574,6 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
             }
         }
     }
-    __syncthreads();
-    if (threadIdx.x < 36 && S.hist[threadIdx.x]) atomicAdd(&a.g->counts[threadIdx.x], (unsigned long long)S.hist[threadIdx.x]);
     if (threadIdx.x == 0) {
         if (S.keep[6]) atomicAdd(&a.g->bytes_in[0], S.keep[6]);
         if (tile + 1 == a.ntiles) {
