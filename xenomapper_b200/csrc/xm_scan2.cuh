@@ -211,6 +211,15 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
     const uint32_t first = ctx ? j0 - 1u : j0;
     const uint32_t nparse = nown + (ctx ? 1u : 0u);
     uint32_t count = 0;                               /* records this span yields */
+    uint32_t wbase = 0, total = 0;
+    if (!skip) {
+        /* every owned line is a record: the tile's count goes out before a single line is parsed */
+        if (lane == 0) s_cnt[warp] = nown;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < C::WARPS; ++w) { const uint32_t c = s_cnt[w]; if (w < warp) wbase += c; total += c; }
+        if (threadIdx.x == 0) dev_publish1(a.chain1, tile, total, false);
+    }
     /* results are kept for two batches (64 lines, i.e. lines of 160 bytes or more); shorter lines take the exact kernel */
     constexpr int MAXB = 2;
     uint4 Rrec[MAXB];
@@ -253,14 +262,15 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
     if (bad) { count = 0; if (lane == 0) a.g->pad = 1u; }      /* Globals::pad doubles as the fallback flag */
 
     /* ---- the tile's record base: look-back chain 1 over CTAs ------------------------------------------ */
-    if (lane == 0) s_cnt[warp] = count;
-    __syncthreads();
-    uint32_t wbase = 0, total = 0;
+    if (skip) {
+        if (lane == 0) s_cnt[warp] = count;
+        __syncthreads();
 #pragma unroll
-    for (int w = 0; w < C::WARPS; ++w) { const uint32_t c = s_cnt[w]; if (w < warp) wbase += c; total += c; }
-    /* the tile's count goes out now; its base is looked up after the aux tokens are parsed, when the tiles before
-     * this one have long published theirs */
-    if (threadIdx.x == 0) dev_publish1(a.chain1, tile, total, false);
+        for (int w = 0; w < C::WARPS; ++w) { const uint32_t c = s_cnt[w]; if (w < warp) wbase += c; total += c; }
+        /* the tile's count goes out now; its base is looked up after the aux tokens are parsed, when the tiles
+         * before this one have long published theirs */
+        if (threadIdx.x == 0) dev_publish1(a.chain1, tile, total, false);
+    }
     if (!bad) {
 #pragma unroll
         for (int b = 0; b < MAXB; ++b) {
@@ -366,6 +376,15 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
     const uint32_t nparse = nown + (ctx ? 1u : 0u);
     if (nparse > (uint32_t)CLS2_LINES) bad = true;
     uint32_t count = 0;
+    uint32_t wbase = 0, total = 0;
+    if (!skip) {
+        /* every owned line is a record: the tile's count goes out before a single line is parsed */
+        if (lane == 0) S.cnt[warp] = nown;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < C::WARPS; ++w) { const uint32_t c = S.cnt[w]; if (w < warp) wbase += c; total += c; }
+        if (threadIdx.x == 0) dev_publish1(a.chain1, tile, total, false);
+    }
     {
         uint32_t prev_qlen = 0, prev_h1 = 0, prev_h2 = 0, prev_qs = 0;
         for (uint32_t kb = 0; kb < nparse && !bad; kb += 32u) {
@@ -403,12 +422,13 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
     if (bad) { count = 0; if (lane == 0) a.g->pad = 1u; }
 
     /* ---- record base: chain 1 ------------------------------------------------------------------- */
-    if (lane == 0) S.cnt[warp] = count;
-    __syncthreads();
-    uint32_t wbase = 0, total = 0;
+    if (skip) {
+        if (lane == 0) S.cnt[warp] = count;
+        __syncthreads();
 #pragma unroll
-    for (int w = 0; w < C::WARPS; ++w) { const uint32_t c = S.cnt[w]; if (w < warp) wbase += c; total += c; }
-    if (threadIdx.x == 0) dev_publish1(a.chain1, tile, total, false);
+        for (int w = 0; w < C::WARPS; ++w) { const uint32_t c = S.cnt[w]; if (w < warp) wbase += c; total += c; }
+        if (threadIdx.x == 0) dev_publish1(a.chain1, tile, total, false);
+    }
     /* the aux tokens (scores), while the tiles before this one publish their counts */
     for (uint32_t kb = 0; kb < nparse && !bad; kb += 32u) {
         const uint32_t k = kb + (uint32_t)lane;
