@@ -374,6 +374,33 @@ __device__ void dev_copy_piece(uint8_t *dst, const uint8_t *win, uint32_t src_of
  * source vectors with funnel shifts (the shift is the same for the whole piece).  The source was read by this
  * kernel a few hundred tiles ago and normally still sits in L2; it is readable up to the next multiple of 16.
  */
+/* the aligned body of a copy whose source sits WSH words and bsh bits past a 16-byte boundary: four rows of 32
+ * chunks per trip, all eight loads of a lane requested before the first is used */
+template <int WSH>
+__device__ __forceinline__ void copy_body(uint8_t *body, const uint8_t *sa, uint32_t nchunk, uint32_t bsh, uint32_t lane)
+{
+    auto shift = [bsh](const uint4 &q0, const uint4 &q1) {
+        uint4 o;
+        if (WSH == 0) { o.x = __funnelshift_r(q0.x, q0.y, bsh); o.y = __funnelshift_r(q0.y, q0.z, bsh); o.z = __funnelshift_r(q0.z, q0.w, bsh); o.w = __funnelshift_r(q0.w, q1.x, bsh); }
+        else if (WSH == 1) { o.x = __funnelshift_r(q0.y, q0.z, bsh); o.y = __funnelshift_r(q0.z, q0.w, bsh); o.z = __funnelshift_r(q0.w, q1.x, bsh); o.w = __funnelshift_r(q1.x, q1.y, bsh); }
+        else if (WSH == 2) { o.x = __funnelshift_r(q0.z, q0.w, bsh); o.y = __funnelshift_r(q0.w, q1.x, bsh); o.z = __funnelshift_r(q1.x, q1.y, bsh); o.w = __funnelshift_r(q1.y, q1.z, bsh); }
+        else { o.x = __funnelshift_r(q0.w, q1.x, bsh); o.y = __funnelshift_r(q1.x, q1.y, bsh); o.z = __funnelshift_r(q1.y, q1.z, bsh); o.w = __funnelshift_r(q1.z, q1.w, bsh); }
+        return o;
+    };
+    uint32_t c = lane;
+    for (; c + 96u < nchunk; c += 128u) {
+        uint4 a0[4], a1[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { a0[r] = ld_src16(sa + 16u * (c + 32u * r), false); a1[r] = ld_src16(sa + 16u * (c + 32u * r) + 16u, false); }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) __stcs((uint4 *)(body + 16u * (c + 32u * r)), shift(a0[r], a1[r]));
+    }
+    for (; c < nchunk; c += 32u) {
+        const uint4 q0 = ld_src16(sa + 16u * c, false), q1 = ld_src16(sa + 16u * c + 16u, false);
+        __stcs((uint4 *)(body + 16u * c), shift(q0, q1));
+    }
+}
+
 __device__ void dev_copy_global(uint8_t *dst, const uint8_t *src, uint32_t len)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -393,21 +420,13 @@ __device__ void dev_copy_global(uint8_t *dst, const uint8_t *src, uint32_t len)
             __stcs((uint4 *)(body + 16u * c), ld_src16(sa + 16u * c, false));
         return;
     }
-#pragma unroll 2
-    for (uint32_t c = lane; c < nchunk; c += 32u) {
-        const uint4 q0 = ld_src16(sa + 16u * c, false);
-        const uint4 q1 = ld_src16(sa + 16u * c + 16u, false);
-        uint4 o;
-        switch (u >> 2) {
-        case 0: o.x = __funnelshift_r(q0.x, q0.y, bsh); o.y = __funnelshift_r(q0.y, q0.z, bsh); o.z = __funnelshift_r(q0.z, q0.w, bsh); o.w = __funnelshift_r(q0.w, q1.x, bsh); break;
-        case 1: o.x = __funnelshift_r(q0.y, q0.z, bsh); o.y = __funnelshift_r(q0.z, q0.w, bsh); o.z = __funnelshift_r(q0.w, q1.x, bsh); o.w = __funnelshift_r(q1.x, q1.y, bsh); break;
-        case 2: o.x = __funnelshift_r(q0.z, q0.w, bsh); o.y = __funnelshift_r(q0.w, q1.x, bsh); o.z = __funnelshift_r(q1.x, q1.y, bsh); o.w = __funnelshift_r(q1.y, q1.z, bsh); break;
-        default: o.x = __funnelshift_r(q0.w, q1.x, bsh); o.y = __funnelshift_r(q1.x, q1.y, bsh); o.z = __funnelshift_r(q1.y, q1.z, bsh); o.w = __funnelshift_r(q1.z, q1.w, bsh); break;
-        }
-        __stcs((uint4 *)(body + 16u * c), o);
+    switch (u >> 2) {
+    case 0: copy_body<0>(body, sa, nchunk, bsh, lane); break;
+    case 1: copy_body<1>(body, sa, nchunk, bsh, lane); break;
+    case 2: copy_body<2>(body, sa, nchunk, bsh, lane); break;
+    default: copy_body<3>(body, sa, nchunk, bsh, lane); break;
     }
 }
-
 }  // namespace xm
 #include "xm_scan2.cuh"
 namespace xm {
