@@ -532,14 +532,20 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
                 }
             }
             { const uint32_t add = __reduce_add_sync(0xffffffffu, raw); if (lane == 6) wtot_l += add; }
-            /* copy items; neighbouring primary parts that continue each other in the input and in the bin are merged */
+            /* copy items; primary parts that continue each other in the input and in the bin are merged into runs.
+             * Lanes without a primary part (first mates of a pair, secondary-only bins) do not break a run. */
             const uint32_t pend_src = src + plen, pend_dst = off + plen;
-            const uint32_t q_src = __shfl_up_sync(0xffffffffu, pend_src, 1), q_dst = __shfl_up_sync(0xffffffffu, pend_dst, 1),
-                           q_bin = __shfl_up_sync(0xffffffffu, bin, 1), q_len = __shfl_up_sync(0xffffffffu, plen, 1);
-            const bool head = plen && !(lane > 0 && q_len && q_bin == bin && q_src == src && q_dst == off);
-            const uint32_t heads = __ballot_sync(0xffffffffu, head || !plen);          /* lanes that end the run before them */
+            const uint32_t items = __ballot_sync(0xffffffffu, plen != 0u);
+            const uint32_t below = items & ((1u << lane) - 1u);
+            const int pl = below ? 31 - __clz((int)below) : 0;                          /* the item before this lane's */
+            const uint32_t q_src = __shfl_sync(0xffffffffu, pend_src, pl), q_dst = __shfl_sync(0xffffffffu, pend_dst, pl),
+                           q_bin = __shfl_sync(0xffffffffu, bin, pl);
+            const bool head = plen && !(below && q_bin == bin && q_src == src && q_dst == off);
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
             const uint32_t above = heads & (lane == 31 ? 0u : (0xffffffffu << (lane + 1)));
-            const int last = above ? __ffs((int)above) - 2 : 31;                        /* last lane of this lane's run */
+            const uint32_t upto = above ? ((1u << (__ffs((int)above) - 1)) - 1u) : 0xffffffffu;   /* lanes before the next run */
+            const uint32_t mineq = items & upto;
+            const int last = mineq ? 31 - __clz((int)mineq) : lane;                     /* last item of this lane's run */
             const uint32_t run_end = __shfl_sync(0xffffffffu, pend_src, last);
             if (mine) {
                 it_dst[k] = off; it_bin[k] = (uint8_t)bin;
