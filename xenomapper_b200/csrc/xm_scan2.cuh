@@ -43,7 +43,10 @@ struct Scan2Cfg {
 #ifndef XM_SCAN2_SPAN_S
 #define XM_SCAN2_SPAN_S 11264
 #endif
-using Scan2Big = Scan2Cfg<XM_SCAN2_WARPS, XM_SCAN2_SPAN, 1024, 2048>;        /* k_classify2: ~28 primary lines of 440 bytes per span */
+#ifndef XM_CLS2_WARPS
+#define XM_CLS2_WARPS XM_SCAN2_WARPS
+#endif
+using Scan2Big = Scan2Cfg<XM_CLS2_WARPS, XM_SCAN2_SPAN, 1024, 2048>;        /* k_classify2: ~28 primary lines of 440 bytes per span */
 using Scan2Sec = Scan2Cfg<XM_SCAN2_WARPS, XM_SCAN2_SPAN_S, 1024, 2048>;      /* k_scan2: ~30 secondary lines of 378 bytes (one parse batch) */
 
 /* what a warp knows about its span once the masks are built and the line starts are listed */
