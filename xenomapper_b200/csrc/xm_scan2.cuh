@@ -43,8 +43,10 @@ struct Scan2Cfg {
 #ifndef XM_SCAN2_SPAN_S
 #define XM_SCAN2_SPAN_S 11264
 #endif
+/* k_classify2 needs 68 registers: seven warps per CTA let four CTAs (28 warps) share a SM's register file; told to
+ * fit 64 the compiler produces markedly slower code (profiles/r01_geometry_sweep.md) */
 #ifndef XM_CLS2_WARPS
-#define XM_CLS2_WARPS XM_SCAN2_WARPS
+#define XM_CLS2_WARPS 7
 #endif
 using Scan2Big = Scan2Cfg<XM_CLS2_WARPS, XM_SCAN2_SPAN, 1024, 2048>;        /* k_classify2: ~28 primary lines of 440 bytes per span */
 using Scan2Sec = Scan2Cfg<XM_SCAN2_WARPS, XM_SCAN2_SPAN_S, 1024, 2048>;      /* k_scan2: ~30 secondary lines of 378 bytes (one parse batch) */
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
  * only; everything else raises the fallback flag and k_classify runs.
  * ========================================================================= */
 #ifndef XM_CLS2_OCC
-#define XM_CLS2_OCC 3
+#define XM_CLS2_OCC 4
 #endif
 constexpr int CLS2_LINES = 64;            /* lines (with the context line) a span may hold: two batches */
 
