@@ -18,6 +18,7 @@
  */
 #pragma once
 #include "xm_common.h"
+#include <string.h>
 
 namespace xm {
 
@@ -111,6 +112,31 @@ XM_HD void masks16(const uint4 v, uint32_t &W, uint32_t &T)
 XM_HD uint32_t newlines16(const uint4 v)
 {
     return pack16(eq_mask(v.x, 0x0a0a0a0au), eq_mask(v.y, 0x0a0a0a0au), eq_mask(v.z, 0x0a0a0a0au), eq_mask(v.w, 0x0a0a0a0au));
+}
+
+/* The per-line parse reads a line's bytes straight from global memory, every lane of a warp at an address of
+ * its own: such a load occupies the SM's L1 pipeline once per 128-byte line it touches whatever its width, and
+ * that pipeline, not HBM, bounds the barrier-free kernels (profiles/r02_l1_wavefronts.md).  XM_PARSE16 makes the
+ * parse fetch aligned 16-byte blocks and take its words and bytes from registers. */
+#ifndef XM_PARSE16
+#define XM_PARSE16 1
+#endif
+/* aligned 16-byte block; every buffer the parse looks at is readable up to the next multiple of 16 */
+XM_HD uint4 ld16(const uint8_t *p)
+{
+#if XM_DEVICE_PASS
+    return *(const uint4 *)p;
+#else
+    uint4 v;
+    memcpy(&v, p, 16);
+    return v;
+#endif
+}
+/* byte b (0..15) of a block */
+XM_HD uint32_t byte_of16(const uint4 &v, int b)
+{
+    const uint32_t w = b < 8 ? (b < 4 ? v.x : v.y) : (b < 12 ? v.z : v.w);
+    return (w >> (8 * (b & 3))) & 0xffu;
 }
 
 XM_HD bool is_w_byte(uint32_t c) { return c < 0x21u || c >= 0x80u; }
@@ -356,6 +382,36 @@ XM_HD int token_end(const WinMasks &M, int q)
 /* plain integer after the last ':' of the token [ts, te) */
 XM_HD bool token_value(const uint8_t *win, int ts, int te, int32_t &out)
 {
+#if XM_PARSE16
+    /* the usual shape, ':' [+-] one to nine digits at the token's end, read backwards from the block that holds the
+     * token's last byte (and the block before it when the value straddles); anything else takes the loop below */
+    if (te > ts) {
+        int p = te - 1, b = p & 15;
+        const uint8_t *blk = win + (p & ~15);
+        uint4 v = ld16(blk);
+        uint32_t val = 0, mul = 1, nd = 0, c = 0;
+        bool fast = true;
+        for (;;) {
+            c = byte_of16(v, b);
+            const uint32_t d = c - '0';
+            if (d > 9u) break;
+            if (nd == 9u || p == ts) { fast = false; break; }
+            val += d * mul; mul *= 10u; ++nd;
+            --p;
+            if (--b < 0) { blk -= 16; v = ld16(blk); b = 15; }
+        }
+        if (fast && nd) {
+            bool neg = false;
+            if ((c == '-' || c == '+') && p > ts) {
+                neg = c == '-';
+                --p;
+                if (--b < 0) { blk -= 16; v = ld16(blk); b = 15; }
+                c = byte_of16(v, b);
+            }
+            if (c == ':') { out = neg ? -(int32_t)val : (int32_t)val; return true; }
+        }
+    }
+#endif
     int vs = te;
     while (vs > ts && win[vs - 1] != ':') --vs;
     NumSt n; num_reset(n);
@@ -414,6 +470,29 @@ XM_HD bool fast_head(const WinMasks &M, int s, int e, LineRec &L, FastCtx &fc)
         const int base = s >> 2;
         const uint32_t sh = (uint32_t)(s & 3) * 8u;
         const int nw = (qlen + 3) >> 2;
+#if XM_PARSE16
+        /* the words base .. base + nw, fetched a block at a time: word j of the name's words closes hash step j - 1 */
+        const uint32_t lastmask = (qlen & 3) ? (1u << (8 * (qlen & 3))) - 1u : 0xffffffffu;
+        uint32_t lo = 0;
+        int j = ((base >> 2) << 2) - base;              /* index of the block's first word, relative to base */
+        auto step = [&](uint32_t wd) {
+            const int k = j - 1;
+            if (k >= 0 && k < nw) {
+                uint32_t w = funnel_r(lo, wd, sh);
+                if (k == nw - 1) w &= lastmask;
+                hash_word(h, w);
+            }
+            lo = wd; ++j;
+        };
+#if defined(XM_WHATIF) && XM_WHATIF == 4
+        if (false)
+#endif
+        for (int qb = base >> 2; qb <= (base + nw) >> 2; ++qb) {
+            const uint4 v = ld16(win + (qb << 4));
+            step(v.x); step(v.y); step(v.z); step(v.w);
+        }
+        (void)w32;
+#else
         uint32_t lo = w32[base];
         for (int k = 0; k < nw; ++k) {
             const uint32_t hi = w32[base + k + 1];
@@ -422,6 +501,7 @@ XM_HD bool fast_head(const WinMasks &M, int s, int e, LineRec &L, FastCtx &fc)
             if (k == nw - 1 && (qlen & 3)) w &= (1u << (8 * (qlen & 3))) - 1u;
             hash_word(h, w);
         }
+#endif
     }
     hash_final(h, (uint32_t)qlen);
     L.s = (uint32_t)s; L.rawbytes = outlen; L.outlen = outlen;
@@ -433,6 +513,9 @@ XM_HD bool fast_head(const WinMasks &M, int s, int e, LineRec &L, FastCtx &fc)
 XM_HD void fast_tail(const WinMasks &M, int s, int e, int score_src, const FastCtx &fc, LineRec &L)
 {
     if (fc.ntab < 11) return;           /* no token with index >= 11: both scores absent (xm.py:186-188) */
+#if defined(XM_WHATIF) && XM_WHATIF == 3
+    return;
+#endif
     const uint8_t *win = M.win;
     const uint32_t *w32 = (const uint32_t *)win;
     const int w0 = s >> 5, w1 = e >> 5;
@@ -444,6 +527,26 @@ XM_HD void fast_tail(const WinMasks &M, int s, int e, int score_src, const FastC
     const int a = tab_select(M, fc.r0 + 10, w0, w1) + 1;
     int as_ts = -1, xs_ts = -1, nm_ts = -1;
     uint32_t as_cnt = 0, xs_cnt = 0;
+#if XM_PARSE16
+    const int k0 = a >> 4, k1 = (e - 1) >> 4;
+    uint32_t prev_last = 0;                                   /* the byte before the block */
+    (void)w32;
+    for (int k = k0; k <= k1; ++k) {
+        const uint4 v = ld16(win + (k << 4));
+        uint32_t z0 = eq_mask(v.x, 0x53535353u), z1 = eq_mask(v.y, 0x53535353u), z2 = eq_mask(v.z, 0x53535353u), z3 = eq_mask(v.w, 0x53535353u);   /* 'S' */
+        if (cigar) { z0 |= eq_mask(v.x, 0x4d4d4d4du); z1 |= eq_mask(v.y, 0x4d4d4d4du); z2 |= eq_mask(v.z, 0x4d4d4d4du); z3 |= eq_mask(v.w, 0x4d4d4d4du); }   /* 'M' */
+        uint32_t z = pack16(z0, z1, z2, z3);                  /* one bit per byte */
+        if (k == k0) z &= 0xffffu << (a & 15);
+        if (k == k1) z &= 0xffffu >> (15 - ((e - 1) & 15));
+        const uint32_t carry = prev_last;
+        prev_last = v.w >> 24;
+        while (z) {
+            const int b = ffs32(z) - 1;
+            const int p = (k << 4) + b;
+            z &= z - 1;
+            if (p <= a) continue;
+            const uint32_t c1 = byte_of16(v, b), c0 = b ? byte_of16(v, b - 1) : carry;
+#else
     const int k0 = a >> 2, k1 = (e - 1) >> 2;
     for (int k = k0; k <= k1; ++k) {
         const uint32_t w = w32[k];
@@ -456,6 +559,7 @@ XM_HD void fast_tail(const WinMasks &M, int s, int e, int score_src, const FastC
             z &= z - 1;
             if (p <= a) continue;
             const uint32_t c1 = win[p], c0 = win[p - 1];
+#endif
             if (c1 == 'S') {
                 if (c0 == 'A' && !cigar) {
                     const int ts = token_start(M, p - 1);
