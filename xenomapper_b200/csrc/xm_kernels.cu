@@ -296,34 +296,9 @@ __device__ __forceinline__ uint4 ld_src16(const uint8_t *p, bool smem)
     return v;
 }
 
-/* L2 residency hints (XM_L2_HINTS): k_classify2 reads every primary line twice, in the mask pass and, tens of
- * microseconds and ~80 MB of L2 traffic later, in the copy.  The first read asks L2 to keep the line (evict_last),
- * the second marks it as done with (evict_first), like the streaming stores of the bins. */
-#ifndef XM_L2_HINTS
-#define XM_L2_HINTS 0
-#endif
 #ifndef XM_WHATIF
 #define XM_WHATIF 0      /* timing experiments that break the output: 1 copy without source loads, 2 no copy, 3 no aux parse, 4 no QNAME hash */
 #endif
-__device__ __forceinline__ uint64_t l2_policy_keep()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t l2_policy_done()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint4 ld_src16_pol(const uint8_t *p, uint64_t pol)
-{
-    uint4 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-    return v;
-}
-
 __device__ void dev_warp_copy(uint8_t *dst, const uint8_t *src_smem, const uint8_t *src_glob, uint32_t len)
 {
     const int lane = threadIdx.x & 31;
@@ -412,17 +387,11 @@ __device__ __forceinline__ void xm_st_fake(uint4 *p, uint4 v) { if ((v.x ^ v.y ^
 #else
 #define XM_ST(p, v) __stcs(p, v)
 #endif
-#ifndef XM_COPY_TAILBATCH
-#define XM_COPY_TAILBATCH 1
-#endif
 template <int WSH>
 __device__ __forceinline__ void copy_body(uint8_t *body, const uint8_t *sa, uint32_t nchunk, uint32_t bsh, uint32_t lane)
 {
 #if XM_WHATIF == 1 || XM_WHATIF == 8
     auto ld = [](const uint8_t *q) { return make_uint4((uint32_t)(uintptr_t)q, 1u, 2u, 3u); };
-#elif XM_L2_HINTS
-    const uint64_t pol = l2_policy_done();
-    auto ld = [pol](const uint8_t *q) { return ld_src16_pol(q, pol); };
 #else
     auto ld = [](const uint8_t *q) { return ld_src16(q, false); };
 #endif
@@ -435,7 +404,6 @@ __device__ __forceinline__ void copy_body(uint8_t *body, const uint8_t *sa, uint
         return o;
     };
     uint32_t c = lane;
-#if XM_COPY_TAILBATCH
     /* four rows per trip, the last trip with fewer: every load of a trip is requested before the first is used */
     for (; c < nchunk; c += 128u) {
         uint4 a0[4], a1[4];
@@ -448,19 +416,6 @@ __device__ __forceinline__ void copy_body(uint8_t *body, const uint8_t *sa, uint
         for (int r = 0; r < 4; ++r)
             if (c + 32u * r < nchunk) XM_ST((uint4 *)(body + 16u * (c + 32u * r)), shift(a0[r], a1[r]));
     }
-#else
-    for (; c + 96u < nchunk; c += 128u) {
-        uint4 a0[4], a1[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) { a0[r] = ld(sa + 16u * (c + 32u * r)); a1[r] = ld(sa + 16u * (c + 32u * r) + 16u); }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) XM_ST((uint4 *)(body + 16u * (c + 32u * r)), shift(a0[r], a1[r]));
-    }
-    for (; c < nchunk; c += 32u) {
-        const uint4 q0 = ld(sa + 16u * c), q1 = ld(sa + 16u * c + 16u);
-        XM_ST((uint4 *)(body + 16u * c), shift(q0, q1));
-    }
-#endif
 }
 
 __device__ void dev_copy_global(uint8_t *dst, const uint8_t *src, uint32_t len)

@@ -116,11 +116,8 @@ XM_HD uint32_t newlines16(const uint4 v)
 
 /* The per-line parse reads a line's bytes straight from global memory, every lane of a warp at an address of
  * its own: such a load occupies the SM's L1 pipeline once per 128-byte line it touches whatever its width, and
- * that pipeline, not HBM, bounds the barrier-free kernels (profiles/r02_l1_wavefronts.md).  XM_PARSE16 makes the
- * parse fetch aligned 16-byte blocks and take its words and bytes from registers. */
-#ifndef XM_PARSE16
-#define XM_PARSE16 1
-#endif
+ * that pipeline is busier than HBM in the barrier-free kernels (profiles/r01_parse16_and_whatifs.md).  So the parse
+ * fetches aligned 16-byte blocks and takes its words and bytes from registers. */
 /* aligned 16-byte block; every buffer the parse looks at is readable up to the next multiple of 16 */
 XM_HD uint4 ld16(const uint8_t *p)
 {
@@ -382,7 +379,6 @@ XM_HD int token_end(const WinMasks &M, int q)
 /* plain integer after the last ':' of the token [ts, te) */
 XM_HD bool token_value(const uint8_t *win, int ts, int te, int32_t &out)
 {
-#if XM_PARSE16
     /* the usual shape, ':' [+-] one to nine digits at the token's end, read backwards from the block that holds the
      * token's last byte (and the block before it when the value straddles); anything else takes the loop below */
     if (te > ts) {
@@ -411,7 +407,6 @@ XM_HD bool token_value(const uint8_t *win, int ts, int te, int32_t &out)
             if (c == ':') { out = neg ? -(int32_t)val : (int32_t)val; return true; }
         }
     }
-#endif
     int vs = te;
     while (vs > ts && win[vs - 1] != ':') --vs;
     NumSt n; num_reset(n);
@@ -439,7 +434,6 @@ struct FastCtx {
 XM_HD bool fast_head(const WinMasks &M, int s, int e, LineRec &L, FastCtx &fc)
 {
     const uint8_t *win = M.win;
-    const uint32_t *w32 = (const uint32_t *)win;
     if ((uint32_t)e >= M.wbytes || e <= s || win[e] != '\n') return false;
     if (s == 0 && (M.wsm(0) & 1u)) return false;            /* the stream opens with a separator */
     const int w0 = s >> 5, w1 = e >> 5;
@@ -470,7 +464,6 @@ XM_HD bool fast_head(const WinMasks &M, int s, int e, LineRec &L, FastCtx &fc)
         const int base = s >> 2;
         const uint32_t sh = (uint32_t)(s & 3) * 8u;
         const int nw = (qlen + 3) >> 2;
-#if XM_PARSE16
         /* the words base .. base + nw, fetched a block at a time: word j of the name's words closes hash step j - 1 */
         const uint32_t lastmask = (qlen & 3) ? (1u << (8 * (qlen & 3))) - 1u : 0xffffffffu;
         uint32_t lo = 0;
@@ -491,17 +484,6 @@ XM_HD bool fast_head(const WinMasks &M, int s, int e, LineRec &L, FastCtx &fc)
             const uint4 v = ld16(win + (qb << 4));
             step(v.x); step(v.y); step(v.z); step(v.w);
         }
-        (void)w32;
-#else
-        uint32_t lo = w32[base];
-        for (int k = 0; k < nw; ++k) {
-            const uint32_t hi = w32[base + k + 1];
-            uint32_t w = funnel_r(lo, hi, sh);
-            lo = hi;
-            if (k == nw - 1 && (qlen & 3)) w &= (1u << (8 * (qlen & 3))) - 1u;
-            hash_word(h, w);
-        }
-#endif
     }
     hash_final(h, (uint32_t)qlen);
     L.s = (uint32_t)s; L.rawbytes = outlen; L.outlen = outlen;
@@ -517,9 +499,8 @@ XM_HD void fast_tail(const WinMasks &M, int s, int e, int score_src, const FastC
     return;
 #endif
     const uint8_t *win = M.win;
-    const uint32_t *w32 = (const uint32_t *)win;
     const int w0 = s >> 5, w1 = e >> 5;
-    /* aux tokens (index >= 11): look for the tag letters a word at a time */
+    /* aux tokens (index >= 11): look for the tag letters a 16-byte block at a time */
     uint32_t flags = 0;
     int32_t as = SCORE_ABSENT, xs = SCORE_ABSENT;
     const bool cigar = score_src == SCORE_CIGAR_NM;
@@ -527,10 +508,8 @@ XM_HD void fast_tail(const WinMasks &M, int s, int e, int score_src, const FastC
     const int a = tab_select(M, fc.r0 + 10, w0, w1) + 1;
     int as_ts = -1, xs_ts = -1, nm_ts = -1;
     uint32_t as_cnt = 0, xs_cnt = 0;
-#if XM_PARSE16
     const int k0 = a >> 4, k1 = (e - 1) >> 4;
     uint32_t prev_last = 0;                                   /* the byte before the block */
-    (void)w32;
     for (int k = k0; k <= k1; ++k) {
         const uint4 v = ld16(win + (k << 4));
         uint32_t z0 = eq_mask(v.x, 0x53535353u), z1 = eq_mask(v.y, 0x53535353u), z2 = eq_mask(v.z, 0x53535353u), z3 = eq_mask(v.w, 0x53535353u);   /* 'S' */
@@ -546,20 +525,6 @@ XM_HD void fast_tail(const WinMasks &M, int s, int e, int score_src, const FastC
             z &= z - 1;
             if (p <= a) continue;
             const uint32_t c1 = byte_of16(v, b), c0 = b ? byte_of16(v, b - 1) : carry;
-#else
-    const int k0 = a >> 2, k1 = (e - 1) >> 2;
-    for (int k = k0; k <= k1; ++k) {
-        const uint32_t w = w32[k];
-        uint32_t z = eq_mask(w, 0x53535353u);                 /* 'S' */
-        if (cigar) z |= eq_mask(w, 0x4d4d4d4du);              /* 'M' */
-        if (k == k0) z &= 0xffffffffu << (8 * (a & 3));
-        if (k == k1) z &= 0xffffffffu >> (8 * (3 - ((e - 1) & 3)));
-        while (z) {
-            const int p = (k << 2) + ((ffs32(z) - 1) >> 3);
-            z &= z - 1;
-            if (p <= a) continue;
-            const uint32_t c1 = win[p], c0 = win[p - 1];
-#endif
             if (c1 == 'S') {
                 if (c0 == 'A' && !cigar) {
                     const int ts = token_start(M, p - 1);

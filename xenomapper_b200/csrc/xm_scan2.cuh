@@ -29,7 +29,7 @@ struct Scan2Cfg {
     static constexpr int WINB = BACK + SPAN + EXT;          /* bytes a warp may look at */
     static constexpr int NWW = WINB / 32 + 2;               /* mask words per warp (an even count and one spare) */
     static constexpr int LQ = 160;                          /* line starts a warp can list */
-    static_assert(SPAN % 1024 == 0 && BACK % 1024 == 0 && EXT % 1024 == 0 && WINB < 65535 && NWW % 2 == 0, "geometry");
+    static_assert(SPAN % 1024 == 0 && BACK % 1024 == 0 && EXT % 1024 == 0 && WINB < 65535, "geometry");
 };
 #ifndef XM_SCAN2_WARPS
 #define XM_SCAN2_WARPS 8
@@ -51,26 +51,6 @@ struct Scan2Cfg {
 using Scan2Big = Scan2Cfg<XM_CLS2_WARPS, XM_SCAN2_SPAN, 1024, 2048>;        /* k_classify2: ~28 primary lines of 440 bytes per span */
 using Scan2Sec = Scan2Cfg<XM_SCAN2_WARPS, XM_SCAN2_SPAN_S, 1024, 2048>;      /* k_scan2: ~30 secondary lines of 378 bytes (one parse batch) */
 
-/* bytes of its copy source a warp of k_classify2 requests into L1 ahead of the copy engine (0: none): the lines were
- * read by the mask pass tens of microseconds earlier and sit in L2 (one in eight has been evicted to HBM); without the
- * request every trip of the copy loop and every copy item starts with a full round trip to L2 / HBM */
-#ifndef XM_CLS2_PF
-#define XM_CLS2_PF 0
-#endif
-/* 1: the mask pass loads rows of 512 consecutive bytes per warp and instruction */
-#ifndef XM_MASK_ROWS
-#define XM_MASK_ROWS 0
-#endif
-/* 1: a warp requests its whole window into L2 before the mask pass walks it */
-#ifndef XM_SPAN_PF
-#define XM_SPAN_PF 0
-#endif
-/* requests the 128-byte lines of win[from, to) into L1, one line per lane and trip; from is a multiple of 128 */
-__device__ __forceinline__ void prefetch_l1_range(const uint8_t *win, uint32_t from, uint32_t to, int lane)
-{
-    for (uint32_t o = from + 128u * (uint32_t)lane; o < to; o += 4096u) asm volatile("prefetch.global.L1 [%0];" ::"l"(win + o));
-}
-
 /* what a warp knows about its span once the masks are built and the line starts are listed */
 struct SpanInfo {
     uint64_t win0, wend;       /* the window [win0, wend) in the stream */
@@ -81,7 +61,7 @@ struct SpanInfo {
 
 /* masks (tbm, nlm, trk: this warp's private shared memory), line starts and the owned range of one span.
  * need_prev: the line before the first owned one will be looked at (run heads, pair units). */
-template <class C, bool KEEP = false>
+template <class C>
 __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span_lo, bool need_prev, uint32_t *tbm, uint32_t *nlm, uint16_t *trk, uint16_t *starts)
 {
     const int lane = threadIdx.x & 31;
@@ -103,9 +83,6 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
     bool bad = false;
     const uint32_t own_hi = hoff + C::SPAN < wbytes ? hoff + (uint32_t)C::SPAN : wbytes;     /* owned starts lie in [hoff, own_hi) */
     const uint8_t *win = B.p + win0;          /* read through L1/L2: no staged copy, so a SM holds 32 of these warps */
-#if XM_SPAN_PF
-    for (uint32_t o = 128u * (uint32_t)lane; o < wbytes; o += 4096u) asm volatile("prefetch.global.L2 [%0];" ::"l"(win + o));
-#endif
 
     /* ---- masks and line starts ------------------------------------------------------------------ */
     uint32_t nst = 0;                                 /* line starts listed so far (uniform) */
@@ -122,51 +99,17 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
         bool done = false;
         const uint32_t lim16 = (wbytes + 15u) & ~15u;      /* the buffer is readable up to the next multiple of 16 */
         const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-        /* KEEP: the lines will be read again by the copy (see XM_L2_HINTS in xm_kernels.cu) */
-        const uint64_t pol = (KEEP && XM_L2_HINTS) ? l2_policy_keep() : 0ull;
-        auto ldw = [pol](const uint8_t *q) { return (KEEP && XM_L2_HINTS) ? ld_src16_pol(q, pol) : ld_src16(q, false); };
         const uint32_t lastp = own_hi - 1u;
         for (uint32_t wb = w_first; wb < nwords && !done; wb += 64u) {
             const uint32_t w = wb + 2u * (uint32_t)lane;           /* this lane's words: w, w + 1 */
             if (w + 64u < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(win + (size_t)(w + 64u) * 32u));      /* the next step's bytes */
             uint32_t W0 = 0, T0 = 0, W1 = 0, T1 = 0;
-#if XM_MASK_ROWS
-            /* four rows of 32 consecutive 16-byte chunks: every load of the warp covers 512 consecutive bytes (four
-             * 128-byte lines in the L1 pipeline, where 64 consecutive bytes per lane would touch sixteen).  The half
-             * words go through the warp's mask arrays and come back as two whole words per lane. */
-            {
-                uint16_t *tb16 = reinterpret_cast<uint16_t *>(tbm), *nl16 = reinterpret_cast<uint16_t *>(nlm);
-                uint4 v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t off = (wb * 2u + 32u * (uint32_t)j + (uint32_t)lane) * 16u;
-                    v[j] = off < wbytes ? ldw(win + off) : filler;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t c = wb * 2u + 32u * (uint32_t)j + (uint32_t)lane, off = c * 16u;
-                    uint32_t Wa, Ta;
-                    masks16(v[j], Wa, Ta);
-                    if (off + 16u > wbytes) {                  /* the window's last chunk: bytes past its end do not count */
-                        const uint32_t k = off < wbytes ? (1u << (wbytes - off)) - 1u : 0u;
-                        Wa &= k; Ta &= k;
-                    }
-                    if (c < 2u * (uint32_t)C::NWW) { tb16[c] = (uint16_t)Ta; nl16[c] = (uint16_t)Wa; }
-                }
-                __syncwarp();
-                if (w < nwords) {
-                    const uint2 t2 = *reinterpret_cast<const uint2 *>(tbm + w), w2 = *reinterpret_cast<const uint2 *>(nlm + w);
-                    T0 = t2.x; T1 = t2.y; W0 = w2.x; W1 = w2.y;
-                }
-            }
-            (void)lim16;
-#else
             if (w < nwords) {
                 const uint32_t off = w * 32u;
-                const uint4 v0 = ldw(win + off);
-                const uint4 v1 = off + 16u < lim16 ? ldw(win + off + 16u) : filler;
-                const uint4 v2 = off + 32u < lim16 ? ldw(win + off + 32u) : filler;
-                const uint4 v3 = off + 48u < lim16 ? ldw(win + off + 48u) : filler;
+                const uint4 v0 = ld_src16(win + off, false);
+                const uint4 v1 = off + 16u < lim16 ? ld_src16(win + off + 16u, false) : filler;
+                const uint4 v2 = off + 32u < lim16 ? ld_src16(win + off + 32u, false) : filler;
+                const uint4 v3 = off + 48u < lim16 ? ld_src16(win + off + 48u, false) : filler;
                 uint32_t Wa, Ta, Wb, Tb;
                 masks16(v0, Wa, Ta);
                 masks16(v1, Wb, Tb);
@@ -181,7 +124,6 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
                     W0 &= k0; T0 &= k0; W1 &= k1; T1 &= k1;
                 }
             }
-#endif
             const uint32_t N0 = W0 & ~T0, N1 = W1 & ~T1;
             uint32_t prevW = __shfl_up_sync(0xffffffffu, W1 >> 31, 1);
             if (lane == 0) prevW = carryW;
@@ -196,14 +138,8 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
             const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
             const uint32_t exc = inc - x;
             if (w + 1u < (uint32_t)C::NWW) {
-#if XM_MASK_ROWS
-                *reinterpret_cast<uint2 *>(nlm + w) = make_uint2(N0, N1);         /* the tab words are in place already */
-#else
-                tbm[w] = T0; nlm[w] = N0;
-                tbm[w + 1] = T1; nlm[w + 1] = N1;
-#endif
-                trk[w] = (uint16_t)(tab_run + (exc & 0xffffu));
-                trk[w + 1] = (uint16_t)(tab_run + ((exc + x0) & 0xffffu));
+                tbm[w] = T0; nlm[w] = N0; trk[w] = (uint16_t)(tab_run + (exc & 0xffffu));
+                tbm[w + 1] = T1; nlm[w + 1] = N1; trk[w + 1] = (uint16_t)(tab_run + ((exc + x0) & 0xffffu));
             }
             uint32_t idx = nst + (exc >> 16);
             for (uint32_t m = N0; m; m &= m - 1) {
@@ -255,7 +191,7 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
 template <class C>
 __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const ScanArgs a)
 {
-    __shared__ __align__(16) uint32_t s_tbm[C::WARPS][C::NWW], s_nlm[C::WARPS][C::NWW];
+    __shared__ uint32_t s_tbm[C::WARPS][C::NWW], s_nlm[C::WARPS][C::NWW];
     __shared__ uint16_t s_trk[C::WARPS][C::NWW];
     __shared__ uint16_t s_start[C::WARPS][C::LQ];
     __shared__ uint32_t s_cnt[C::WARPS];
@@ -431,7 +367,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
     static_assert(C::NWW * 4 >= CLS2_LINES * 18, "the copy items overlay the tab mask");
     uint32_t *it_dst = tbm, *it_sl = tbm + CLS2_LINES, *is_dst = tbm + 2 * CLS2_LINES, *is_len = tbm + 3 * CLS2_LINES;
     uint8_t *it_bin = (uint8_t *)(tbm + 4 * CLS2_LINES), *is_nl = it_bin + CLS2_LINES;
-    const SpanInfo si = span_front<C, true>(a.P, span_lo, need_prev, tbm, nlm, trk, starts);
+    const SpanInfo si = span_front<C>(a.P, span_lo, need_prev, tbm, nlm, trk, starts);
     bool bad = si.bad;
     const uint64_t win0 = si.win0;
     const uint32_t wbytes = si.wbytes, j0 = si.j0, nown = si.nown;
@@ -628,17 +564,6 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
         wtot_l = 0;
     }
 
-    /* the first bytes the copy engine will read, requested while the warp waits for its byte bases */
-    uint32_t pf_pos = 0, pf_hi = 0;
-    if (XM_CLS2_PF && !bad && nparse) {
-        const uint32_t lo = (uint32_t)starts[first];
-        pf_hi = (uint32_t)starts[first + nparse];
-        if (pf_hi > wbytes) pf_hi = wbytes;
-        const uint32_t t = lo + (uint32_t)XM_CLS2_PF < pf_hi ? lo + (uint32_t)XM_CLS2_PF : pf_hi;
-        prefetch_l1_range(win, lo & ~127u, t, lane);
-        pf_pos = (t + 127u) & ~127u;
-    }
-
     /* ---- byte bases: chain 2 ------------------------------------------------------------------------- */
     if (lane < 8) S.wtot[warp][lane] = lane < 7 ? wtot_l : 0u;
     __syncthreads();
@@ -670,12 +595,6 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
             if (sl) {
                 const uint32_t len = sl >> 16;
                 const unsigned long long doff = bb + it_dst[k];
-                if (XM_CLS2_PF) {
-                    /* the rest of this run and the head of the next one, while the first trips of this copy run */
-                    uint32_t t = (sl & 0xffffu) + len + (uint32_t)XM_CLS2_PF;
-                    if (t > pf_hi) t = pf_hi;
-                    if (t > pf_pos) { prefetch_l1_range(win, pf_pos, t, lane); pf_pos = (t + 127u) & ~127u; }
-                }
                 if (doff + len <= a.out_cap[bin]) dev_copy_global(a.out[bin] + doff, win + (sl & 0xffffu), len);
             }
             if (slen) {
