@@ -1,8 +1,8 @@
 # end-of-milestone GPU visit: parity tests, smoke, full-size bench, reference arm, ncu launch list + full capture (2 M records)
-# TAG names the outputs (default r01_final3)
+# TAG names the outputs (default r01_final4)
 set -x
-TAG=${TAG:-r01_final3}
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+TAG=${TAG:-r01_final4}
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -c 600 gpurun_out/bench_full.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err

@@ -108,6 +108,19 @@ XM_HD void masks16(const uint4 v, uint32_t &W, uint32_t &T)
     W = pack16(ctrl_mask(v.x), ctrl_mask(v.y), ctrl_mask(v.z), ctrl_mask(v.w));
     T = pack16(eq_mask(v.x, 0x09090909u), eq_mask(v.y, 0x09090909u), eq_mask(v.z, 0x09090909u), eq_mask(v.w, 0x09090909u));
 }
+/* The same for the barrier-free kernels, whose spans give up (exact kernel) when two W bytes touch: the tab test
+ * is the three-operation zero-byte test on v ^ '\t'.  Its only false positive is a backspace (0x08) in the byte
+ * after a tab inside the same word -- two touching W bytes, so that span never uses the mask. */
+XM_HD uint32_t tab_mask_loose(uint32_t w)
+{
+    const uint32_t x = w ^ 0x09090909u;
+    return (x - 0x01010101u) & ~x & 0x80808080u;
+}
+XM_HD void masks16_span(const uint4 v, uint32_t &W, uint32_t &T)
+{
+    W = pack16(ctrl_mask(v.x), ctrl_mask(v.y), ctrl_mask(v.z), ctrl_mask(v.w));
+    T = pack16(tab_mask_loose(v.x), tab_mask_loose(v.y), tab_mask_loose(v.z), tab_mask_loose(v.w));
+}
 /* exact newline mask of 16 staged bytes (tiles whose W & ~T bytes are not all '\n') */
 XM_HD uint32_t newlines16(const uint4 v)
 {

@@ -19,6 +19,7 @@
  * SCompact rows, n_stream / end_off.
  */
 #pragma once
+#include <type_traits>
 
 namespace xm {
 
@@ -61,7 +62,7 @@ struct SpanInfo {
 
 /* masks (tbm, nlm, trk: this warp's private shared memory), line starts and the owned range of one span.
  * need_prev: the line before the first owned one will be looked at (run heads, pair units). */
-template <class C>
+template <class C, bool SPLIT>
 __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span_lo, bool need_prev, uint32_t *tbm, uint32_t *nlm, uint16_t *trk, uint16_t *starts)
 {
     const int lane = threadIdx.x & 31;
@@ -100,24 +101,28 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
         const uint32_t lim16 = (wbytes + 15u) & ~15u;      /* the buffer is readable up to the next multiple of 16 */
         const uint4 filler = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
         const uint32_t lastp = own_hi - 1u;
-        for (uint32_t wb = w_first; wb < nwords && !done; wb += 64u) {
+        /* one step: 64 mask words, two per lane.  INTERIOR steps lie wholly inside the window and before the span's
+         * last byte: no bounds selects, no partial words, and the last owned line cannot close there.  SPLIT compiles
+         * the step twice; it pays in k_scan2 (+4 %) and costs in k_classify2 (-1.6 %, a larger kernel already). */
+        auto step = [&](auto interior_c, const uint32_t wb) {
+            constexpr bool INTERIOR = decltype(interior_c)::value;
             const uint32_t w = wb + 2u * (uint32_t)lane;           /* this lane's words: w, w + 1 */
             if (w + 64u < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(win + (size_t)(w + 64u) * 32u));      /* the next step's bytes */
             uint32_t W0 = 0, T0 = 0, W1 = 0, T1 = 0;
-            if (w < nwords) {
+            if (INTERIOR || w < nwords) {
                 const uint32_t off = w * 32u;
                 const uint4 v0 = ld_src16(win + off, false);
-                const uint4 v1 = off + 16u < lim16 ? ld_src16(win + off + 16u, false) : filler;
-                const uint4 v2 = off + 32u < lim16 ? ld_src16(win + off + 32u, false) : filler;
-                const uint4 v3 = off + 48u < lim16 ? ld_src16(win + off + 48u, false) : filler;
+                const uint4 v1 = (INTERIOR || off + 16u < lim16) ? ld_src16(win + off + 16u, false) : filler;
+                const uint4 v2 = (INTERIOR || off + 32u < lim16) ? ld_src16(win + off + 32u, false) : filler;
+                const uint4 v3 = (INTERIOR || off + 48u < lim16) ? ld_src16(win + off + 48u, false) : filler;
                 uint32_t Wa, Ta, Wb, Tb;
-                masks16(v0, Wa, Ta);
-                masks16(v1, Wb, Tb);
+                masks16_span(v0, Wa, Ta);
+                masks16_span(v1, Wb, Tb);
                 W0 = Wa | (Wb << 16); T0 = Ta | (Tb << 16);
-                masks16(v2, Wa, Ta);
-                masks16(v3, Wb, Tb);
+                masks16_span(v2, Wa, Ta);
+                masks16_span(v3, Wb, Tb);
                 W1 = Wa | (Wb << 16); T1 = Ta | (Tb << 16);
-                if (off + 64u > wbytes) {                      /* the window's last words: bytes past its end do not count */
+                if (!INTERIOR && off + 64u > wbytes) {         /* the window's last words: bytes past its end do not count */
                     const uint32_t valid = wbytes - off;       /* 1..63 */
                     const uint32_t k0 = valid >= 32u ? 0xffffffffu : (1u << valid) - 1u;
                     const uint32_t k1 = valid > 32u ? (1u << (valid - 32u)) - 1u : 0u;
@@ -137,7 +142,7 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
             for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
             const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
             const uint32_t exc = inc - x;
-            if (w + 1u < (uint32_t)C::NWW) {
+            if (INTERIOR || w + 1u < (uint32_t)C::NWW) {
                 tbm[w] = T0; nlm[w] = N0; trk[w] = (uint16_t)(tab_run + (exc & 0xffffu));
                 tbm[w + 1] = T1; nlm[w + 1] = N1; trk[w + 1] = (uint16_t)(tab_run + ((exc + x0) & 0xffffu));
             }
@@ -152,10 +157,17 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
             }
             tab_run += tot & 0xffffu;
             nst += tot >> 16;
-            /* the last owned line is closed once a terminator at or beyond the span's last byte has been seen */
-            const bool closed = (N1 && (w * 32u + 63u - (uint32_t)__clz((int)N1)) >= lastp) ||
-                                (N0 && (w * 32u + 31u - (uint32_t)__clz((int)N0)) >= lastp);
-            done = __any_sync(0xffffffffu, closed);
+            if (!INTERIOR) {
+                /* the last owned line is closed once a terminator at or beyond the span's last byte has been seen */
+                const bool closed = (N1 && (w * 32u + 63u - (uint32_t)__clz((int)N1)) >= lastp) ||
+                                    (N0 && (w * 32u + 31u - (uint32_t)__clz((int)N0)) >= lastp);
+                done = __any_sync(0xffffffffu, closed);
+            }
+        };
+        for (uint32_t wb = w_first; wb < nwords && !done; wb += 64u) {
+            const uint32_t step_end = (wb + 64u) * 32u;            /* the byte after this step's last */
+            if (SPLIT && step_end <= wbytes && step_end <= lastp) step(std::true_type{}, wb);
+            else step(std::false_type{}, wb);
         }
         adj = __any_sync(0xffffffffu, adj);
         if (nst > (uint32_t)C::LQ || adj) bad = true;
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
     const bool skip = a.skip != 0;
     uint32_t *tbm = s_tbm[warp], *nlm = s_nlm[warp];
     uint16_t *trk = s_trk[warp], *starts = s_start[warp];
-    const SpanInfo si = span_front<C>(a.S, span_lo, skip, tbm, nlm, trk, starts);
+    const SpanInfo si = span_front<C, true>(a.S, span_lo, skip, tbm, nlm, trk, starts);
     bool bad = si.bad;                                /* this span needs the exact kernel */
     const uint64_t win0 = si.win0;
     const uint32_t wbytes = si.wbytes, j0 = si.j0, nown = si.nown;
@@ -367,7 +379,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
     static_assert(C::NWW * 4 >= CLS2_LINES * 18, "the copy items overlay the tab mask");
     uint32_t *it_dst = tbm, *it_sl = tbm + CLS2_LINES, *is_dst = tbm + 2 * CLS2_LINES, *is_len = tbm + 3 * CLS2_LINES;
     uint8_t *it_bin = (uint8_t *)(tbm + 4 * CLS2_LINES), *is_nl = it_bin + CLS2_LINES;
-    const SpanInfo si = span_front<C>(a.P, span_lo, need_prev, tbm, nlm, trk, starts);
+    const SpanInfo si = span_front<C, false>(a.P, span_lo, need_prev, tbm, nlm, trk, starts);
     bool bad = si.bad;
     const uint64_t win0 = si.win0;
     const uint32_t wbytes = si.wbytes, j0 = si.j0, nown = si.nown;
