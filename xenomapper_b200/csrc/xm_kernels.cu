@@ -296,6 +296,9 @@ __device__ __forceinline__ uint4 ld_src16(const uint8_t *p, bool smem)
     return v;
 }
 
+#ifndef XM_COPY_ROWS
+#define XM_COPY_ROWS 4      /* 512-byte rows a lane keeps in flight per trip of the copy */
+#endif
 #ifndef XM_WHATIF
 #define XM_WHATIF 0      /* timing experiments that break the output: 1 copy without source loads, 2 no copy, 3 no aux parse, 4 no QNAME hash */
 #endif
@@ -404,16 +407,16 @@ __device__ __forceinline__ void copy_body(uint8_t *body, const uint8_t *sa, uint
         return o;
     };
     uint32_t c = lane;
-    /* four rows per trip, the last trip with fewer: every load of a trip is requested before the first is used */
-    for (; c < nchunk; c += 128u) {
-        uint4 a0[4], a1[4];
+    /* XM_COPY_ROWS rows per trip, the last trip with fewer: every load of a trip is requested before the first is used */
+    for (; c < nchunk; c += 32u * XM_COPY_ROWS) {
+        uint4 a0[XM_COPY_ROWS], a1[XM_COPY_ROWS];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < XM_COPY_ROWS; ++r) {
             const uint32_t cr = c + 32u * r < nchunk ? c + 32u * r : c;       /* rows past the end re-read this lane's first chunk */
             a0[r] = ld(sa + 16u * cr); a1[r] = ld(sa + 16u * cr + 16u);
         }
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < XM_COPY_ROWS; ++r)
             if (c + 32u * r < nchunk) XM_ST((uint4 *)(body + 16u * (c + 32u * r)), shift(a0[r], a1[r]));
     }
 }

@@ -107,7 +107,9 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
         auto step = [&](auto interior_c, const uint32_t wb) {
             constexpr bool INTERIOR = decltype(interior_c)::value;
             const uint32_t w = wb + 2u * (uint32_t)lane;           /* this lane's words: w, w + 1 */
+#ifndef XM_NO_MASK_PF
             if (w + 64u < nwords) asm volatile("prefetch.global.L1 [%0];" ::"l"(win + (size_t)(w + 64u) * 32u));      /* the next step's bytes */
+#endif
             uint32_t W0 = 0, T0 = 0, W1 = 0, T1 = 0;
             if (INTERIOR || w < nwords) {
                 const uint32_t off = w * 32u;
