@@ -147,6 +147,14 @@ def test_cuda_kernel_selection_and_fallback(ctx):
     ref = oracle.classify(pd, s, skip_repeated=True)
     assert rc == 0 and "k_classify" in ctx.walk_kernels()
     assert outs == ref["outputs"] and list(res.counts) == ref["counts"]
+    # a backspace right after a tab: the one byte pair the span kernels' three-operation tab mask misreads
+    # (xm_parse.h tab_mask_loose); two touching W bytes, so the span declines and the exact kernel runs
+    for prim, sec, kern in ((bytes(p).replace(b"\tXM:i:", b"\t\x08XM:i:", 1), s, "k_classify"),
+                            (p, bytes(s).replace(b"\tXM:i:", b"\t\x08XM:i:", 1), "k_scan")):
+        rc, res, outs = ctx.classify_host(prim, sec, o)
+        ref = oracle.classify(prim, sec, skip_repeated=True)
+        assert rc == 0 and kern in ctx.walk_kernels()
+        assert outs == ref["outputs"] and list(res.counts) == ref["counts"]
     # an input error (two AS tags): reported by the exact kernels, outputs up to the failing record
     pe = bytes(p)
     cut = pe.index(b"\n", len(pe) // 2) + 1
