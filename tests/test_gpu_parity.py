@@ -68,6 +68,24 @@ def test_cuda_fixed_width_lines_match_oracle(ctx, width, mode, skip):
     assert outs == ref["outputs"]
 
 
+@pytest.mark.parametrize("width", [600, 632, 648, 700, 900, 1000])
+@pytest.mark.parametrize("mode,skip", [(0, False), (0, True), (1, False)])
+def test_cuda_span_kernels_find_the_line_before_the_span(ctx, width, mode, skip):
+    """walks that look at the line before a span scan 640 bytes before it first and the whole 1 KiB only when that
+    line starts earlier (xm_scan2.cuh span_front): lines just below and above that length, on the barrier-free pair"""
+    from oracle import oracle
+    from tests.test_emu_tiles import _fixed_width_pair
+    from xenomapper_b200 import _lib
+    ctx.set_debug(0)
+    p, s = _fixed_width_pair(4000, width)
+    ref = oracle.classify(p, s, mode=mode, skip_repeated=skip)
+    rc, res, outs = ctx.classify_host(p, s, _lib.Context.opts(mode, 0, skip))
+    assert rc == 0, ctx.error()
+    assert ctx.walk_kernels() == ["k_scan2", "k_classify2"]
+    assert list(res.counts) == ref["counts"]
+    assert outs == ref["outputs"]
+
+
 @pytest.mark.parametrize("style,mode,skip", [(0, 0, True), (1, 1, False), (2, 2, False)])
 def test_cuda_large_synthetic_matches_oracle(ctx, style, mode, skip):
     """300 k records (about 130 MB per stream: thousands of tiles, look-back across several waves of CTAs)"""

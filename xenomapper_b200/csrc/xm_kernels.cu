@@ -435,8 +435,15 @@ __device__ void dev_copy_global(uint8_t *dst, const uint8_t *src, uint32_t len)
     const uint8_t *sa = so - u;
     uint8_t *body = dst + head;
 #if XM_WHATIF != 7 && XM_WHATIF != 8
-    if (lane < head) dst[lane] = src[lane];
-    if (lane < tail) body[16u * nchunk + lane] = so[16u * nchunk + lane];
+    {
+        /* the unaligned head bytes by lanes 0-15, the tail bytes by lanes 16-31: one load and one store instruction */
+        const uint32_t i = lane & 15u;
+        const bool is_tail = lane >= 16u;
+        if (i < (is_tail ? tail : head)) {
+            const size_t o = is_tail ? (size_t)head + 16u * (size_t)nchunk + i : (size_t)i;
+            dst[o] = src[o];
+        }
+    }
 #endif
     const uint32_t bsh = (u & 3u) * 8u;
     if (u == 0) {

@@ -88,13 +88,21 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
     /* ---- masks and line starts ------------------------------------------------------------------ */
     uint32_t nst = 0;                                 /* line starts listed so far (uniform) */
     uint32_t tab_run = 0;
+    uint32_t j0 = 0, j1 = 0;
+    /* the first word looked at: the one before the span (its last byte decides whether the span opens a line); when
+     * the line before the span matters, SHORT_BACK bytes before it -- and the whole window in a second attempt if
+     * that line turns out to start earlier (word 0 straight away at the head of the stream) */
+    constexpr uint32_t SHORT_BACK = 640;
+    uint32_t w_first = skip ? ((win0 != 0 && hoff > SHORT_BACK) ? ((hoff - SHORT_BACK) >> 5) & ~1u : 0u)
+                            : ((hoff >= 32u ? hoff / 32u - 1u : 0u) & ~1u);
+#pragma unroll 1
+    for (;;) {
+    nst = 0; tab_run = 0; j0 = 0; j1 = 0; bad = false;
     bool adj = false;
     if (live) {
         if (win0 == 0) { if (lane == 0) starts[0] = 0; nst = 1; }      /* the stream's first byte opens a line */
         /* two consecutive 32-byte words per lane and step (2 KiB per warp), so the scan, the shuffles and the loop
-         * control below are paid once per 64 bytes; the first word looked at is the one before the span (its last
-         * byte decides whether the span opens a line), or word 0 when the line before the span matters */
-        const uint32_t w_first = skip ? 0u : ((hoff >= 32u ? hoff / 32u - 1u : 0u) & ~1u);
+         * control below are paid once per 64 bytes */
         const uint32_t nwords = (wbytes + 31u) >> 5;
         uint32_t carryW = 0;                          /* was the byte before this lane's first word a separator? (lane 0's view) */
         bool done = false;
@@ -177,7 +185,6 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
     __syncwarp();
 
     /* ---- the lines this span owns: starts in [hoff, own_hi) -------------------------------------------- */
-    uint32_t j0 = 0, j1 = 0;
     if (live && !bad) {
         for (uint32_t k = (uint32_t)lane; k < ((nst + 31u) & ~31u); k += 32u) {
             const uint32_t s = k < nst ? (uint32_t)starts[k] : 0xffffffffu;
@@ -193,7 +200,12 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
             const uint32_t last = nst ? (uint32_t)starts[nst - 1] : 0xffffffffu;
             if (last != wbytes && own_hi == wbytes) bad = true;       /* unterminated last line */
         }
-        if (skip && j1 > j0 && j0 == 0 && win0 + starts[0] != 0) bad = true;      /* the line before the span is not in the window */
+        if (skip && j1 > j0 && j0 == 0 && win0 + starts[0] != 0) {
+            if (w_first > 0 && !bad) { w_first = 0; __syncwarp(); continue; }     /* look at the whole window */
+            bad = true;                                                           /* the line before the span is not in the window */
+        }
+    }
+    break;
     }
     si.bad = bad;
     si.j0 = j0;
@@ -473,6 +485,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
 
     /* ---- join, decide, size ------------------------------------------------------------------------ */
     uint32_t wtot_l = 0;                     /* lane b < 7 carries the warp's running total of slot b (six bins, raw bytes) */
+    uint32_t todo0 = 0, todo1 = 0;           /* per batch of 32 lines: which lines start a copy */
     {
         int pst_carry = 0;                       /* state, emitted lengths and validity of the line before lane 0's */
         uint32_t pout_carry = 0, pslen_carry = 0, pso_carry = 0;
@@ -571,6 +584,9 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
                 it_sl[k] = head ? (src | ((run_end - src) << 16)) : 0u;
                 is_dst[k] = off + plen; is_len[k] = sbytes; is_nl[k] = (uint8_t)nl;
             }
+            /* the lines that start a copy (a run of primary parts, or a secondary part): the copy loop visits only these */
+            const uint32_t t = __ballot_sync(0xffffffffu, mine && (head || sbytes != 0u));
+            if (kb == 0) todo0 = t; else todo1 = t;
         }
     }
     if (bad) {
@@ -601,9 +617,13 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
             S.wbase[warp][lane] = t;
         }
         __syncwarp();
-        for (uint32_t k = 0; k < nparse; ++k) {
+        static_assert(CLS2_LINES == 64, "two batches of copy starts");
+#pragma unroll 1
+        for (uint32_t m = todo0, kb = 0; kb < 64u; m = todo1, kb += 32u)
+#pragma unroll 1
+        for (; m; m &= m - 1) {
+            const uint32_t k = kb + (uint32_t)__ffs((int)m) - 1u;
             const uint32_t sl = it_sl[k], slen = is_len[k];
-            if (!sl && !slen) continue;
             const uint32_t bin = it_bin[k];
             const unsigned long long bb = S.wbase[warp][bin < 6u ? bin : 0u];
             if (sl) {
