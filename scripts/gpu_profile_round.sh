@@ -1,7 +1,7 @@
 # end-of-milestone GPU visit: parity tests, smoke, full-size bench, reference arm, ncu launch list + full capture (2 M records)
-# TAG names the outputs (default r01_final4)
+# TAG names the outputs (default r01_final5)
 set -x
-TAG=${TAG:-r01_final4}
+TAG=${TAG:-r01_final5}
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -c 600 gpurun_out/bench_full.err
