@@ -95,3 +95,47 @@ def test_tiles_with_exactly_half_the_threads_in_lines(width, skip):
     assert r["status"] == 0, r["message"]
     assert r["counts"] == ref["counts"]
     assert r["outputs"] == ref["outputs"]
+
+
+def _pair_with_widths(widths, first=0):
+    """one record per entry of `widths` in both streams (primary `w` bytes, secondary `w - 8`)"""
+    P, S = [], []
+    for k, w in enumerate(widths):
+        p, s = _fixed_width_pair(1, w, first=first + k)
+        P.append(p); S.append(s)
+    return b"".join(P), b"".join(S)
+
+
+def test_more_secondary_records_than_the_sampled_estimate():
+    """The compact per-record arrays are sized from the mean line length of the stream's first 256 KiB.  Long lines
+    up front and many short lines behind them yield more records than that estimate plus its margin: the classify
+    kernels must not look past the arrays (out-of-bounds read at classify_tile) and the host must grow
+    them and walk again."""
+    from oracle import oracle
+    p, s = _pair_with_widths([1000] * 400 + [90] * 30000)
+    ref = oracle.classify(p, s)
+    r = _emu.classify(p, s)
+    assert r["status"] == 0, r["message"]
+    assert r["n_records"] == 30400
+    assert r["counts"] == ref["counts"]
+    assert r["outputs"] == ref["outputs"]
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("where", ["middle", "chunk_boundary"])
+def test_chunked_walk_refuses_a_line_longer_than_the_chunk(where):
+    """A line that fits no staging step must end the walk with XM_ERR_UNSUPPORTED after the records before it,
+    not spin (from step 1 on the carried halo record hid the 'longer than the buffer' test)."""
+    from oracle import oracle
+    chunk = 256
+    head = 40 if where == "middle" else 5       # 100-byte lines: the long one starts mid-chunk or right at a cut
+    p, s = _pair_with_widths([100] * head + [1300] + [100] * 40)
+    r = _emu.classify(p, s, chunk=chunk)
+    assert r["status"] == 5, (r["status"], r["message"])
+    assert "longer than the staging buffer" in r["message"]
+    assert r["n_records"] <= head
+    # the control: without the long line the same walk finishes and matches the oracle
+    p2, s2 = _pair_with_widths([100] * (head + 40))
+    r2 = _emu.classify(p2, s2, chunk=chunk)
+    ref = oracle.classify(p2, s2)
+    assert r2["status"] == 0 and r2["outputs"] == ref["outputs"] and r2["counts"] == ref["counts"]

@@ -101,6 +101,7 @@ struct ScanArgs {
 struct ClassifyArgs {
     StreamBuf P, S;
     SCompact sc;
+    uint64_t sc_cap;                  /* rows the compact arrays hold: records at or beyond it are not looked up (the host grows the arrays and walks again) */
     unsigned long long *chain1;       /* [ntiles] */
     unsigned long long *chain2;       /* [ntiles][C2_SLOTS] status << 62 | bytes, one look-back chain per bin */
     Globals *g;

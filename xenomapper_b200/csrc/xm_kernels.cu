@@ -390,6 +390,53 @@ __device__ __forceinline__ void xm_st_fake(uint4 *p, uint4 v) { if ((v.x ^ v.y ^
 #else
 #define XM_ST(p, v) __stcs(p, v)
 #endif
+#ifndef XM_COPY_SHFL_ROWS
+#define XM_COPY_SHFL_ROWS 0      /* > 0: the experiment below, that many rows per trip (measured slower: 7.6 / 8.0 / 10.5 ms against 6.9 ms at 4 / 6 / 8 rows, profiles/r02_kernel_experiments.md) */
+#endif
+#if XM_COPY_SHFL_ROWS > 0
+/* Experiment (off by default): every destination chunk needs source vectors V[c] and V[c + 1]; lane L of row r holds
+ * V[c], and V[c + 1] sits in lane L + 1 of the same row -- for lane 31 in lane 0 of the next row.  Each lane loads one
+ * vector per chunk and takes the words it needs of the next one by a rotating shuffle to which lane 0 contributes its
+ * next row's vector: half the load instructions and L1 wavefronts, more rows in flight per trip -- and slower, the
+ * shuffles sit on the dependent path between the load and the store. */
+template <int WSH>
+__device__ __forceinline__ void copy_body(uint8_t *body, const uint8_t *sa, uint32_t nchunk, uint32_t bsh, uint32_t lane)
+{
+    constexpr int R = XM_COPY_SHFL_ROWS;
+    auto ld = [](const uint8_t *q) { return ld_src16(q, false); };
+    const int nxt = (int)((lane + 1u) & 31u);
+#pragma unroll 1
+    for (uint32_t cb = 0; cb < nchunk; cb += 32u * R) {
+        uint4 a[R + 1];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t c = cb + 32u * r + lane;
+            a[r] = ld(sa + 16u * (c < nchunk ? c : nchunk));            /* V[nchunk] is the last vector any chunk needs */
+        }
+        {
+            const uint32_t c = cb + 32u * R;
+            a[R] = ld(sa + 16u * (c < nchunk ? c : nchunk));            /* one address for the whole warp */
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t c = cb + 32u * r + lane;
+            if (cb + 32u * r >= nchunk) break;                            /* uniform: the trip's last rows may be empty */
+            const uint4 q0 = a[r];
+            uint4 q1;
+            q1.x = __shfl_sync(0xffffffffu, lane == 0 ? a[r + 1].x : q0.x, nxt);
+            if (WSH >= 1) q1.y = __shfl_sync(0xffffffffu, lane == 0 ? a[r + 1].y : q0.y, nxt);
+            if (WSH >= 2) q1.z = __shfl_sync(0xffffffffu, lane == 0 ? a[r + 1].z : q0.z, nxt);
+            if (WSH >= 3) q1.w = __shfl_sync(0xffffffffu, lane == 0 ? a[r + 1].w : q0.w, nxt);
+            uint4 o;
+            if (WSH == 0) { o.x = __funnelshift_r(q0.x, q0.y, bsh); o.y = __funnelshift_r(q0.y, q0.z, bsh); o.z = __funnelshift_r(q0.z, q0.w, bsh); o.w = __funnelshift_r(q0.w, q1.x, bsh); }
+            else if (WSH == 1) { o.x = __funnelshift_r(q0.y, q0.z, bsh); o.y = __funnelshift_r(q0.z, q0.w, bsh); o.z = __funnelshift_r(q0.w, q1.x, bsh); o.w = __funnelshift_r(q1.x, q1.y, bsh); }
+            else if (WSH == 2) { o.x = __funnelshift_r(q0.z, q0.w, bsh); o.y = __funnelshift_r(q0.w, q1.x, bsh); o.z = __funnelshift_r(q1.x, q1.y, bsh); o.w = __funnelshift_r(q1.y, q1.z, bsh); }
+            else { o.x = __funnelshift_r(q0.w, q1.x, bsh); o.y = __funnelshift_r(q1.x, q1.y, bsh); o.z = __funnelshift_r(q1.y, q1.z, bsh); o.w = __funnelshift_r(q1.z, q1.w, bsh); }
+            if (c < nchunk) XM_ST((uint4 *)(body + 16u * c), o);
+        }
+    }
+}
+#else
 template <int WSH>
 __device__ __forceinline__ void copy_body(uint8_t *body, const uint8_t *sa, uint32_t nchunk, uint32_t bsh, uint32_t lane)
 {
@@ -421,6 +468,8 @@ __device__ __forceinline__ void copy_body(uint8_t *body, const uint8_t *sa, uint
     }
 }
 
+#endif
+
 __device__ void dev_copy_global(uint8_t *dst, const uint8_t *src, uint32_t len)
 {
 #if XM_WHATIF == 2
@@ -434,30 +483,28 @@ __device__ void dev_copy_global(uint8_t *dst, const uint8_t *src, uint32_t len)
     const uint32_t u = (uint32_t)((uintptr_t)so & 15u);
     const uint8_t *sa = so - u;
     uint8_t *body = dst + head;
-#if XM_WHATIF != 7 && XM_WHATIF != 8
-    {
-        /* the unaligned head bytes by lanes 0-15, the tail bytes by lanes 16-31: one load and one store instruction */
-        const uint32_t i = lane & 15u;
-        const bool is_tail = lane >= 16u;
-        if (i < (is_tail ? tail : head)) {
-            const size_t o = is_tail ? (size_t)head + 16u * (size_t)nchunk + i : (size_t)i;
-            dst[o] = src[o];
-        }
-    }
-#endif
+    /* the unaligned head bytes by lanes 0-15, the tail bytes by lanes 16-31: one load instruction, requested before
+     * the body's loads, and one store instruction behind the body -- the copy waits for L2 once, not twice */
+    const uint32_t hi = lane & 15u;
+    const bool is_tail = lane >= 16u;
+    const bool has_byte = hi < (is_tail ? tail : head);
+    const size_t ho = is_tail ? (size_t)head + 16u * (size_t)nchunk + hi : (size_t)hi;
+    uint8_t hb = 0;
+    if (has_byte) hb = src[ho];
     const uint32_t bsh = (u & 3u) * 8u;
     if (u == 0) {
 #pragma unroll 4
         for (uint32_t c = lane; c < nchunk; c += 32u)
             __stcs((uint4 *)(body + 16u * c), ld_src16(sa + 16u * c, false));
-        return;
+    } else {
+        switch (u >> 2) {
+        case 0: copy_body<0>(body, sa, nchunk, bsh, lane); break;
+        case 1: copy_body<1>(body, sa, nchunk, bsh, lane); break;
+        case 2: copy_body<2>(body, sa, nchunk, bsh, lane); break;
+        default: copy_body<3>(body, sa, nchunk, bsh, lane); break;
+        }
     }
-    switch (u >> 2) {
-    case 0: copy_body<0>(body, sa, nchunk, bsh, lane); break;
-    case 1: copy_body<1>(body, sa, nchunk, bsh, lane); break;
-    case 2: copy_body<2>(body, sa, nchunk, bsh, lane); break;
-    default: copy_body<3>(body, sa, nchunk, bsh, lane); break;
-    }
+    if (has_byte) dst[ho] = hb;
 }
 }  // namespace xm
 #include "xm_scan2.cuh"

@@ -61,7 +61,10 @@ struct SpanInfo {
 };
 
 /* masks (tbm, nlm, trk: this warp's private shared memory), line starts and the owned range of one span.
- * need_prev: the line before the first owned one will be looked at (run heads, pair units). */
+ * need_prev: the line before the first owned one will be looked at (run heads, pair units).
+ * (Round 2 tried a three-pass version -- bare mask steps, 512-byte tail steps, one index pass per span -- with
+ * 15 % fewer instructions: 10 % slower in k_scan2, 1.5 % faster in k_classify2; these kernels are paced by the
+ * dependent latencies a warp strings together, not by its instruction count.  profiles/r02_kernel_experiments.md) */
 template <class C, bool SPLIT>
 __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span_lo, bool need_prev, uint32_t *tbm, uint32_t *nlm, uint16_t *trk, uint16_t *starts)
 {
@@ -482,6 +485,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
     const unsigned long long base = S.base1[0] + wbase;        /* record index of this span's first yielded record */
     unsigned long long ncap = a.g->n_stream[1];
     if (a.limit < ncap) ncap = a.limit;
+    if (a.sc_cap < ncap) ncap = a.sc_cap;      /* more secondary records than compact rows: nothing past them is read; the host grows the arrays and walks again */
 
     /* ---- join, decide, size ------------------------------------------------------------------------ */
     uint32_t wtot_l = 0;                     /* lane b < 7 carries the warp's running total of slot b (six bins, raw bytes) */

@@ -88,6 +88,7 @@ inline int walk_stream(BE &be, Scratch &sc, HostIn in[2], DevIn dev[2], uint8_t 
     int halo = first_is_context ? 1 : 0;                      /* sharded walks: the caller's buffers open with the record before its range */
     for (uint64_t step = 0;; ++step) {
         const int cur = (int)(step & 1), prev = cur ^ 1;
+        uint64_t staged = 0;                                   /* new bytes this step, both streams */
         /* stage: carry to the front, new bytes behind it */
         for (int s = 0; s < 2; ++s) {
             if (carry_len[s] && be.copy_dd(dev[s].buf[cur], dev[s].buf[prev] + carry_off[s], carry_len[s])) { errmsg = "carry copy failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
@@ -122,6 +123,7 @@ inline int walk_stream(BE &be, Scratch &sc, HostIn in[2], DevIn dev[2], uint8_t 
             const bool is_final2 = in[s].pos + take == in[s].len;
             if (take && be.upload(dev[s].buf[cur] + carry_len[s], src, take)) { errmsg = "H2D copy failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
             in[s].pos += take;
+            staged += take;
             final_sent[s] = is_final2;
             dev[s].len = carry_len[s] + take;
         }
@@ -169,6 +171,12 @@ inline int walk_stream(BE &be, Scratch &sc, HostIn in[2], DevIn dev[2], uint8_t 
         if (done) break;
         if (fresh == 0 && (dev[0].len == dev[0].cap || dev[1].len == dev[1].cap)) {
             errmsg = "no complete record fits the staging buffers";
+            return res->status = XM_ERR_UNSUPPORTED;
+        }
+        if (fresh == 0 && staged == 0) {
+            /* nothing was yielded and nothing new could be staged behind the carry: the next step would be this one
+             * again.  A line that does not fit the staging chunk of a descriptor source ends here. */
+            errmsg = "a line is longer than the staging buffer (" + std::to_string(plan.chunk) + " bytes per step)";
             return res->status = XM_ERR_UNSUPPORTED;
         }
         /* carry: from the last yielded record (the next step's halo) to the end of each buffer */

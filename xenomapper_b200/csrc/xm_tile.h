@@ -801,6 +801,7 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
     /* records at or beyond ncap are not yielded: the other stream ended first, or an error re-run cut here */
     unsigned long long ncap = a.g->n_stream[1];
     if (a.limit < ncap) ncap = a.limit;
+    if (a.sc_cap < ncap) ncap = a.sc_cap;      /* the secondary stream held more records than the compact arrays: nothing past them is read */
     if (pstop) ncap = 0;
 
     /* per-record decision.  Paired walks publish it for the next line's owner. */

@@ -301,7 +301,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         sa.score_src = o.score_src; sa.skip = o.skip_repeated ? 1 : 0; sa.stream_id = 1; sa.debug = debug;
         ClassifyArgs ca;
         memset(&ca, 0, sizeof ca);
-        ca.P = P; ca.S = S; ca.sc = sc.sc; ca.chain1 = sc.chain1_p; ca.chain2 = sc.chain2;
+        ca.P = P; ca.S = S; ca.sc = sc.sc; ca.sc_cap = sc.sc_cap; ca.chain1 = sc.chain1_p; ca.chain2 = sc.chain2;
         ca.g = sc.g; ca.ntiles = (uint32_t)nt_p; ca.mode = o.mode; ca.score_src = o.score_src; ca.skip = sa.skip;
         ca.thr = score_threshold(o.min_score); ca.enabled = o.enabled_bins & 0x3f; ca.limit = limit; ca.debug = debug;
         for (int b = 0; b < 6; ++b) { ca.out[b] = out[b]; ca.out_cap[b] = ((ca.enabled >> b) & 1u) ? out_cap[b] : 0; }
