@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define XM_ABI_VERSION 4
+#define XM_ABI_VERSION 5
 
 /* States and bins share one numbering: the order of the reference's output
  * arguments (xm.py:291-297).  counts[] is indexed [state] for single-end and
@@ -98,6 +98,8 @@ typedef struct xm_result {
     float ms_classify;       /* device time of the primary-stream classify+emit kernel */
     float ms_total;          /* device time of the whole call (CUDA events) */
     uint32_t n_launches;     /* kernels launched by the call */
+    float ms_kernel[6];      /* the walk over rows (clean inputs): secondary scan, primary scan, size, prefix + emit; rest 0 */
+    uint32_t reserved[2];
 } xm_result;
 
 typedef struct xm_ctx xm_ctx;
@@ -164,6 +166,51 @@ int xm_count_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repea
 int xm_locate_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repeated, uint32_t n_queries,
                      const uint64_t *record_index, uint64_t *byte_offset);
 
+/* ---- the walk across the GPUs of one box (one process per GPU, NCCL inside the library) ------------ */
+
+/* Every rank holds a BYTE shard of each record region -- bytes [len*r/W, len*(r+1)/W), cut anywhere -- and walks
+ * the RECORDS its primary shard holds (getReadPairs is a lockstep reader, xm.py:95-118: the two files must stay
+ * aligned by record index, and pair units / QNAME runs must not be cut, xm.py:402, :110-114).  Line heads,
+ * context lines and the rows + text of the few secondary records that sit in a neighbour's shard travel over
+ * NCCL; nothing else does.  Shard outputs concatenated in rank order equal the single-GPU output.
+ * The launcher ferries 128 bytes: rank 0 calls xm_comm_unique_id, every rank xm_comm_init_rank with it. */
+#define XM_COMM_ID_BYTES 128
+int xm_comm_unique_id(void *id128);
+int xm_comm_init_rank(xm_ctx *ctx, int nranks, int rank, const void *id128);
+int xm_comm_destroy(xm_ctx *ctx);
+/* small collectives for launchers and benchmarks, so that they need no communication library of their own */
+int xm_comm_barrier(xm_ctx *ctx);
+int xm_comm_allreduce_f64(xm_ctx *ctx, double *values, int n, int op /* 0 sum, 1 max */);
+
+typedef struct xm_shard_stats {
+    uint64_t rec_lo, rec_hi;        /* this rank walked records [rec_lo, rec_hi) of the yielded sequence */
+    uint64_t n_records_total;       /* records of the whole job */
+    uint64_t out_offset[6];         /* where this rank's bytes go inside each bin (sum of the lower ranks' lengths) */
+    uint64_t out_total[6];          /* length of each bin over all ranks */
+    uint64_t sliver_bytes;          /* bytes this rank received from other ranks: line heads, context lines, rows and text of record slivers */
+    uint64_t sent_bytes;
+    float align_ms, index_ms, sliver_ms, walk_ms;      /* host wall time of the phases: line heads + context lines, the two scans, the
+                                                          sliver exchange, size + prefix + emit */
+    float comm_ms;                  /* of which inside collectives / send-receive groups */
+    float total_ms;
+    uint32_t n_collectives;
+    int32_t first_bad_rank;         /* rank that reported the first failing record, -1 if none */
+} xm_shard_stats;
+
+/* Device-resident byte shards.  d_prim / d_sec point at the first byte of this rank's shard inside an allocation
+ * with at least front_room writable bytes before it and back_room after it (received line heads, slivers; 1 MiB
+ * each is plenty unless the two streams' record densities differ wildly between shards).  res->counts and
+ * res->n_records describe the whole job, res->out_len this rank's bins.  Clean SAM only (what the barrier-free
+ * kernels handle): anything else returns XM_ERR_UNSUPPORTED on every rank, nothing written -- use
+ * xm_classify_sharded_host, which then gathers the shards on rank 0 for the exact walk. */
+int xm_classify_sharded_device(xm_ctx *ctx, void *d_prim, uint64_t prim_len, void *d_sec, uint64_t sec_len,
+                               uint64_t front_room, uint64_t back_room, const xm_opts *opts,
+                               void *const d_out[6], const uint64_t out_cap[6], xm_result *res, xm_shard_stats *stats);
+/* The same from host memory: this rank's byte shards are uploaded once, walked, and the rank's six bins come back
+ * in library-owned host blocks (xm_get_output).  What `torchrun -m xenomapper_b200.xenomapper` calls per rank. */
+int xm_classify_sharded_host(xm_ctx *ctx, const void *prim, uint64_t prim_len, const void *sec, uint64_t sec_len,
+                             const xm_opts *opts, xm_result *res, xm_shard_stats *stats);
+
 /* ---- BAM input ---------------------------------------------------------- */
 
 /* Replaces the two `samtools view` pipes of xm.py:48-64 (get_bam_header,
@@ -197,6 +244,7 @@ int xm_bam_get_stats(xm_ctx *ctx, xm_bam_stats *out, int reset);
 #define XM_KERNEL_CLASSIFY2 2u
 #define XM_KERNEL_SCAN 4u
 #define XM_KERNEL_CLASSIFY 8u
+#define XM_KERNEL_ROWS 16u          /* k_scan2 over both streams + k_size / k_prefix / k_emit */
 int xm_get_walk_kernels(xm_ctx *ctx, uint32_t *mask);
 
 /* ---- device memory helpers (so bindings need no CUDA of their own) ----- */
@@ -212,6 +260,8 @@ int xm_dev_mem_info(xm_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
 /* tuning knobs for tests: which tile geometry and parse path the kernels use */
 #define XM_DEBUG_FORCE_GENERIC 1u   /* every line through the exact byte-wise tokeniser */
 #define XM_DEBUG_SMALL_TILES   2u   /* 1 KiB tiles: exercises tile-boundary logic on small inputs */
+#define XM_DEBUG_ROWS          4u   /* clean inputs walk over rows (k_scan2 on both streams, k_size, k_prefix, k_emit: the kernels of
+                                       the sharded walk) instead of k_scan2 + the fused k_classify2 */
 int xm_set_debug(xm_ctx *ctx, uint32_t flags);
 
 #ifdef __cplusplus

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "xm_emu.cpp")
 SO = os.path.join(HERE, "emu", "libxm_emu.so")
 DEPS = [SRC] + [os.path.join(ROOT, "xenomapper_b200", "csrc", f) for f in
-                ("xm_common.h", "xm_parse.h", "xm_tile.h", "xm_walk.h", "xm_stream.h")] + [os.path.join(ROOT, "include", "xenomapper_b200.h")]
+                ("xm_common.h", "xm_parse.h", "xm_tile.h", "xm_walk.h", "xm_stream.h", "xm_shard.h")] + [os.path.join(ROOT, "include", "xenomapper_b200.h")]
 
 
 class Opts(C.Structure):
@@ -20,12 +20,28 @@ class Result(C.Structure):
     _fields_ = [("counts", C.c_uint64 * 36), ("n_records", C.c_uint64), ("out_len", C.c_uint64 * 6),
                 ("bytes_in", C.c_uint64 * 2), ("status", C.c_int32), ("err_stream", C.c_int32),
                 ("err_record", C.c_uint64), ("ms_scan", C.c_float), ("ms_classify", C.c_float),
-                ("ms_total", C.c_float), ("n_launches", C.c_uint32)]
+                ("ms_total", C.c_float), ("n_launches", C.c_uint32),
+                ("ms_kernel", C.c_float * 6), ("reserved", C.c_uint32 * 2)]
 
 
 class ShardInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("first_start", C.c_uint64), ("stop_at", C.c_uint64), ("end_off", C.c_uint64)]
 
+
+class ShardStats(C.Structure):
+    _fields_ = [("rec_lo", C.c_uint64), ("rec_hi", C.c_uint64), ("n_records_total", C.c_uint64),
+                ("out_offset", C.c_uint64 * 6), ("out_total", C.c_uint64 * 6), ("sliver_bytes", C.c_uint64),
+                ("sent_bytes", C.c_uint64), ("align_ms", C.c_float), ("index_ms", C.c_float), ("sliver_ms", C.c_float),
+                ("walk_ms", C.c_float), ("comm_ms", C.c_float), ("total_ms", C.c_float), ("n_collectives", C.c_uint32),
+                ("first_bad_rank", C.c_int32)]
+
+
+class Xfer(C.Structure):
+    _fields_ = [("peer", C.c_int), ("ptr", C.c_void_p), ("bytes", C.c_uint64)]
+
+
+ALL_GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(Xfer), C.c_int, C.POINTER(Xfer), C.c_int)
 
 _lib = None
 
@@ -48,6 +64,10 @@ def lib():
         _lib.xm_emu_index.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_uint64), C.POINTER(ShardInfo), C.c_char_p, C.c_size_t]
         _lib.xm_emu_index.restype = C.c_int
+        _lib.xm_emu_classify_sharded.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(Opts), C.c_int, C.c_int,
+                                                 ALL_GATHER_FN, EXCHANGE_FN, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                                 C.POINTER(Result), C.POINTER(ShardStats), C.c_char_p, C.c_size_t]
+        _lib.xm_emu_classify_sharded.restype = C.c_int
     return _lib
 
 
@@ -86,3 +106,26 @@ def classify(prim, sec, mode=0, score_src=0, skip_repeated=False, min_score=floa
     outs = [bufs[b].raw[:r.out_len[b]] for b in range(6)]
     return dict(status=rc, outputs=outs, counts=list(r.counts), n_records=r.n_records, err_record=r.err_record,
                 bytes_in=list(r.bytes_in), message=err.value.decode())
+
+
+def classify_sharded(prim, sec, rank, world, all_gather, exchange, mode=0, score_src=0, skip_repeated=False,
+                     min_score=float("-inf"), enabled_bins=0x3F, room=1 << 16):
+    """one rank of the walk across ranks (csrc/xm_shard.h) on the CPU.  prim / sec: this rank's BYTE shards;
+    all_gather(send_addr, recv_addr, nbytes) and exchange(sends, ns, recvs, nr) are the test's collectives.
+    status -2: every rank declined together (input needs the exact kernels)."""
+    L = lib()
+    prim, sec = bytes(prim), bytes(sec)
+    cap = 4 * (len(prim) + len(sec)) + 2 * room + 4096
+    bufs = [C.create_string_buffer(cap) for _ in range(6)]
+    outp = (C.c_void_p * 6)(*[C.cast(b, C.c_void_p) for b in bufs])
+    caps = (C.c_uint64 * 6)(*([cap] * 6))
+    o = Opts(mode, score_src, int(bool(skip_repeated)), enabled_bins, min_score)
+    r, st = Result(), ShardStats()
+    err = C.create_string_buffer(512)
+    ag, ex = ALL_GATHER_FN(all_gather), EXCHANGE_FN(exchange)
+    rc = L.xm_emu_classify_sharded(prim, len(prim), sec, len(sec), C.byref(o), rank, world, ag, ex, room, outp, caps,
+                                   C.byref(r), C.byref(st), err, 512)
+    outs = [bufs[b].raw[:r.out_len[b]] for b in range(6)]
+    return dict(status=rc, outputs=outs, counts=list(r.counts), n_records=int(r.n_records), err_record=int(r.err_record),
+                out_offset=list(st.out_offset), out_total=list(st.out_total), records=(int(st.rec_lo), int(st.rec_hi)),
+                sliver_bytes=int(st.sliver_bytes), message=err.value.decode())

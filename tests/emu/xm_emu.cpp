@@ -72,6 +72,10 @@ struct EmuBackend {
     int scan2(const ScanArgs &) { return -1; }      /* the warp-synchronous scan exists on the device only */
     uint64_t scan2_tiles(uint64_t) { return 0; }
     int classify2(const ClassifyArgs &) { return -1; }
+    bool rows_enabled() { return false; }          /* the row kernels exist on the device only */
+    int size(const EmitArgs &) { return -1; }
+    int prefix(const EmitArgs &) { return -1; }
+    int emit(const EmitArgs &) { return -1; }
     int classify(const ClassifyArgs &a, bool small) { if (small) classify_t<CfgSmall>(a); else classify_t<CfgBig>(a); return 0; }
 };
 
@@ -156,6 +160,163 @@ extern "C" int xm_emu_index(const void *buf, uint64_t len, int skip, uint32_t de
     std::string msg;
     const int rc = index_resident(be, sc, StreamBuf{b.data(), len}, skip != 0, debug, nq, q, off, info, msg);
     scratch_release(be, sc);
+    if (errbuf && errcap) { strncpy(errbuf, msg.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
+    return rc;
+}
+
+/* ================================================================================================================
+ * The walk across ranks (xm_shard.h) on the CPU: the same host logic as the NCCL runtime, with
+ *   - scalar stand-ins for the device-only row kernels (k_scan2 -> rows, k_size, k_prefix, k_emit): they follow the
+ *     same contract (rows of clean lines, Globals::pad for anything else) so that the orchestration -- line heads,
+ *     context lines, filler, counts, slivers, placement in the bins -- is what gets tested;
+ *   - a Comm whose all-gather and send/receive are callbacks into the test process (torch.distributed, gloo).
+ * ================================================================================================================ */
+#include "../../xenomapper_b200/csrc/xm_shard.h"
+
+namespace {
+
+struct EmuRowsBackend : EmuBackend {
+    int add64(void *p, uint64_t n, unsigned long long d) { unsigned long long *q = (unsigned long long *)p; for (uint64_t k = 0; k < n; ++k) q[k] += d; return 0; }
+    uint64_t scan2_tiles(uint64_t len) { return len / 4096 + 1; }
+    /* rows of every line (run heads with skip); a blank line raises pad, flagged lines keep their flags for k_size */
+    int scan2(const ScanArgs &a)
+    {
+        const Reader rd{a.S.p, a.S.p, 0, (uint32_t)std::min<uint64_t>(a.S.len, 0xffffffffu), a.S.len};
+        uint64_t n = 0, off = 0;
+        LineRec prev;
+        bool have_prev = false;
+        while (off < a.S.len) {
+            LineRec L;
+            generic_parse(rd, off, a.score_src, L);
+            if (L.flags & F_BLANK) { if (getenv("XM_EMU_DEBUG")) fprintf(stderr, "[emu scan] blank line at %llu of %llu\n", (unsigned long long)off, (unsigned long long)a.S.len); a.g->pad = 1; break; }
+            bool same = false;
+            if (have_prev && (a.skip || a.want_same) && prev.qlen == L.qlen && memcmp(a.S.p + prev.qs, a.S.p + L.qs, L.qlen) == 0) same = true;
+            if (!(a.skip && same)) {
+                if (n < a.sc_cap) {
+                    a.sc.start[n] = a.start_bias + off;
+                    a.sc.rec[n] = make_uint4((uint32_t)L.as, (uint32_t)L.xs, L.h1, L.h2);
+                    a.sc.meta[n] = (L.outlen & META_LEN_MASK) | ((L.flags & 0x3fu) << META_LEN_BITS) | (same ? META_SAME : 0u);
+                }
+                ++n;
+            }
+            prev = L; have_prev = true;
+            off += L.rawbytes;
+        }
+        a.g->n_stream[a.stream_id] = n;
+        a.g->end_off[a.stream_id] = a.S.len;
+        if (n <= a.sc_cap) a.sc.start[n] = a.start_bias + a.S.len;
+        return 0;
+    }
+    /* the decision of one record from its rows (xm_emit.cuh rows_decide, scalar) */
+    struct Dec { uint32_t key, bin, plen, slen; uint64_t psrc, ssrc; };
+    static Dec decide(const EmitArgs &a, uint64_t i, bool check, bool &bad)
+    {
+        Dec d{36, NO_BIN, 0, 0, 0, 0};
+        auto state = [&](uint64_t k) { const uint4 p = a.rp.rec[k], s = a.rs.rec[k]; return mapping_state((int32_t)p.x, (int32_t)p.y, (int32_t)s.x, (int32_t)s.y, a.thr); };
+        const uint32_t pm = a.rp.meta[i], sm = a.rs.meta[i];
+        const uint64_t ps = a.rp.start[i], ss = a.rs.start[i];
+        if (check) {
+            const uint4 p = a.rp.rec[i], s = a.rs.rec[i];
+            if (((pm | sm) & META_FLAGS) || p.z != s.z || p.w != s.w) bad = true;
+            else {
+                const uint8_t *x = a.P.p + ps, *y = a.S.p + ss;
+                for (;; ++x, ++y) { if (*x != *y) { bad = true; break; } if (*x < 0x21) break; }
+            }
+        }
+        const int st = state(i);
+        const uint32_t pout = pm & META_LEN_MASK, sout = sm & META_LEN_MASK;
+        if (a.mode == MODE_SE) {
+            if (!(a.halo && i == 0)) {
+                d.key = (uint32_t)st; d.bin = (uint32_t)st;
+                const bool pside = st == PS || st == PM || st == UA || st == UR, sside = st == SS || st == SM || st == UR;
+                d.plen = pside ? pout : 0; d.slen = sside ? sout : 0; d.psrc = ps; d.ssrc = ss;
+            }
+        } else if (!a.skip && (pm & META_SAME) && i > 0) {
+            const int pst = state(i - 1);
+            const uint32_t ppout = a.rp.meta[i - 1] & META_LEN_MASK, psout = a.rs.meta[i - 1] & META_LEN_MASK;
+            d.key = (uint32_t)(pst * 6 + st);
+            d.bin = (uint32_t)(a.mode == MODE_PE_CONSERVATIVE ? pair_bin_conservative(pst, st) : pair_bin_liberal(pst, st));
+            const bool pside = d.bin == PS || d.bin == PM || d.bin == UA || d.bin == UR, sside = d.bin == SS || d.bin == SM || d.bin == UR;
+            d.plen = pside ? ppout + pout : 0; d.slen = sside ? psout + sout : 0; d.psrc = a.rp.start[i - 1]; d.ssrc = a.rs.start[i - 1];
+            if (check && (d.psrc + ppout != ps || d.ssrc + psout != ss)) bad = true;
+        }
+        if (d.bin != NO_BIN && !((a.enabled >> d.bin) & 1u)) { d.plen = 0; d.slen = 0; }
+        return d;
+    }
+    int size(const EmitArgs &a)
+    {
+        bool bad = false;
+        unsigned long long tot[6] = {0, 0, 0, 0, 0, 0};
+        for (uint64_t i = 0; i < a.n; ++i) {
+            const bool was = bad;
+            const Dec d = decide(a, i, true, bad);
+            if (bad && !was && getenv("XM_EMU_DEBUG"))
+                fprintf(stderr, "[emu size] record %llu of %llu bad: pmeta %x smeta %x pstart %llu sstart %llu P:'%.24s' S:'%.24s'\n", (unsigned long long)i, (unsigned long long)a.n,
+                        a.rp.meta[i], a.rs.meta[i], (unsigned long long)a.rp.start[i], (unsigned long long)a.rs.start[i], a.P.p + a.rp.start[i], a.S.p + a.rs.start[i]);
+            if (d.key < 36) a.g->counts[d.key]++;
+            if (d.bin < 6) tot[d.bin] += d.plen + d.slen;
+        }
+        if (bad) a.g->pad = 1;
+        for (int b = 0; b < 6; ++b) a.tile_tot[b] = tot[b];      /* one tile */
+        return 0;
+    }
+    int prefix(const EmitArgs &a) { for (int b = 0; b < 6; ++b) { a.g->out_len[b] = a.tile_tot[b]; a.tile_tot[b] = 0; } return 0; }
+    int emit(const EmitArgs &a)
+    {
+        bool bad = false;
+        unsigned long long at[6] = {0, 0, 0, 0, 0, 0};
+        for (uint64_t i = 0; i < a.n; ++i) {
+            const Dec d = decide(a, i, false, bad);
+            if (d.bin >= 6) continue;
+            if (d.plen && at[d.bin] + d.plen <= a.out_cap[d.bin]) memcpy(a.out[d.bin] + at[d.bin], a.P.p + d.psrc, d.plen);
+            at[d.bin] += d.plen;
+            if (d.slen && at[d.bin] + d.slen <= a.out_cap[d.bin]) memcpy(a.out[d.bin] + at[d.bin], a.S.p + d.ssrc, d.slen);
+            at[d.bin] += d.slen;
+        }
+        return 0;
+    }
+};
+
+typedef int (*emu_all_gather_fn)(const void *send, void *recv, uint64_t bytes);
+typedef int (*emu_exchange_fn)(const Xfer *sends, int ns, const Xfer *recvs, int nr);
+struct EmuComm {
+    int my, n;
+    emu_all_gather_fn ag;
+    emu_exchange_fn ex;
+    int rank() const { return my; }
+    int size() const { return n; }
+    std::string last_error() const { return "callback failed"; }
+    int all_gather(const void *send, void *recv, size_t bytes) { if (n == 1) { memcpy(recv, send, bytes); return 0; } return ag(send, recv, bytes); }
+    int exchange(const Xfer *sends, int ns, const Xfer *recvs, int nr) { return ex(sends, ns, recvs, nr); }
+};
+
+}  // namespace
+
+extern "C" int xm_emu_classify_sharded(const void *prim, uint64_t plen, const void *sec, uint64_t slen, const xm_opts *o, int rank, int world,
+                                       emu_all_gather_fn ag, emu_exchange_fn ex, uint64_t room, void *const out[6], const uint64_t cap[6],
+                                       xm_result *res, xm_shard_stats *st, char *errbuf, size_t errcap)
+{
+    /* shard buffers with room on both sides, deliberately misaligned so that the filler line is exercised */
+    std::vector<uint8_t> buf[2];
+    const void *src[2] = {prim, sec};
+    const uint64_t len[2] = {plen, slen};
+    ShardBuf in[2];
+    for (int s = 0; s < 2; ++s) {
+        buf[s].assign(len[s] + 2 * room + 96, 0xEE);
+        uint8_t *p = buf[s].data() + room + 16;
+        p += (16 - ((uintptr_t)p & 15)) & 15;
+        p += (rank * 5 + s * 3) & 15;
+        if (len[s]) memcpy(p, src[s], len[s]);
+        in[s] = ShardBuf{p, len[s], room, room};
+    }
+    EmuRowsBackend be;
+    EmuComm cm{rank, world, ag, ex};
+    ShardScratch sc;
+    std::string msg;
+    uint8_t *o6[6];
+    for (int b = 0; b < 6; ++b) o6[b] = (uint8_t *)out[b];
+    const int rc = walk_sharded(be, cm, sc, in, *o, o6, cap, 0, res, st, msg);
+    shard_release(be, sc);
     if (errbuf && errcap) { strncpy(errbuf, msg.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
     return rc;
 }

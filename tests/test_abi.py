@@ -26,14 +26,14 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared_functions():
         assert hasattr(L, name), "libxenomapper_b200.so does not export " + name
-    assert _lib.load().xm_abi_version() == 4
+    assert _lib.load().xm_abi_version() == 5
     assert sorted(_lib.EXPORTS) == declared_functions()
 
 
 def test_struct_layouts_match_the_header():
     from xenomapper_b200 import _lib
     assert ctypes.sizeof(_lib.Opts) == 24
-    assert ctypes.sizeof(_lib.Result) == 36 * 8 + 8 + 48 + 16 + 8 + 8 + 16
+    assert ctypes.sizeof(_lib.Result) == 36 * 8 + 8 + 48 + 16 + 8 + 8 + 16 + 24 + 8
     assert ctypes.sizeof(_lib.ShardInfo) == 32
 
 

@@ -34,10 +34,12 @@ def run_case(ctx, case, debug):
         assert G.counts_dict(list(res.counts), o["mode"]) == e["counts"]
 
 
-@pytest.mark.parametrize("debug", [0, 1, 2, 3], ids=["big", "big_generic", "small", "small_generic"])
+@pytest.mark.parametrize("debug", [0, 1, 2, 3, 4], ids=["big", "big_generic", "small", "small_generic", "rows"])
 @pytest.mark.parametrize("case", G.CASES, ids=[c["name"] for c in G.CASES])
 def test_cuda_matches_reference_golden(ctx, case, debug):
-    if debug >= 2 and case["input"]["kind"] == "synth" and case["input"]["seed"] != 1:
+    """debug 4 (XM_DEBUG_ROWS): clean cases walk over rows (both streams through k_scan2, then k_size / k_prefix /
+    k_emit -- the kernels of the sharded walk); every other case must be handed to the exact pair"""
+    if debug in (2, 3) and case["input"]["kind"] == "synth" and case["input"]["seed"] != 1:
         pytest.skip("covered by seed 1")
     run_case(ctx, case, debug)
 
@@ -68,30 +70,32 @@ def test_cuda_fixed_width_lines_match_oracle(ctx, width, mode, skip):
     assert outs == ref["outputs"]
 
 
+@pytest.mark.parametrize("rows", [0, 4], ids=["fused", "rows"])
 @pytest.mark.parametrize("width", [600, 632, 648, 700, 900, 1000])
 @pytest.mark.parametrize("mode,skip", [(0, False), (0, True), (1, False)])
-def test_cuda_span_kernels_find_the_line_before_the_span(ctx, width, mode, skip):
+def test_cuda_span_kernels_find_the_line_before_the_span(ctx, width, mode, skip, rows):
     """walks that look at the line before a span scan 640 bytes before it first and the whole 1 KiB only when that
     line starts earlier (xm_scan2.cuh span_front): lines just below and above that length, on the barrier-free pair"""
     from oracle import oracle
     from tests.test_emu_tiles import _fixed_width_pair
     from xenomapper_b200 import _lib
-    ctx.set_debug(0)
+    ctx.set_debug(rows)
     p, s = _fixed_width_pair(4000, width)
     ref = oracle.classify(p, s, mode=mode, skip_repeated=skip)
     rc, res, outs = ctx.classify_host(p, s, _lib.Context.opts(mode, 0, skip))
     assert rc == 0, ctx.error()
-    assert ctx.walk_kernels() == ["k_scan2", "k_classify2"]
+    assert ctx.walk_kernels() == (["k_scan2", "k_size+k_prefix+k_emit"] if rows else ["k_scan2", "k_classify2"])
     assert list(res.counts) == ref["counts"]
     assert outs == ref["outputs"]
 
 
+@pytest.mark.parametrize("rows", [0, 4], ids=["fused", "rows"])
 @pytest.mark.parametrize("style,mode,skip", [(0, 0, True), (1, 1, False), (2, 2, False)])
-def test_cuda_large_synthetic_matches_oracle(ctx, style, mode, skip):
+def test_cuda_large_synthetic_matches_oracle(ctx, style, mode, skip, rows):
     """300 k records (about 130 MB per stream: thousands of tiles, look-back across several waves of CTAs)"""
     from oracle import oracle
     from xenomapper_b200 import _lib, synth
-    ctx.set_debug(0)
+    ctx.set_debug(rows)
     p, s = synth.generate(300000, seed=77, style=style)
     score = 1 if style == 2 else 0
     ref = oracle.classify(p, s, mode=mode, score_src=score, skip_repeated=skip, min_score=-18.0 if style == 2 else float("-inf"))
@@ -182,3 +186,33 @@ def test_cuda_kernel_selection_and_fallback(ctx):
     ref = oracle.classify(pe, s, skip_repeated=True)
     assert ERR[rc] == "ValueError" and ref["err"] == 2
     assert outs == ref["outputs"]
+
+
+def test_cuda_row_walk_selection_and_fallback(ctx):
+    """XM_DEBUG_ROWS: clean input walks over rows; a dirty line in either stream, a QNAME that differs in one byte
+    (same length, so only the hash and the byte compare of k_size can tell) or an input error hands the whole walk
+    to the exact pair, with the reference's result either way"""
+    from oracle import oracle
+    from xenomapper_b200 import _lib, synth
+    ctx.set_debug(_lib.DEBUG_ROWS)
+    for style, mode, skip in ((0, 0, True), (1, 1, False), (1, 2, False)):
+        p, s = synth.generate(40000, seed=21, style=style)
+        o = _lib.Context.opts(mode, 0, skip)
+        rc, res, outs = ctx.classify_host(p, s, o)
+        assert rc == 0 and ctx.walk_kernels() == ["k_scan2", "k_size+k_prefix+k_emit"]
+        ref = oracle.classify(p, s, mode=mode, skip_repeated=skip)
+        assert outs == ref["outputs"] and list(res.counts) == ref["counts"]
+        for prim, sec in ((bytes(p).replace(b"\tXM:i:", b" XM:i:", 1), s), (p, bytes(s).replace(b"\tXM:i:", b" XM:i:", 1))):
+            rc, res, outs = ctx.classify_host(prim, sec, o)
+            ref = oracle.classify(prim, sec, mode=mode, skip_repeated=skip)
+            assert rc == 0 and "k_classify" in ctx.walk_kernels()
+            assert outs == ref["outputs"] and list(res.counts) == ref["counts"]
+        # one QNAME byte changed in the middle of the secondary stream: AssertionError at that record, the prefix before it
+        sb = bytearray(bytes(s))
+        at = sb.index(b"\n", len(sb) // 2) + 1
+        sb[at + 5] = ord("Z") if sb[at + 5] != ord("Z") else ord("Y")
+        rc, res, outs = ctx.classify_host(p, bytes(sb), o)
+        ref = oracle.classify(p, bytes(sb), mode=mode, skip_repeated=skip)
+        assert ERR[rc] == "AssertionError" and ref["err"] == 1
+        assert outs == ref["outputs"]
+    ctx.set_debug(0)

@@ -64,7 +64,7 @@ def make_case(kind):
     raise KeyError(kind)
 
 
-def run_sharded(tmp_path, world, p, s, o, debug=0, engine="emu"):
+def run_sharded(tmp_path, world, p, s, o, engine="emu", room=1 << 20):
     files = {}
     for name, data in (("prim", p), ("sec", s)):
         files[name] = str(tmp_path / (name + ".sam"))
@@ -72,7 +72,8 @@ def run_sharded(tmp_path, world, p, s, o, debug=0, engine="emu"):
     outs = [str(tmp_path / ("out%d.sam" % b)) for b in range(6)]
     for f in outs:
         open(f, "wb").close()
-    case = dict(files, outs=outs, result=str(tmp_path / "result.json"), enabled_bins=0x3F, debug=debug, engine=engine, **o)
+    case = dict(files, outs=outs, result=str(tmp_path / "result.json"), enabled_bins=0x3F, engine=engine, room=room,
+                rendezvous=str(tmp_path / "rv"), **o)
     casefile = str(tmp_path / "case.json")
     json.dump(case, open(casefile, "w"))
     port = free_port()
@@ -81,7 +82,26 @@ def run_sharded(tmp_path, world, p, s, o, debug=0, engine="emu"):
     for pr in procs:
         _, err = pr.communicate(timeout=600)
         assert pr.returncode == 0, err.decode()[-2000:]
-    return json.load(open(case["result"])), [open(f, "rb").read() for f in outs]
+    per_rank = [json.load(open("%s.%d" % (case["result"], r))) for r in range(world)]
+    return per_rank, [open(f, "rb").read() for f in outs]
+
+
+def check_against_oracle(per_rank, outs, ref, world):
+    """rank-order concatenated bins, the summed histogram and the record ranges equal the single pass"""
+    first = per_rank[0]
+    assert all(r["status"] == 0 for r in per_rank), [r["message"] for r in per_rank]
+    if first.get("declined"):
+        counts, n = first["counts"], first["n_records"]
+    else:
+        # every rank reports the whole job's histogram and record count
+        assert all(r["counts"] == first["counts"] and r["n_records"] == first["n_records"] for r in per_rank)
+        counts, n = first["counts"], first["n_records"]
+        spans = [tuple(r["records"]) for r in per_rank]
+        assert spans[0][0] == 0 and all(spans[k][1] == spans[k + 1][0] for k in range(world - 1))
+    assert counts == ref["counts"]
+    assert n == ref["n_yielded"]
+    assert first["out_total"] == [len(x) for x in ref["outputs"]]
+    assert outs == ref["outputs"]
 
 
 @pytest.mark.parametrize("world", [2, 3])
@@ -91,59 +111,113 @@ def test_sharded_walk_equals_single_pass(tmp_path, kind, world):
     p, s, o = make_case(kind)
     ref = oracle.classify(p, s, mode=o["mode"], score_src=o["score_src"], skip_repeated=o["skip"], min_score=o["min_score"])
     assert ref["err"] == 0
-    res, outs = run_sharded(tmp_path, world, p, s, o)
-    assert res["status"] == 0, res["message"]
-    assert res["counts"] == ref["counts"]
-    assert res["n_records"] == ref["n_yielded"]
-    assert res["out_total"] == [len(x) for x in ref["outputs"]]
-    assert outs == ref["outputs"]
+    per_rank, outs = run_sharded(tmp_path, world, p, s, o)
+    check_against_oracle(per_rank, outs, ref, world)
+    if kind != "pe_cigar_blank_stop":
+        assert not per_rank[0].get("declined")                  # the row kernels walked it: slivers, not a gather on rank 0
 
 
-def test_sharded_walk_small_tiles_many_boundaries(tmp_path):
-    """1 KiB tiles inside every shard on top of the shard boundaries"""
-    p, s, o = make_case("se_skip")
-    p, s = p[:60000], s[:50000]
-    p, s = p[:p.rfind(b"\n") + 1], s[:s.rfind(b"\n") + 1]
-    ref = oracle.classify(p, s, mode=0, skip_repeated=True)
-    res, outs = run_sharded(tmp_path, 2, p, s, o, debug=2)
-    assert res["status"] == 0, res["message"]
-    assert res["counts"] == ref["counts"] and outs == ref["outputs"]
+def test_sharded_walk_with_skewed_record_density(tmp_path):
+    """the secondary stream's lines are much shorter in its second half: byte shards and record-index shards differ by
+    hundreds of records, which travel as slivers (rows + text) between the ranks"""
+    p, s, o = make_case("pe_liberal")
+    lines = s.split(b"\n")[:-1]
+    half = len(lines) // 2
+    short = []
+    for ln in lines[half:]:
+        f = ln.split(b"\t")
+        f[9] = f[9][:20]; f[10] = f[10][:20]                      # SEQ and QUAL cut to 20 bases
+        short.append(b"\t".join(f))
+    s2 = b"\n".join(lines[:half] + short) + b"\n"
+    ref = oracle.classify(p, s2, mode=o["mode"], score_src=o["score_src"], skip_repeated=o["skip"], min_score=o["min_score"])
+    per_rank, outs = run_sharded(tmp_path, 3, p, s2, o)
+    check_against_oracle(per_rank, outs, ref, 3)
+    assert max(r["sliver_bytes"] for r in per_rank) > 20000
+
+
+def test_sharded_walk_reports_too_little_room(tmp_path):
+    """slivers that do not fit the room around a shard end the walk on every rank with XM_ERR_NOMEM, not with garbage"""
+    p, s, o = make_case("pe_liberal")
+    lines = s.split(b"\n")[:-1]
+    s2 = b"\n".join([b"\t".join(ln.split(b"\t")[:9] + [b"A", b"I"] + ln.split(b"\t")[11:]) for ln in lines[len(lines) // 2:]])
+    s2 = b"\n".join(lines[:len(lines) // 2]) + b"\n" + s2 + b"\n"
+    files = {}
+    per_rank = None
+    try:
+        per_rank, _ = run_sharded(tmp_path, 2, p, s2, o, room=2048)
+    except AssertionError:
+        pytest.fail("a rank crashed instead of reporting the missing room")
+    assert all(r["status"] == 6 for r in per_rank), per_rank
 
 
 def test_single_rank_is_the_plain_walk(tmp_path):
     p, s, o = make_case("pe_liberal")
     ref = oracle.classify(p, s, mode=1)
-    res, outs = run_sharded(tmp_path, 1, p, s, o)
-    assert res["counts"] == ref["counts"] and outs == ref["outputs"]
+    per_rank, outs = run_sharded(tmp_path, 1, p, s, o)
+    check_against_oracle(per_rank, outs, ref, 1)
 
 
-def test_line_alignment_helpers():
-    src = sharded.BytesSource(b"aa\nbbbb\n\ncc\n")
-    assert [sharded.line_start_at_or_after(src, x) for x in range(13)] == [0, 3, 3, 3, 8, 8, 8, 8, 8, 9, 12, 12, 12]
-    assert sharded.previous_line_start(src, 3) == 0
-    assert sharded.previous_line_start(src, 8) == 3
-    assert sharded.previous_line_start(src, 9) == 8
-    assert sharded.plan_partition(10, 4) == [0, 2, 5, 7, 10]
+def test_byte_ranges_and_rendezvous(tmp_path):
+    assert [sharded.byte_range(10, r, 4) for r in range(4)] == [(0, 2), (2, 5), (5, 7), (7, 10)]
+    assert sharded.byte_range(0, 1, 3) == (0, 0)
+    a, b = sharded.Rendezvous(0, 2, directory=str(tmp_path / "rv")), sharded.Rendezvous(1, 2, directory=str(tmp_path / "rv"))
+    a.publish("blob", b"x" * 128)
+    assert b.fetch("blob") == b"x" * 128
+    with pytest.raises(TimeoutError):
+        sharded.Rendezvous(1, 2, directory=str(tmp_path / "rv"), timeout=0.05).fetch("nothing")
+    a.cleanup()
+    assert not os.path.exists(str(tmp_path / "rv"))
+
+
+def _gpu_count():
+    try:
+        import ctypes
+        cuda = ctypes.CDLL("libcuda.so.1")
+        n = ctypes.c_int(0)
+        return n.value if cuda.cuInit(0) == 0 and cuda.cuDeviceGetCount(ctypes.byref(n)) == 0 else 0
+    except OSError:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["se_skip", "se_noskip_short_secondary", "pe_liberal", "pe_conservative_zs", "pe_cigar_blank_stop", "tiny"])
+def test_sharded_entry_point_with_one_rank_on_gpu(tmp_path, kind):
+    """xm_classify_sharded_host with a single rank: the whole record region is one (deliberately unaligned) shard --
+    filler line, both scans into rows, k_size / k_prefix / k_emit, and the gather-to-rank-0 path for the blank line"""
+    from xenomapper_b200 import _lib
+    p, s, o = make_case(kind)
+    ref = oracle.classify(p, s, mode=o["mode"], score_src=o["score_src"], skip_repeated=o["skip"], min_score=o["min_score"])
+    ctx = _lib.Context(0)
+    ctx.comm_init_rank(1, 0, None)
+    opts = ctx.opts(o["mode"], o["score_src"], o["skip"], o["min_score"])
+    rc, res, st, outs = ctx.classify_sharded_host(p, s, opts)
+    assert rc == 0, ctx.error()
+    assert list(res.counts) == ref["counts"] and int(res.n_records) == ref["n_yielded"]
+    assert outs == ref["outputs"]
+    assert list(st.out_total) == [len(x) for x in ref["outputs"]] and list(st.out_offset) == [0] * 6
+    ctx.close()
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["se_skip", "pe_liberal", "pe_conservative_zs", "pe_cigar_blank_stop"])
-def test_sharded_walk_on_gpu(tmp_path, kind):
-    """two ranks (gloo for the few words exchanged), each driving the CUDA kernels through the C ABI"""
+def test_sharded_walk_on_two_gpus(tmp_path, kind):
+    """two ranks, one device each, NCCL inside the library (`gpurun --gpus 2`)"""
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs")
     p, s, o = make_case(kind)
     ref = oracle.classify(p, s, mode=o["mode"], score_src=o["score_src"], skip_repeated=o["skip"], min_score=o["min_score"])
-    res, outs = run_sharded(tmp_path, 2, p, s, o, engine="gpu")
-    assert res["status"] == 0, res["message"]
-    assert res["counts"] == ref["counts"]
-    assert outs == ref["outputs"]
+    per_rank, outs = run_sharded(tmp_path, 2, p, s, o, engine="gpu")
+    check_against_oracle(per_rank, outs, ref, 2)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("flags", [[], ["--paired"], ["--paired", "--conservative", "--min_score", "-18", "--use_zs"]],
                          ids=["se", "pe", "pe_conservative_zs"])
 def test_sharded_cli_equals_single_process_cli(tmp_path, flags):
-    """`torchrun -m xenomapper_b200.xenomapper` (two ranks on one device, gloo for the words exchanged) writes the
-    same six files, headers included, as the single-process command"""
+    """the launcher + `-m xenomapper_b200.xenomapper` (two ranks, one device each, NCCL inside the library) writes
+    the same six files, headers included, as the single-process command"""
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs")
     style = synth.STYLE_PE_HISAT if "--use_zs" in flags else (synth.STYLE_PE_BOWTIE2 if flags else synth.STYLE_SE_BOWTIE2)
     p, s = synth.generate(3000, seed=21, style=style)
     if not flags:
@@ -165,7 +239,7 @@ def test_sharded_cli_equals_single_process_cli(tmp_path, flags):
     one, summary1 = run("one", [sys.executable], {})
     two, summary2 = run("two", [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                                 "--master-addr", "127.0.0.1", "--master-port", str(free_port())],
-                        {"XENOMAPPER_DIST_BACKEND": "gloo", "XENOMAPPER_DEVICE": "0"})
+                        {})
     assert two == one
     assert summary1[summary1.index("Read Count"):].strip() in summary2
 
@@ -173,8 +247,7 @@ def test_sharded_cli_equals_single_process_cli(tmp_path, flags):
 @pytest.mark.gpu
 def test_sharded_cli_over_nccl_on_two_gpus(tmp_path):
     """one process per GPU, NCCL for the words exchanged (needs two devices: `gpurun --gpus 2`)"""
-    import torch
-    if torch.cuda.device_count() < 2:
+    if _gpu_count() < 2:
         pytest.skip("needs two GPUs")
     p, s = synth.generate(200000, seed=23, style=synth.STYLE_PE_BOWTIE2)
     open(tmp_path / "p.sam", "wb").write(synth.HEADER_PRIMARY.encode() + bytes(p))

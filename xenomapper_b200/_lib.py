@@ -16,13 +16,15 @@ MODE_SE, MODE_PE_LIBERAL, MODE_PE_CONSERVATIVE = 0, 1, 2
 SCORE_AS_XS, SCORE_AS_ZS, SCORE_CIGAR_NM = 0, 1, 2
 (XM_OK, XM_ERR_ASSERT, XM_ERR_VALUE, XM_ERR_RUNTIME, XM_ERR_UNICODE, XM_ERR_UNSUPPORTED,
  XM_ERR_NOMEM, XM_ERR_CUDA, XM_ERR_ARG, XM_ERR_IO) = range(10)
-DEBUG_FORCE_GENERIC, DEBUG_SMALL_TILES = 1, 2
+DEBUG_FORCE_GENERIC, DEBUG_SMALL_TILES, DEBUG_ROWS = 1, 2, 4
 
 EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_classify_device",
            "xm_classify_host", "xm_get_output", "xm_classify_fds", "xm_count_device", "xm_dev_alloc",
            "xm_dev_free", "xm_host_alloc_pinned", "xm_host_free_pinned", "xm_memcpy_h2d", "xm_memcpy_d2h",
            "xm_memcpy_d2d", "xm_dev_mem_info", "xm_set_debug", "xm_locate_device", "xm_classify_bam_host",
-           "xm_bam_header_text", "xm_bam_render_host", "xm_bam_get_stats", "xm_get_walk_kernels")
+           "xm_bam_header_text", "xm_bam_render_host", "xm_bam_get_stats", "xm_get_walk_kernels",
+           "xm_comm_unique_id", "xm_comm_init_rank", "xm_comm_destroy", "xm_comm_barrier", "xm_comm_allreduce_f64",
+           "xm_classify_sharded_device", "xm_classify_sharded_host")
 
 
 class Opts(C.Structure):
@@ -34,12 +36,21 @@ class Result(C.Structure):
     _fields_ = [("counts", C.c_uint64 * 36), ("n_records", C.c_uint64), ("out_len", C.c_uint64 * 6),
                 ("bytes_in", C.c_uint64 * 2), ("status", C.c_int32), ("err_stream", C.c_int32),
                 ("err_record", C.c_uint64), ("ms_scan", C.c_float), ("ms_classify", C.c_float),
-                ("ms_total", C.c_float), ("n_launches", C.c_uint32)]
+                ("ms_total", C.c_float), ("n_launches", C.c_uint32),
+                ("ms_kernel", C.c_float * 6), ("reserved", C.c_uint32 * 2)]
 
 
 class ShardInfo(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("first_start", C.c_uint64), ("stop_at", C.c_uint64),
                 ("end_off", C.c_uint64)]
+
+
+class ShardStats(C.Structure):
+    _fields_ = [("rec_lo", C.c_uint64), ("rec_hi", C.c_uint64), ("n_records_total", C.c_uint64),
+                ("out_offset", C.c_uint64 * 6), ("out_total", C.c_uint64 * 6), ("sliver_bytes", C.c_uint64),
+                ("sent_bytes", C.c_uint64), ("align_ms", C.c_float), ("index_ms", C.c_float), ("sliver_ms", C.c_float),
+                ("walk_ms", C.c_float), ("comm_ms", C.c_float), ("total_ms", C.c_float), ("n_collectives", C.c_uint32),
+                ("first_bad_rank", C.c_int32)]
 
 
 class BamStats(C.Structure):
@@ -95,6 +106,14 @@ def load():
     L.xm_bam_render_host.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
     L.xm_bam_get_stats.argtypes = [vp, C.POINTER(BamStats), i]
     L.xm_get_walk_kernels.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.xm_comm_unique_id.argtypes = [vp]
+    L.xm_comm_init_rank.argtypes = [vp, i, i, vp]
+    L.xm_comm_destroy.argtypes = [vp]
+    L.xm_comm_barrier.argtypes = [vp]
+    L.xm_comm_allreduce_f64.argtypes = [vp, C.POINTER(C.c_double), i, i]
+    L.xm_classify_sharded_device.argtypes = [vp, vp, u64, vp, u64, u64, u64, C.POINTER(Opts), C.POINTER(vp), C.POINTER(u64),
+                                             C.POINTER(Result), C.POINTER(ShardStats)]
+    L.xm_classify_sharded_host.argtypes = [vp, vp, u64, vp, u64, C.POINTER(Opts), C.POINTER(Result), C.POINTER(ShardStats)]
     for name in EXPORTS:
         if name not in ("xm_create", "xm_destroy", "xm_last_error", "xm_abi_version"):
             getattr(L, name).restype = i
@@ -209,6 +228,55 @@ class Context:
         del pk, sk
         return rc, res, outs
 
+    # ---- the walk across GPUs: one process per GPU, NCCL inside the library ------
+    @staticmethod
+    def comm_unique_id():
+        """128 opaque bytes made by rank 0; the launcher hands them to every rank (comm_init_rank)"""
+        buf = C.create_string_buffer(128)
+        L = load()
+        if L.xm_comm_unique_id(buf) != XM_OK:
+            raise XenomapperLibraryError("xm_comm_unique_id failed: " + L.xm_last_error(None).decode())
+        return buf.raw
+
+    def comm_init_rank(self, nranks, rank, unique_id=None):
+        buf = C.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
+        self._check(self.lib.xm_comm_init_rank(self.h, nranks, rank, buf), "xm_comm_init_rank")
+
+    def comm_barrier(self):
+        self._check(self.lib.xm_comm_barrier(self.h), "xm_comm_barrier")
+
+    def comm_allreduce(self, values, op="sum"):
+        arr = (C.c_double * len(values))(*values)
+        self._check(self.lib.xm_comm_allreduce_f64(self.h, arr, len(values), 1 if op == "max" else 0), "xm_comm_allreduce_f64")
+        return list(arr)
+
+    def classify_sharded_host(self, prim, sec, opts, want_outputs=True):
+        """prim / sec: this rank's BYTE shards of the two record regions (bytes-like).  Returns (rc, Result with the
+        whole job's counts, ShardStats with this rank's place in the six bins, this rank's six outputs)."""
+        pa, pn, pk = _host_ptr(prim)
+        sa, sn, sk = _host_ptr(sec)
+        res, st = Result(), ShardStats()
+        rc = self.lib.xm_classify_sharded_host(self.h, pa, pn, sa, sn, C.byref(opts), C.byref(res), C.byref(st))
+        self._check(rc, "xm_classify_sharded_host")
+        outs = None
+        if want_outputs:
+            outs = []
+            for b in range(6):
+                p, n = C.c_void_p(), C.c_uint64()
+                self.lib.xm_get_output(self.h, b, C.byref(p), C.byref(n))
+                outs.append(C.string_at(p.value, n.value) if n.value else b"")
+        del pk, sk
+        return rc, res, st, outs
+
+    def classify_sharded_device(self, d_prim, prim_len, d_sec, sec_len, front_room, back_room, opts, d_out, out_cap):
+        res, st = Result(), ShardStats()
+        outp = (C.c_void_p * 6)(*d_out)
+        caps = (C.c_uint64 * 6)(*out_cap)
+        rc = self.lib.xm_classify_sharded_device(self.h, d_prim, prim_len, d_sec, sec_len, front_room, back_room, C.byref(opts),
+                                                 outp, caps, C.byref(res), C.byref(st))
+        self._check(rc, "xm_classify_sharded_device")
+        return rc, res, st
+
     def classify_bam_host(self, prim_bam, sec_bam, opts, want_outputs=True):
         """prim_bam / sec_bam: bytes-like BAM files (BGZF): inflated on the host, rendered and walked on the device"""
         pa, pn, pk = _host_ptr(prim_bam)
@@ -241,7 +309,7 @@ class Context:
         """names of the kernels the last resident walk ran"""
         m = C.c_uint32()
         self.lib.xm_get_walk_kernels(self.h, C.byref(m))
-        return [n for b, n in enumerate(("k_scan2", "k_classify2", "k_scan", "k_classify")) if (m.value >> b) & 1]
+        return [n for b, n in enumerate(("k_scan2", "k_classify2", "k_scan", "k_classify", "k_size+k_prefix+k_emit")) if (m.value >> b) & 1]
 
     def bam_stats(self, reset=True):
         st = BamStats()

@@ -24,6 +24,8 @@
 #include "xm_walk.h"
 #include "xm_stream.h"
 #include "xm_bam.h"
+#include "xm_shard.h"
+#include "xm_nccl.h"
 
 using namespace xm;
 
@@ -36,7 +38,7 @@ struct DeviceBackend {
     int upload(void *d, const void *h, size_t n) { const int k = up_next; up_next ^= 1; return chk(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, up[k])); }
     int upload_wait() { return chk(cudaStreamSynchronize(up[0])) || chk(cudaStreamSynchronize(up[1])); }
     int copy_dd(void *d, const void *s, size_t n) { return chk(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st)) || chk(cudaStreamSynchronize(st)); }
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int chk(cudaError_t e)
     {
@@ -77,6 +79,11 @@ struct DeviceBackend {
         if (off) return -1;
         return chk(launch_classify2(a, st));
     }
+    bool rows_enabled() { return true; }           /* the walk over rows (xm_emit.cuh), chosen with XM_DEBUG_ROWS */
+    int size(const EmitArgs &a) { return chk(launch_size(a, st)); }
+    int prefix(const EmitArgs &a) { return chk(launch_prefix(a, st)); }
+    int emit(const EmitArgs &a) { return chk(launch_emit(a, st)); }
+    int add64(void *p, uint64_t n, unsigned long long d) { return chk(launch_add_u64((unsigned long long *)p, d, n, st)) || chk(cudaStreamSynchronize(st)); }
     uint64_t scan2_tiles(uint64_t len) { const uint64_t t = scan2_tile_bytes(); return (len + t - 1) / t; }
     int classify(const ClassifyArgs &a, bool small) { return chk(launch_classify(a, small, st)); }
 };
@@ -88,6 +95,65 @@ struct DevBuf {
 struct HostBuf {
     uint8_t *p = nullptr;
     uint64_t cap = 0, len = 0;
+};
+
+/* the Comm of xm_shard.h over NCCL: small host vectors travel through a device staging buffer */
+struct NcclComm_ {
+    NcclComm comm = nullptr;
+    int nranks = 1, my = 0;
+    cudaStream_t st = nullptr;
+    uint8_t *d_stage = nullptr;       /* [send | recv * nranks] */
+    size_t stage_cap = 0;
+    std::string err;
+    int rank() const { return my; }
+    int size() const { return nranks; }
+    std::string last_error() const { return err; }
+    int ck(int r, const char *what)
+    {
+        if (r == 0) return 0;
+        const char *m = nccl_api().GetErrorString ? nccl_api().GetErrorString(r) : "?";
+        err = std::string(what) + ": " + m;
+        return 1;
+    }
+    int cu(cudaError_t e, const char *what)
+    {
+        if (e == cudaSuccess) return 0;
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return 1;
+    }
+    int stage(size_t bytes)
+    {
+        const size_t need = bytes * ((size_t)nranks + 1) + 256;
+        if (need <= stage_cap) return 0;
+        if (d_stage) cudaFree(d_stage);
+        d_stage = nullptr; stage_cap = 0;
+        if (cu(cudaMalloc((void **)&d_stage, need), "cudaMalloc")) return 1;
+        stage_cap = need;
+        return 0;
+    }
+    int all_gather(const void *send, void *recv, size_t bytes)
+    {
+        if (nranks == 1) { memcpy(recv, send, bytes); return 0; }
+        if (!comm) { err = "no communicator: call xm_comm_init_rank first"; return 1; }
+        if (stage(bytes)) return 1;
+        uint8_t *ds = d_stage, *dr = d_stage + ((bytes + 15) & ~(size_t)15);
+        if (cu(cudaMemcpyAsync(ds, send, bytes, cudaMemcpyHostToDevice, st), "H2D copy")) return 1;
+        if (ck(nccl_api().AllGather(ds, dr, bytes, NCCL_UINT8, comm, st), "ncclAllGather")) return 1;
+        if (cu(cudaMemcpyAsync(recv, dr, bytes * (size_t)nranks, cudaMemcpyDeviceToHost, st), "D2H copy")) return 1;
+        return cu(cudaStreamSynchronize(st), "all-gather");
+    }
+    int exchange(const Xfer *sends, int ns, const Xfer *recvs, int nr)
+    {
+        if (nranks == 1) return (ns || nr) ? (err = "exchange with one rank", 1) : 0;
+        if (!comm) { err = "no communicator: call xm_comm_init_rank first"; return 1; }
+        NcclApi &A = nccl_api();
+        if (ck(A.GroupStart(), "ncclGroupStart")) return 1;
+        int bad = 0;
+        for (int k = 0; k < ns && !bad; ++k) bad = ck(A.Send(sends[k].ptr, (size_t)sends[k].bytes, NCCL_UINT8, sends[k].peer, comm, st), "ncclSend");
+        for (int k = 0; k < nr && !bad; ++k) bad = ck(A.Recv(recvs[k].ptr, (size_t)recvs[k].bytes, NCCL_UINT8, recvs[k].peer, comm, st), "ncclRecv");
+        if (ck(A.GroupEnd(), "ncclGroupEnd") || bad) return 1;
+        return cu(cudaStreamSynchronize(st), "send/receive group");
+    }
 };
 
 struct xm_ctx {
@@ -112,6 +178,10 @@ struct xm_ctx {
     DevBuf d_bam[2], d_bam_rec[2], d_bam_ref[2], d_bam_len[2], d_bam_sum[2], d_bam_text[2];
     std::vector<uint8_t> bam_text_host;
     xm_bam_stats bam_stats{};
+    /* the walk across GPUs (xm_shard.h): communicator, row scratch, shard staging of the host entry point */
+    NcclComm_ comm;
+    ShardScratch shard;
+    DevBuf d_shard[2];
 };
 
 static int fail(xm_ctx *c, int code, const std::string &msg)
@@ -173,8 +243,9 @@ xm_ctx *xm_create(int device, uint32_t flags)
         delete c;
         return nullptr;
     }
-    for (int k = 0; k < 4; ++k) cudaEventCreate(&c->be.ev[k]);
+    for (int k = 0; k < 6; ++k) cudaEventCreate(&c->be.ev[k]);
     c->be.up[0] = c->copy_st[0]; c->be.up[1] = c->copy_st[1];
+    xm_set_debug(c, 0);
     return c;
 }
 
@@ -184,6 +255,9 @@ void xm_destroy(xm_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->be.st);
     scratch_release(c->be, c->scratch);
+    shard_release(c->be, c->shard);
+    xm_comm_destroy(c);
+    for (auto &b : c->d_shard) if (b.p) cudaFree(b.p);
     for (auto &s : c->d_in) for (auto &b : s) if (b.p) cudaFree(b.p);
     for (auto &s : c->d_out) for (auto &b : s) if (b.p) cudaFree(b.p);
     for (auto &b : c->h_stage) if (b.p) cudaFreeHost(b.p);
@@ -192,7 +266,7 @@ void xm_destroy(xm_ctx *c)
     for (auto &v : c->bins) for (auto &b : v) cudaFreeHost(b.p);
     for (auto &b : c->pool) cudaFreeHost(b.p);
     if (c->dl) cudaStreamDestroy(c->dl);
-    for (int k = 0; k < 4; ++k) if (c->be.ev[k]) cudaEventDestroy(c->be.ev[k]);
+    for (int k = 0; k < 6; ++k) if (c->be.ev[k]) cudaEventDestroy(c->be.ev[k]);
     if (c->be.st) cudaStreamDestroy(c->be.st);
     for (auto s : c->copy_st) if (s) cudaStreamDestroy(s);
     delete c;
@@ -202,6 +276,9 @@ int xm_set_debug(xm_ctx *c, uint32_t flags)
 {
     if (!c) return XM_ERR_ARG;
     c->debug = flags;
+    /* XM_ROWS=1 in the environment: every context walks over rows (benchmarks of the sharded walk's kernels) */
+    static const bool rows = [] { const char *e = getenv("XM_ROWS"); return e && e[0] == '1'; }();
+    if (rows) c->debug |= DBG_ROWS;
     return XM_OK;
 }
 
@@ -697,6 +774,235 @@ int xm_locate_device(xm_ctx *c, const void *d_buf, uint64_t len, int skip_repeat
     std::string msg;
     const int rc = index_resident(c->be, c->scratch, StreamBuf{(const uint8_t *)d_buf, len}, skip_repeated != 0, c->debug, n_queries, record_index, byte_offset, &info, msg);
     c->err = msg;
+    return rc;
+}
+
+/* ---- the walk across GPUs (xm_shard.h) ------------------------------------------------------------------------ */
+int xm_comm_unique_id(void *id128)
+{
+    if (!id128) return XM_ERR_ARG;
+    NcclApi &A = nccl_api();
+    if (!A.load()) { g_create_error = A.err; return XM_ERR_CUDA; }
+    NcclId id;
+    const int r = A.GetUniqueId(&id);
+    if (r) { g_create_error = std::string("ncclGetUniqueId: ") + A.GetErrorString(r); return XM_ERR_CUDA; }
+    memcpy(id128, &id, sizeof id);
+    return XM_OK;
+}
+
+int xm_comm_init_rank(xm_ctx *c, int nranks, int rank, const void *id128)
+{
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !id128)) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    xm_comm_destroy(c);
+    c->comm.nranks = nranks; c->comm.my = rank; c->comm.st = c->be.st;
+    if (nranks == 1) return XM_OK;
+    NcclApi &A = nccl_api();
+    if (!A.load()) return fail(c, XM_ERR_CUDA, A.err);
+    NcclId id;
+    memcpy(&id, id128, sizeof id);
+    const int r = A.CommInitRank(&c->comm.comm, nranks, id, rank);
+    if (r) { c->comm.comm = nullptr; c->comm.nranks = 1; c->comm.my = 0; return fail(c, XM_ERR_CUDA, std::string("ncclCommInitRank: ") + A.GetErrorString(r)); }
+    return XM_OK;
+}
+
+int xm_comm_destroy(xm_ctx *c)
+{
+    if (!c) return XM_ERR_ARG;
+    if (c->comm.comm) { cudaStreamSynchronize(c->be.st); nccl_api().CommDestroy(c->comm.comm); c->comm.comm = nullptr; }
+    if (c->comm.d_stage) { cudaFree(c->comm.d_stage); c->comm.d_stage = nullptr; c->comm.stage_cap = 0; }
+    c->comm.nranks = 1; c->comm.my = 0;
+    return XM_OK;
+}
+
+int xm_comm_barrier(xm_ctx *c)
+{
+    if (!c) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (cudaStreamSynchronize(c->be.st) != cudaSuccess) return fail(c, XM_ERR_CUDA, "stream synchronize failed");
+    uint64_t one = 1;
+    std::vector<uint64_t> all((size_t)c->comm.nranks);
+    if (c->comm.all_gather(&one, all.data(), 8)) return fail(c, XM_ERR_CUDA, c->comm.err);
+    return XM_OK;
+}
+
+int xm_comm_allreduce_f64(xm_ctx *c, double *values, int n, int op)
+{
+    if (!c || !values || n < 0) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    std::vector<double> all((size_t)n * (size_t)c->comm.nranks);
+    if (n && c->comm.all_gather(values, all.data(), (size_t)n * 8)) return fail(c, XM_ERR_CUDA, c->comm.err);
+    for (int k = 0; k < n; ++k) {
+        double v = all[(size_t)k];
+        for (int q = 1; q < c->comm.nranks; ++q) { const double w = all[(size_t)q * (size_t)n + (size_t)k]; v = op == 1 ? std::max(v, w) : v + w; }
+        values[k] = v;
+    }
+    return XM_OK;
+}
+
+int xm_classify_sharded_device(xm_ctx *c, void *d_prim, uint64_t prim_len, void *d_sec, uint64_t sec_len, uint64_t front_room,
+                               uint64_t back_room, const xm_opts *opts, void *const d_out[6], const uint64_t out_cap[6],
+                               xm_result *res, xm_shard_stats *stats)
+{
+    if (!c || !opts || !res || !stats) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    c->comm.st = c->be.st;
+    ShardBuf in[2] = {{(uint8_t *)d_prim, prim_len, front_room, back_room}, {(uint8_t *)d_sec, sec_len, front_room, back_room}};
+    uint8_t *o6[6];
+    uint64_t cap6[6];
+    for (int b = 0; b < 6; ++b) { o6[b] = d_out ? (uint8_t *)d_out[b] : nullptr; cap6[b] = (out_cap && o6[b]) ? out_cap[b] : 0; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, c->be.st);
+    std::string msg;
+    int rc = walk_sharded(c->be, c->comm, c->shard, in, *opts, o6, cap6, c->debug, res, stats, msg);
+    cudaEventRecord(e1, c->be.st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    res->ms_total = ms;                     /* device time of the whole call: alignment, scans, exchanges, emit */
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->err = msg;
+    if (rc == XM_SHARD_DECLINED) { rc = XM_ERR_UNSUPPORTED; c->err = "the sharded device walk handles clean SAM only: " + msg; res->status = rc; }
+    return rc;
+}
+
+/* pageable host memory -> device through two pinned blocks, the memcpy of one overlapping the H2D of the other */
+static int upload_shard(xm_ctx *c, uint8_t *d_dst, const uint8_t *src, uint64_t n)
+{
+    const uint64_t blk = 64ull << 20;
+    int rc;
+    for (int k = 0; k < 2; ++k) if ((rc = reserve_host(c, c->h_stage[k], std::min<uint64_t>(blk, n ? n : 1)))) return rc;
+    cudaEvent_t ev[2];
+    cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]);
+    uint64_t done = 0;
+    for (int k = 0; done < n; ++k) {
+        const int b = k & 1;
+        const uint64_t m = std::min<uint64_t>(std::min<uint64_t>(blk, c->h_stage[b].cap), n - done);
+        if (k >= 2) cudaEventSynchronize(ev[b]);
+        memcpy(c->h_stage[b].p, src + done, (size_t)m);
+        cudaMemcpyAsync(d_dst + done, c->h_stage[b].p, (size_t)m, cudaMemcpyHostToDevice, c->copy_st[b]);
+        cudaEventRecord(ev[b], c->copy_st[b]);
+        done += m;
+    }
+    cudaError_t e = cudaStreamSynchronize(c->copy_st[0]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->copy_st[1]);
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    if (e != cudaSuccess) return cuda_fail(c, e, "H2D copy");
+    return XM_OK;
+}
+
+int xm_classify_sharded_host(xm_ctx *c, const void *prim, uint64_t prim_len, const void *sec, uint64_t sec_len,
+                             const xm_opts *opts, xm_result *res, xm_shard_stats *stats)
+{
+    if (!c || !opts || !res || !stats) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    c->comm.st = c->be.st;
+    recycle_bins(c);
+    uint64_t room = 1ull << 20;
+    if (const char *e = getenv("XM_SHARD_ROOM_MB")) { const long long v = atoll(e); if (v > 0) room = (uint64_t)v << 20; }
+    const void *src[2] = {prim, sec};
+    const uint64_t len[2] = {prim_len, sec_len};
+    ShardBuf in[2];
+    int rc;
+    for (int s = 0; s < 2; ++s) {
+        if ((rc = reserve_dev(c, c->d_shard[s], len[s] + 2 * room + 64))) return res->status = rc;
+        in[s] = ShardBuf{c->d_shard[s].p + room, len[s], room, room};
+        if (len[s] && (rc = upload_shard(c, in[s].p, (const uint8_t *)src[s], len[s]))) return res->status = rc;
+    }
+    uint8_t *none[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t nocap[6] = {0, 0, 0, 0, 0, 0};
+    auto alloc_out = [&](const uint64_t *want, uint8_t **ptr, uint64_t *cap) -> int {
+        for (int b = 0; b < 6; ++b) {
+            if (reserve_dev(c, c->d_out[0][b], want[b] + 16)) return 1;
+            ptr[b] = c->d_out[0][b].p; cap[b] = want[b];
+        }
+        return 0;
+    };
+    struct Alloc {
+        decltype(alloc_out) &f;
+        int operator()(const uint64_t *w, uint8_t **p, uint64_t *cp) const { return f(w, p, cp); }
+        explicit operator bool() const { return true; }
+    } al{alloc_out};
+    std::string msg;
+    rc = walk_sharded(c->be, c->comm, c->shard, in, *opts, none, nocap, c->debug, res, stats, msg, al);
+    c->err = msg;
+    if (rc == XM_SHARD_DECLINED) {
+        /* some rank's shard needs the exact kernels: every rank sends its (untouched) bytes to rank 0, which walks the
+         * whole streams alone; the other ranks contribute empty bins */
+        const int W = c->comm.size(), r = c->comm.rank();
+        std::vector<uint64_t> mine = {len[0], len[1]}, all((size_t)2 * (size_t)W);
+        if (c->comm.all_gather(mine.data(), all.data(), 16)) return res->status = fail(c, XM_ERR_CUDA, c->comm.err);
+        for (int s = 0; s < 2; ++s) if (len[s] && (rc = upload_shard(c, in[s].p, (const uint8_t *)src[s], len[s]))) return res->status = rc;
+        uint64_t total[2] = {0, 0};
+        for (int q = 0; q < W; ++q) { total[0] += all[(size_t)2 * q]; total[1] += all[(size_t)2 * q + 1]; }
+        DevBuf whole[2];
+        int alloc_rc = XM_OK;
+        if (r == 0) for (int s = 0; s < 2; ++s) if (!alloc_rc) alloc_rc = reserve_dev(c, whole[s], total[s] + 64);
+        std::vector<uint64_t> ok = {(uint64_t)alloc_rc}, allok((size_t)W);
+        c->comm.all_gather(ok.data(), allok.data(), 8);
+        if (allok[0]) { for (auto &w : whole) if (w.p) cudaFree(w.p); return res->status = fail(c, XM_ERR_NOMEM, "rank 0 cannot hold the whole streams for the exact walk"); }
+        std::vector<Xfer> sends, recvs;
+        for (int s = 0; s < 2; ++s) {
+            if (r > 0 && len[s]) sends.push_back(Xfer{0, in[s].p, len[s]});
+            if (r == 0) {
+                uint64_t at = len[s];
+                if (len[s]) cudaMemcpyAsync(whole[s].p, in[s].p, len[s], cudaMemcpyDeviceToDevice, c->be.st);
+                for (int q = 1; q < W; ++q) { const uint64_t n = all[(size_t)2 * q + s]; if (n) recvs.push_back(Xfer{q, whole[s].p + at, n}); at += n; }
+            }
+        }
+        if ((!sends.empty() || !recvs.empty()) && c->comm.exchange(sends.data(), (int)sends.size(), recvs.data(), (int)recvs.size())) {
+            for (auto &w : whole) if (w.p) cudaFree(w.p);
+            return res->status = fail(c, XM_ERR_CUDA, c->comm.err);
+        }
+        xm_result rr;
+        memset(&rr, 0, sizeof rr);
+        int wrc = XM_OK;
+        std::string wmsg;
+        if (r == 0) {
+            xm_opts o = *opts;
+            o.skip_repeated &= 1;
+            uint8_t *no[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            uint64_t cap[6] = {0, 0, 0, 0, 0, 0};
+            xm_result dry;
+            wrc = walk_resident(c->be, c->scratch, StreamBuf{whole[0].p, total[0]}, StreamBuf{whole[1].p, total[1]}, o, no, cap, c->debug, &dry, wmsg);
+            if (wrc != XM_ERR_CUDA && wrc != XM_ERR_NOMEM) {
+                uint8_t *outs[6];
+                for (int b = 0; b < 6; ++b) {
+                    cap[b] = ((o.enabled_bins >> b) & 1u) ? dry.out_len[b] : 0;
+                    if (reserve_dev(c, c->d_out[0][b], cap[b] + 16)) wrc = XM_ERR_NOMEM;
+                    outs[b] = c->d_out[0][b].p;
+                }
+                if (wrc != XM_ERR_NOMEM) wrc = walk_resident(c->be, c->scratch, StreamBuf{whole[0].p, total[0]}, StreamBuf{whole[1].p, total[1]}, o, outs, cap, c->debug, &rr, wmsg);
+            }
+        }
+        for (auto &w : whole) if (w.p) cudaFree(w.p);
+        /* rank 0's result is everybody's */
+        std::vector<uint64_t> g((size_t)4 + 6 + 36, 0), allg(g.size() * (size_t)W);
+        if (r == 0) {
+            g[0] = (uint64_t)wrc; g[1] = rr.n_records; g[2] = rr.err_record; g[3] = (uint64_t)(int64_t)rr.err_stream;
+            for (int b = 0; b < 6; ++b) g[(size_t)4 + b] = rr.out_len[b];
+            for (int k = 0; k < 36; ++k) g[(size_t)10 + k] = rr.counts[k];
+        }
+        if (c->comm.all_gather(g.data(), allg.data(), g.size() * 8)) return res->status = fail(c, XM_ERR_CUDA, c->comm.err);
+        memset(res, 0, sizeof *res);
+        memset(stats, 0, sizeof *stats);
+        res->status = (int32_t)allg[0]; res->n_records = allg[1]; res->err_record = allg[2]; res->err_stream = (int32_t)(int64_t)allg[3];
+        for (int k = 0; k < 36; ++k) res->counts[k] = allg[(size_t)10 + k];
+        for (int b = 0; b < 6; ++b) { stats->out_total[b] = allg[(size_t)4 + b]; stats->out_offset[b] = r == 0 ? 0 : allg[(size_t)4 + b]; res->out_len[b] = r == 0 ? allg[(size_t)4 + b] : 0; }
+        stats->n_records_total = allg[1]; stats->rec_lo = 0; stats->rec_hi = r == 0 ? allg[1] : 0;
+        stats->first_bad_rank = allg[0] ? 0 : -1;
+        rc = (int)allg[0];
+        c->err = r == 0 ? wmsg : (rc ? "the exact walk on rank 0 failed" : "");
+        if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM) return rc;
+    } else if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM || rc == XM_ERR_ARG) return rc;
+    /* this rank's bins back to host blocks */
+    uint64_t biggest = 4096;
+    for (int b = 0; b < 6; ++b) biggest = std::max<uint64_t>(biggest, res->out_len[b]);
+    c->block_bytes = std::min<uint64_t>(biggest, 256ull << 20);
+    for (int b = 0; b < 6; ++b)
+        if (((opts->enabled_bins >> b) & 1u) && res->out_len[b]) { const int r2 = bin_append_d2h(c, b, c->d_out[0][b].p, res->out_len[b]); if (r2) return r2; }
+    if (cudaStreamSynchronize(c->dl) != cudaSuccess) return fail(c, XM_ERR_CUDA, "D2H copy failed");
     return rc;
 }
 

@@ -49,6 +49,10 @@ enum : uint32_t {
 };
 constexpr uint32_t META_LEN_BITS = 24;
 constexpr uint32_t META_LEN_MASK = (1u << META_LEN_BITS) - 1;
+/* meta bit 30 (row kernels, xm_emit.cuh): this record's QNAME equals the QNAME of the line before it -- the pair
+ * predicate of xm.py:402, decided by the scan where both lines are at hand (hash, then bytes) */
+constexpr uint32_t META_SAME = 1u << 30;
+constexpr uint32_t META_FLAGS = 0x3fu << META_LEN_BITS;
 
 /* error word: (record index << 8) | (code << 2) | (previous-record << 1) | stream; atomicMin keeps the first */
 enum { EC_ASSERT = 1, EC_TEXT = 2, EC_DUP = 3, EC_NUM_AS = 4, EC_NUM_XS = 5 };
@@ -96,6 +100,26 @@ struct ScanArgs {
     int32_t score_src, skip;
     int32_t stream_id;                /* which n_stream / ticket slot this scan owns */
     uint32_t debug;
+    int32_t want_same;                /* mark rows whose QNAME repeats the previous line's (META_SAME): paired walks over rows */
+    int32_t count_only;               /* record counts and row offsets only: the score tokens are not parsed */
+    uint64_t start_bias;              /* added to every row's byte offset (sharded walks: offsets count from the shard allocation's first byte) */
+};
+
+/* The row walk (xm_emit.cuh): both streams have been scanned into compact rows; record i of the walk is row i of
+ * both.  k_size sizes the six bins tile by tile, k_prefix turns the tile totals into bases, k_emit copies. */
+constexpr int EM_WARPS = 8, EM_PER_WARP = 64, EM_TILE = EM_WARPS * EM_PER_WARP;
+struct EmitArgs {
+    StreamBuf P, S;
+    SCompact rp, rs;                  /* rows of the primary / secondary stream, already offset to the walk's record 0 */
+    uint64_t n;                       /* records to walk */
+    int32_t mode, skip, halo;
+    long long thr;
+    uint32_t enabled;
+    Globals *g;
+    unsigned long long *tile_tot;     /* [ntiles][C2_SLOTS]: bytes per bin of each tile, then (k_prefix) where each tile starts */
+    uint32_t ntiles;
+    uint8_t *out[6];
+    uint64_t out_cap[6];
 };
 
 struct ClassifyArgs {
@@ -118,7 +142,7 @@ struct ClassifyArgs {
     uint32_t debug;
 };
 
-constexpr uint32_t DBG_FORCE_GENERIC = 1, DBG_SMALL_TILES = 2;
+constexpr uint32_t DBG_FORCE_GENERIC = 1, DBG_SMALL_TILES = 2, DBG_ROWS = 4;
 
 /* tile geometry: one line per thread */
 template <int TILE_, int HALO_, int THREADS_>

@@ -508,6 +508,7 @@ __device__ void dev_copy_global(uint8_t *dst, const uint8_t *src, uint32_t len)
 }
 }  // namespace xm
 #include "xm_scan2.cuh"
+#include "xm_emit.cuh"
 namespace xm {
 
 /* ---- kernels ------------------------------------------------------------------ */
@@ -562,11 +563,22 @@ cudaError_t launch_classify(const ClassifyArgs &a, bool small, cudaStream_t st)
     return small ? launch_classify_t<CfgSmall>(a, st) : launch_classify_t<CfgBig>(a, st);
 }
 
-/* replicate a block of bytes `times` times back to back (bench workloads) -- plain strided copy */
 __global__ void k_fill_u64(unsigned long long *p, unsigned long long v, size_t n)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
+}
+/* p[i] += d (mod 2^64): received rows are moved to where their text landed (xm_shard.h) */
+__global__ void k_add_u64(unsigned long long *p, unsigned long long d, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += d;
+}
+cudaError_t launch_add_u64(unsigned long long *p, unsigned long long d, size_t n, cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    k_add_u64<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, d, n);
+    return cudaGetLastError();
 }
 cudaError_t launch_fill_u64(unsigned long long *p, unsigned long long v, size_t n, cudaStream_t st)
 {

@@ -229,9 +229,10 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
     const uint32_t tile = blockIdx.x;
     const uint64_t span_lo = ((uint64_t)tile * C::WARPS + (uint64_t)warp) * (uint64_t)C::SPAN;
     const bool skip = a.skip != 0;
+    const bool need_prev = skip || a.want_same != 0;      /* the line before the span's first is looked at (run heads, META_SAME) */
     uint32_t *tbm = s_tbm[warp], *nlm = s_nlm[warp];
     uint16_t *trk = s_trk[warp], *starts = s_start[warp];
-    const SpanInfo si = span_front<C, true>(a.S, span_lo, skip, tbm, nlm, trk, starts);
+    const SpanInfo si = span_front<C, true>(a.S, span_lo, need_prev, tbm, nlm, trk, starts);
     bool bad = si.bad;                                /* this span needs the exact kernel */
     const uint64_t win0 = si.win0;
     const uint32_t wbytes = si.wbytes, j0 = si.j0, nown = si.nown;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
     /* skipping walks also parse the head of the line before the first owned one (lane 0 of the first batch) */
     const WinMasks M_{win, tbm, nlm, trk, wbytes, false};
     const Reader rd_{win, a.S.p, win0, wbytes, a.S.len};
-    const bool ctx = skip && nown > 0 && (win0 + starts[j0]) != 0;
+    const bool ctx = need_prev && nown > 0 && (win0 + starts[j0]) != 0;
     const uint32_t first = ctx ? j0 - 1u : j0;
     const uint32_t nparse = nown + (ctx ? 1u : 0u);
     uint32_t count = 0;                               /* records this span yields */
@@ -283,15 +284,17 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
         prev_qlen = __shfl_sync(0xffffffffu, L.qlen, 31); prev_h1 = __shfl_sync(0xffffffffu, L.h1, 31);
         prev_h2 = __shfl_sync(0xffffffffu, L.h2, 31); prev_qs = __shfl_sync(0xffffffffu, L.qs, 31);
         bool yield = mine && !(ctx && k == 0);
-        if (yield && skip && (k > 0)) {
-            if (pq == L.qlen && p1 == L.h1 && p2 == L.h2 && names_equal(rd_, win0 + ps, pq, win0 + L.qs, L.qlen)) yield = false;
+        bool same = false;
+        if (yield && need_prev && (k > 0)) {
+            if (pq == L.qlen && p1 == L.h1 && p2 == L.h2 && names_equal(rd_, win0 + ps, pq, win0 + L.qs, L.qlen)) same = true;
         }
+        if (skip && same) yield = false;
         const uint32_t ym = __ballot_sync(0xffffffffu, yield);
         if (yield) rank[b] = count + (uint32_t)__popc(ym & ((1u << lane) - 1u));
         count += (uint32_t)__popc(ym);
         Rrec[b] = make_uint4((uint32_t)L.as, (uint32_t)L.xs, L.h1, L.h2);
         Rs[b] = L.s;
-        Rmeta[b] = (L.outlen & META_LEN_MASK) | ((L.flags & 0x3fu) << META_LEN_BITS);
+        Rmeta[b] = (L.outlen & META_LEN_MASK) | ((L.flags & 0x3fu) << META_LEN_BITS) | (same ? META_SAME : 0u);
     }
     if (bad) { count = 0; if (lane == 0) a.g->pad = 1u; }      /* Globals::pad doubles as the fallback flag */
 
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
          * before this one have long published theirs */
         if (threadIdx.x == 0) dev_publish1(a.chain1, tile, total, false);
     }
-    if (!bad) {
+    if (!bad && !a.count_only) {
 #pragma unroll
         for (int b = 0; b < MAXB; ++b) {
             const uint32_t k = (uint32_t)(32 * b + lane);
@@ -332,9 +335,8 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
             if (rank[b] == NOT_YIELDED) continue;
             const unsigned long long gi = base + rank[b];
             if (gi < a.sc_cap) {
-                a.sc.start[gi] = win0 + Rs[b];
-                a.sc.rec[gi] = Rrec[b];
-                a.sc.meta[gi] = Rmeta[b];
+                a.sc.start[gi] = a.start_bias + win0 + Rs[b];
+                if (!a.count_only) { a.sc.rec[gi] = Rrec[b]; a.sc.meta[gi] = Rmeta[b]; }
             }
         }
     }
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
         const unsigned long long n = s_base[0] + total;
         a.g->n_stream[a.stream_id] = n;
         a.g->end_off[a.stream_id] = a.S.len;
-        if (a.sc.start && n <= a.sc_cap) a.sc.start[n] = a.S.len;
+        if (a.sc.start && n <= a.sc_cap) a.sc.start[n] = a.start_bias + a.S.len;
     }
 }
 

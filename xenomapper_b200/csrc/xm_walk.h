@@ -22,6 +22,7 @@
 #pragma once
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -152,7 +153,13 @@ struct Scratch {
     uint64_t *p_start = nullptr;       /* chunked walks: byte offset of every yielded primary record */
     uint64_t p_start_cap = 0;
     Globals *g = nullptr;
-    uint32_t last_kernels = 0;       /* bit 0 k_scan2, bit 1 k_classify2, bit 2 k_scan, bit 3 k_classify ran in the last resident walk */
+    uint32_t last_kernels = 0;       /* bit 0 k_scan2, bit 1 k_classify2, bit 2 k_scan, bit 3 k_classify, bit 4 the row kernels ran in the last resident walk */
+    /* the walk over rows (xm_emit.cuh): rows of the primary stream, per-tile bin totals */
+    SCompact scp{nullptr, nullptr, nullptr};
+    uint64_t scp_cap = 0;
+    unsigned long long *tile_tot = nullptr;
+    uint64_t cap_tot = 0;
+    double line_bytes[2] = {0, 0};   /* mean bytes per record of the last walk's streams: sizes the row arrays of the next one */
 };
 
 template <class BE>
@@ -161,6 +168,7 @@ inline void scratch_release(BE &be, Scratch &s)
     be.release(s.chain1_s); be.release(s.chain1_p); be.release(s.chain2);
     be.release(s.sc.start); be.release(s.sc.rec); be.release(s.sc.meta);
     be.release(s.g); be.release(s.p_start);
+    be.release(s.scp.start); be.release(s.scp.rec); be.release(s.scp.meta); be.release(s.tile_tot);
     s = Scratch();
 }
 
@@ -189,6 +197,44 @@ inline bool scratch_reserve(BE &be, Scratch &s, uint64_t tiles_s, uint64_t tiles
         if (!s.sc.start || !s.sc.rec || !s.sc.meta) { s.sc_cap = 0; return false; }
         s.sc_cap = sc_cap;
     }
+    return true;
+}
+
+/* rows of the primary stream and tile totals of the row walk */
+template <class BE>
+inline bool scratch_reserve_rows(BE &be, Scratch &s, uint64_t scp_cap, uint64_t tiles)
+{
+    if (scp_cap > s.scp_cap) {
+        be.release(s.scp.start); be.release(s.scp.rec); be.release(s.scp.meta);
+        s.scp.start = (uint64_t *)be.alloc((scp_cap + 1) * 8);
+        s.scp.rec = (uint4 *)be.alloc(scp_cap * 16 + 16);
+        s.scp.meta = (uint32_t *)be.alloc(scp_cap * 4 + 16);
+        if (!s.scp.start || !s.scp.rec || !s.scp.meta) { s.scp_cap = 0; return false; }
+        s.scp_cap = scp_cap;
+    }
+    if (tiles > s.cap_tot) {
+        be.release(s.tile_tot);
+        s.tile_tot = (unsigned long long *)be.alloc(tiles * 8 * C2_SLOTS);
+        if (!s.tile_tot) { s.cap_tot = 0; return false; }
+        s.cap_tot = tiles;
+    }
+    return true;
+}
+
+/* records a stream of `len` bytes is expected to hold: from the previous walk's density, else from the first 256 KiB */
+template <class BE>
+inline bool estimate_records(BE &be, Scratch &sc, int k, const StreamBuf &B, uint64_t &need)
+{
+    double mean = sc.line_bytes[k];
+    if (mean <= 0) {
+        const size_t n = (size_t)(B.len < (256u << 10) ? B.len : (256u << 10));
+        std::vector<char> smp(n);
+        if (be.read(smp.data(), B.p, n)) return false;
+        uint64_t nl = 0;
+        for (size_t q = 0; q < n; q++) nl += smp[q] == '\n';
+        mean = nl ? (double)n / (double)nl : (double)n;
+    }
+    need = (uint64_t)((double)B.len / mean * 1.05) + 4096;
     return true;
 }
 
@@ -261,26 +307,20 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
     uint64_t limit = ~0ull;
     uint64_t sc_need = 0;
     Globals G;
-    bool no_scan2 = false, no_cls2 = false;
+    bool no_scan2 = false, no_cls2 = false, no_rows = false, rows_walk = false;
+    uint64_t scp_need = 0;
     int code_first = 0;
     unsigned long long err_first = NO_ERROR;
     for (int attempt = 0; attempt < 6; ++attempt) {
         const uint64_t tile = small ? (uint64_t)CfgSmall::TILE : (uint64_t)CfgBig::TILE;
         const uint64_t nt_s = (S.len + tile - 1) / tile, nt_p = (P.len + tile - 1) / tile;
         if (nt_s > 0xffffffffull || nt_p > 0xffffffffull) { errmsg = "stream too large for one call"; return res->status = XM_ERR_ARG; }
-        if (!sc_need) {
-            /* size the per-record arrays from the mean line length of the first 256 KiB */
-            const size_t n = (size_t)(S.len < (256u << 10) ? S.len : (256u << 10));
-            std::vector<char> smp(n);
-            if (be.read(smp.data(), S.p, n)) { errmsg = "sample read failed"; return res->status = XM_ERR_CUDA; }
-            uint64_t nl = 0;
-            for (size_t k = 0; k < n; k++) nl += smp[k] == '\n';
-            const double mean = nl ? (double)n / (double)nl : (double)n;
-            sc_need = (uint64_t)((double)S.len / mean * 1.05) + 4096;
-        }
+        if (!sc_need && !estimate_records(be, sc, 1, S, sc_need)) { errmsg = "sample read failed"; return res->status = XM_ERR_CUDA; }
         const uint64_t nt_s2 = small ? 0 : be.scan2_tiles(S.len);               /* the barrier-free scan has its own tiling */
         const uint64_t nt_sc = nt_s > nt_s2 ? nt_s : nt_s2;
-        if (!scratch_reserve(be, sc, nt_sc, nt_p, sc_need)) { errmsg = "out of device memory for scratch"; return res->status = XM_ERR_NOMEM; }
+        const uint64_t nt_p2 = small ? 0 : be.scan2_tiles(P.len);               /* the row walk scans the primary stream with it too */
+        const uint64_t nt_pc = nt_p > nt_p2 ? nt_p : nt_p2;
+        if (!scratch_reserve(be, sc, nt_sc, nt_pc, sc_need)) { errmsg = "out of device memory for scratch"; return res->status = XM_ERR_NOMEM; }
         if (ctl && ctl->want_tail && sc.p_start_cap < sc.sc_cap) {
             be.release(sc.p_start);
             sc.p_start = (uint64_t *)be.alloc(sc.sc_cap * 8 + 16);
@@ -292,7 +332,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         init.err = NO_ERROR;
         init.limit_off = ~0ull;
         be.tick(0);                                  /* the step starts here: scratch init is part of it */
-        if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_sc * 8) || be.zero(sc.chain1_p, nt_p * 8) ||
+        if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_sc * 8) || be.zero(sc.chain1_p, nt_pc * 8) ||
             be.zero(sc.chain2, nt_p * 8 * C2_SLOTS)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
 
         ScanArgs sa;
@@ -307,6 +347,65 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         for (int b = 0; b < 6; ++b) { ca.out[b] = out[b]; ca.out_cap[b] = ((ca.enabled >> b) & 1u) ? out_cap[b] : 0; }
         if (ctl) { ca.halo = ctl->halo; if (ctl->want_tail) { ca.p_start = sc.p_start; ca.p_start_cap = sc.p_start_cap; } }
 
+        /* ---- the walk over rows (xm_emit.cuh): both streams scanned into rows, then size / prefix / emit --------
+         * Clean, error-free inputs only: a span or a row that needs the exact kernels raises Globals::pad and the
+         * attempt starts over on the exact pair. */
+        if (!small && !(debug & DBG_FORCE_GENERIC) && (debug & DBG_ROWS) && !no_rows && limit == ~0ull && be.rows_enabled()) {
+            if (!scp_need && !estimate_records(be, sc, 0, P, scp_need)) { errmsg = "sample read failed"; return res->status = XM_ERR_CUDA; }
+            {
+                const uint64_t rows_p = scp_need > sc.scp_cap ? scp_need : sc.scp_cap;
+                const uint64_t rec_bound = sc.sc_cap < rows_p ? sc.sc_cap : rows_p;         /* the walk yields min(records of both streams) */
+                if (!scratch_reserve_rows(be, sc, scp_need, (rec_bound + EM_TILE - 1) / EM_TILE + 1)) { errmsg = "out of device memory for scratch"; return res->status = XM_ERR_NOMEM; }
+            }
+            ScanArgs s2 = sa;
+            s2.sc = sc.sc; s2.sc_cap = sc.sc_cap;
+            ScanArgs p2 = sa;
+            p2.S = P; p2.sc = sc.scp; p2.sc_cap = sc.scp_cap; p2.chain1 = sc.chain1_p; p2.stream_id = 0;
+            p2.want_same = (o.mode != MODE_SE && !sa.skip) ? 1 : 0;
+            be.tick(3);
+            int r2 = be.scan2(s2);
+            be.tick(4);
+            if (r2 == 0) r2 = be.scan2(p2);
+            if (r2 > 0) { errmsg = "scan kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            if (r2 == 0) {
+                be.tick(1);
+                if (be.read(&G, sc.g, sizeof G)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+                res->n_launches += 2;
+                if (G.pad) { no_rows = true; continue; }
+                if (G.n_stream[1] > sc.sc_cap) { sc_need = G.n_stream[1] + 1; continue; }
+                if (G.n_stream[0] > sc.scp_cap) { scp_need = G.n_stream[0] + 1; continue; }
+                const uint64_t n = G.n_stream[0] < G.n_stream[1] ? G.n_stream[0] : G.n_stream[1];
+                EmitArgs ea;
+                memset(&ea, 0, sizeof ea);
+                ea.P = P; ea.S = S; ea.rp = sc.scp; ea.rs = sc.sc; ea.n = n;
+                ea.mode = o.mode; ea.skip = sa.skip; ea.halo = ctl ? ctl->halo : 0;
+                ea.thr = ca.thr; ea.enabled = ca.enabled; ea.g = sc.g; ea.tile_tot = sc.tile_tot;
+                ea.ntiles = (uint32_t)((n + EM_TILE - 1) / EM_TILE);
+                for (int b = 0; b < 6; ++b) { ea.out[b] = ca.out[b]; ea.out_cap[b] = ca.out_cap[b]; }
+                if ((uint64_t)ea.ntiles > sc.cap_tot) { errmsg = "tile totals not sized"; return res->status = XM_ERR_ARG; }
+                if (be.size(ea)) { errmsg = "size kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+                be.tick(5);
+                if (be.prefix(ea) || be.emit(ea)) { errmsg = "emit kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+                be.tick(2);
+                if (be.read(&G, sc.g, sizeof G)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+                res->n_launches += 3;
+                if (G.pad) { no_rows = true; continue; }
+                sc.last_kernels = 1u | 16u;
+                res->ms_scan = be.elapsed(3, 1); res->ms_classify = be.elapsed(1, 2); res->ms_total += be.elapsed(0, 2);
+                res->ms_kernel[0] = be.elapsed(3, 4); res->ms_kernel[1] = be.elapsed(4, 1); res->ms_kernel[2] = be.elapsed(1, 5); res->ms_kernel[3] = be.elapsed(5, 2);
+                /* what the fused kernels leave in Globals and the code below reads */
+                if (n > 0) {
+                    unsigned long long p0 = 0, p1 = 0;
+                    be.read(&p0, sc.scp.start, 8);
+                    be.read(&p1, sc.scp.start + n, 8);
+                    G.bytes_in[0] = p1 - p0;
+                }
+                rows_walk = true;
+                break;
+            }
+            /* r2 < 0: the backend has no row kernels */
+            if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_sc * 8) || be.zero(sc.chain1_p, nt_pc * 8)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
+        }
         be.tick(3);
         /* clean inputs take the barrier-free scan (xm_scan2.cuh); it says so when a span needs the exact kernel */
         bool scanned = false, have_gs = false;
@@ -399,10 +498,12 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         }
         if (ctl->want_tail && n > 0) {
             unsigned long long v = 0;
-            be.read(&v, sc.p_start + (n - 1), 8); ctl->last_p = v;
+            be.read(&v, (rows_walk ? sc.scp.start : sc.p_start) + (n - 1), 8); ctl->last_p = v;
             be.read(&v, sc.sc.start + (n - 1), 8); ctl->last_s = v;
         }
     }
+    for (int k = 0; k < 2; ++k)
+        if (G.n_stream[k] > 1000 && G.end_off[k] > 0) sc.line_bytes[k] = (double)G.end_off[k] / (double)G.n_stream[k];
     for (int k = 0; k < 36; ++k) res->counts[k] = G.counts[k];
     for (int b = 0; b < 6; ++b) res->out_len[b] = G.out_len[b];
     res->bytes_in[0] = G.bytes_in[0];

@@ -427,7 +427,7 @@ def main(argv=None):
     skip = not args.paired                       # xm.py:691
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         if not args.primary_sam:
-            raise NotImplementedError("the sharded walk (torchrun, one process per GPU) takes SAM inputs")
+            raise NotImplementedError("the sharded walk (one process per GPU) takes SAM inputs")
         return _main_sharded(args, tag_func, outs, skip)
     if args.primary_sam:
         process_headers(args.primary_sam, args.secondary_sam, **outs)
@@ -444,26 +444,22 @@ def main(argv=None):
 
 
 def _main_sharded(args, tag_func, outs, skip):
-    """`torchrun --nproc-per-node N -m xenomapper_b200.xenomapper ...`: one process per GPU, each walks its
-    record-index shard (xenomapper_b200/sharded.py); outputs must be regular files (every rank writes its part
-    of each bin in place behind the header)."""
-    import torch
-    import torch.distributed as dist
+    """`torchrun --nproc-per-node N -m xenomapper_b200.xenomapper ...` (or any launcher that sets RANK, WORLD_SIZE
+    and LOCAL_RANK): one process per GPU, each walks the records of its byte shard (xenomapper_b200/sharded.py,
+    csrc/xm_shard.h; NCCL inside the library, no torch here).  Outputs must be regular files: every rank writes
+    its part of each bin in place behind the header."""
+    import json
     from . import sharded
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
-    backend = os.environ.get("XENOMAPPER_DIST_BACKEND", "nccl")
-    if backend == "nccl":
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    else:
-        dist.init_process_group(backend)
     names = list(outs)
     files = [outs[k] for k in names]
     for f in files:
         if f and not os.path.isfile(f.name):
             raise ValueError("sharded walks write their outputs in place: {0} is not a regular file".format(f.name))
-    dist.barrier()                                  # every rank has opened (and truncated) the outputs
+    ctx = _lib.Context(local)
+    rv = sharded.init_comm(ctx, rank, world)
+    ctx.comm_barrier()                              # every rank has opened (and truncated) the outputs
     hdr_len = [0] * 6
     if rank == 0:
         process_headers(args.primary_sam, args.secondary_sam, **outs)
@@ -471,27 +467,28 @@ def _main_sharded(args, tag_func, outs, skip):
             if f:
                 f.flush()
                 hdr_len[b] = os.fstat(f.fileno()).st_size
+        rv.publish("header_len", json.dumps(hdr_len).encode())
     else:
         get_sam_header(args.primary_sam), get_sam_header(args.secondary_sam)
-    t = torch.tensor(hdr_len, dtype=torch.int64, device="cuda" if backend == "nccl" else "cpu")
-    dist.broadcast(t, 0)
-    hdr_len = [int(v) for v in t.cpu().tolist()]
-    prim = sharded.FileSource(args.primary_sam.name, _byte_offset(args.primary_sam))
-    sec = sharded.FileSource(args.secondary_sam.name, _byte_offset(args.secondary_sam))
+        hdr_len = json.loads(rv.fetch("header_len").decode())
     mode = _lib.MODE_SE if not args.paired else (_lib.MODE_PE_CONSERVATIVE if args.conservative else _lib.MODE_PE_LIBERAL)
     enabled = sum(1 << b for b, f in enumerate(files) if f)
-    res = sharded.sharded_walk(sharded.GpuEngine(), prim, sec, mode=mode, score_src=_SCORE_SRC[tag_func], skip=skip,
-                               min_score=args.min_score, enabled_bins=enabled)
+    with open(args.primary_sam.name, "rb") as fp, open(args.secondary_sam.name, "rb") as fs:
+        res = sharded.sharded_walk(ctx, rank, world, fp.fileno(), _byte_offset(args.primary_sam), fs.fileno(),
+                                   _byte_offset(args.secondary_sam), mode=mode, score_src=_SCORE_SRC[tag_func], skip=skip,
+                                   min_score=args.min_score, enabled_bins=enabled)
     sharded.write_outputs(res, [f.fileno() if f else -1 for f in files], hdr_len)
-    dist.barrier()
+    ctx.comm_barrier()
     if rank == 0:
+        rv.cleanup()
+        if res["status"] != _lib.XM_OK:
+            ctx.close()
+            raise RuntimeError("sharded walk failed ({0}): {1}".format(res["status"], res["message"]))
+
         class _R:
             counts = res["counts"]
-        if res["status"] != _lib.XM_OK:
-            dist.destroy_process_group()
-            raise RuntimeError("sharded walk failed ({0}): {1}".format(res["status"], res["message"]))
         output_summary(_counter(_R, mode != _lib.MODE_SE))
-    dist.destroy_process_group()
+    ctx.close()
 
 
 def _byte_offset(textfile):
