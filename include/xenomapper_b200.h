@@ -257,6 +257,11 @@ int xm_memcpy_d2h(xm_ctx *ctx, void *h_dst, const void *d_src, uint64_t bytes);
 int xm_memcpy_d2d(xm_ctx *ctx, void *d_dst, const void *d_src, uint64_t bytes);
 int xm_dev_mem_info(xm_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
 
+/* What the host <-> device link alone can do for a walk that uploads h2d_bytes and brings d2h_bytes back: both
+ * directions at once, pinned memory, 256 MiB pieces, no kernels.  *ms receives the time of one such round (best of
+ * `reps`).  Benchmarks report it next to the end-to-end walk: the distance between the two is what the library adds. */
+int xm_copy_ceiling(xm_ctx *ctx, uint64_t h2d_bytes, uint64_t d2h_bytes, int reps, float *ms);
+
 /* tuning knobs for tests: which tile geometry and parse path the kernels use */
 #define XM_DEBUG_FORCE_GENERIC 1u   /* every line through the exact byte-wise tokeniser */
 #define XM_DEBUG_SMALL_TILES   2u   /* 1 KiB tiles: exercises tile-boundary logic on small inputs */

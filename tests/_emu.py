@@ -51,7 +51,7 @@ def lib():
     if _lib is None:
         if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                                   "-o", SO, SRC])
+                                   "-pthread", "-o", SO, SRC])
         _lib = C.CDLL(SO)
         _lib.xm_emu_classify.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(Opts), C.c_uint32,
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(Result),

@@ -120,10 +120,13 @@ extern "C" int xm_emu_classify_stream(const void *prim, uint64_t plen, const voi
     StreamPlan plan;
     plan.chunk = chunk;
     const uint64_t dcap = 2 * chunk + 64;
-    std::vector<uint8_t> ibuf[2][2], obuf[2][6];
+    std::vector<uint8_t> ibuf[2][2], sbuf[2][2], obuf[2][6];
     DevIn dev[2];
     for (int s = 0; s < 2; ++s) {
-        for (int k = 0; k < 2; ++k) { ibuf[s][k].assign(dcap + 64, 0xEE); dev[s].buf[k] = ibuf[s][k].data(); }
+        for (int k = 0; k < 2; ++k) {
+            ibuf[s][k].assign(dcap + 64, 0xEE); dev[s].buf[k] = ibuf[s][k].data();
+            sbuf[s][k].assign(dcap + 64, 0xEE); dev[s].stage[k] = sbuf[s][k].data();
+        }
         dev[s].cap = dcap;
     }
     uint64_t ocap[6];
@@ -135,6 +138,7 @@ extern "C" int xm_emu_classify_stream(const void *prim, uint64_t plen, const voi
     uint64_t filled[6] = {0, 0, 0, 0, 0, 0};
     bool overflow = false;
     auto emit = [&](int, int b, const uint8_t *src, uint64_t n) {
+        if (b < 0) return;
         if (filled[b] + n > cap[b]) { overflow = true; return; }
         memcpy((uint8_t *)out[b] + filled[b], src, n);
         filled[b] += n;

@@ -24,7 +24,7 @@ EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_cla
            "xm_memcpy_d2d", "xm_dev_mem_info", "xm_set_debug", "xm_locate_device", "xm_classify_bam_host",
            "xm_bam_header_text", "xm_bam_render_host", "xm_bam_get_stats", "xm_get_walk_kernels",
            "xm_comm_unique_id", "xm_comm_init_rank", "xm_comm_destroy", "xm_comm_barrier", "xm_comm_allreduce_f64",
-           "xm_classify_sharded_device", "xm_classify_sharded_host")
+           "xm_classify_sharded_device", "xm_classify_sharded_host", "xm_copy_ceiling")
 
 
 class Opts(C.Structure):
@@ -106,6 +106,7 @@ def load():
     L.xm_bam_render_host.argtypes = [vp, vp, u64, C.POINTER(vp), C.POINTER(u64)]
     L.xm_bam_get_stats.argtypes = [vp, C.POINTER(BamStats), i]
     L.xm_get_walk_kernels.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.xm_copy_ceiling.argtypes = [vp, u64, u64, i, C.POINTER(C.c_float)]
     L.xm_comm_unique_id.argtypes = [vp]
     L.xm_comm_init_rank.argtypes = [vp, i, i, vp]
     L.xm_comm_destroy.argtypes = [vp]
@@ -227,6 +228,12 @@ class Context:
                 outs.append(C.string_at(p.value, n.value) if n.value else b"")
         del pk, sk
         return rc, res, outs
+
+    def copy_ceiling(self, h2d_bytes, d2h_bytes, reps=3):
+        """ms one round of bare pinned copies takes: h2d_bytes up and d2h_bytes down at the same time, no kernels"""
+        ms = C.c_float()
+        self._check(self.lib.xm_copy_ceiling(self.h, h2d_bytes, d2h_bytes, reps, C.byref(ms)), "xm_copy_ceiling")
+        return ms.value
 
     # ---- the walk across GPUs: one process per GPU, NCCL inside the library ------
     @staticmethod

@@ -15,7 +15,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/xenomapper_b200.h"
@@ -164,8 +167,9 @@ struct xm_ctx {
     uint32_t debug = 0;
     std::string err;
     /* host-buffer walk: device staging and outputs, host outputs */
-    DevBuf d_in[2][2], d_out[2][6];     /* chunked walk: two input buffers per stream, two sets of six bin buffers */
-    HostBuf h_stage[2];      /* pinned staging for descriptor sources */
+    DevBuf d_in[2][2], d_stage[2][2], d_out[2][6];     /* chunked walk: two walk and two staging buffers per stream, two sets of six bin buffers */
+    HostBuf h_stage[2];      /* pinned blocks of the shard upload */
+    HostBuf h_ring[2][3];    /* pinned slots descriptor sources are read ahead into */
     cudaStream_t dl = nullptr;          /* D2H lane */
     /* the six bins on the host: pinned blocks filled in order; reused from call to call */
     struct Block { uint8_t *p; uint64_t cap, len; };
@@ -259,6 +263,8 @@ void xm_destroy(xm_ctx *c)
     xm_comm_destroy(c);
     for (auto &b : c->d_shard) if (b.p) cudaFree(b.p);
     for (auto &s : c->d_in) for (auto &b : s) if (b.p) cudaFree(b.p);
+    for (auto &s : c->d_stage) for (auto &b : s) if (b.p) cudaFree(b.p);
+    for (auto &s : c->h_ring) for (auto &b : s) if (b.p) cudaFreeHost(b.p);
     for (auto &s : c->d_out) for (auto &b : s) if (b.p) cudaFree(b.p);
     for (auto &b : c->h_stage) if (b.p) cudaFreeHost(b.p);
     for (auto &b : c->h_bam) if (b.p) cudaFreeHost(b.p);
@@ -445,6 +451,86 @@ static int bin_append_d2h(xm_ctx *c, int b, const uint8_t *d_src, uint64_t n)
     return XM_OK;
 }
 
+/* The bins of a descriptor walk are written by a thread of their own: a step's blocks are queued behind the event
+ * that marks the end of their D2H copies, written with write(2) in bin order, and handed back to the pool. */
+struct BinWriter {
+    struct Job { cudaEvent_t ev; std::vector<std::pair<int, xm_ctx::Block>> blocks; };
+    xm_ctx *c;
+    const int *fds;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<Job> queue;
+    std::vector<xm_ctx::Block> done;        /* written blocks, for the pool */
+    size_t in_flight = 0;
+    bool stop = false;
+    int rc = XM_OK;
+    std::string err;
+    BinWriter(xm_ctx *ctx, const int *out_fds) : c(ctx), fds(out_fds) { th = std::thread([this] { run(); }); }
+    void run()
+    {
+        cudaSetDevice(c->device);
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !queue.empty(); });
+                if (queue.empty()) return;
+                j = std::move(queue.front());
+                queue.erase(queue.begin());
+            }
+            if (cudaEventSynchronize(j.ev) != cudaSuccess && rc == XM_OK) { rc = XM_ERR_CUDA; err = "D2H copy failed"; }
+            cudaEventDestroy(j.ev);
+            for (auto &kb : j.blocks) {
+                uint64_t w0 = 0;
+                const int fd = fds[kb.first];
+                while (rc == XM_OK && fd >= 0 && w0 < kb.second.len) {
+                    const ssize_t w = write(fd, kb.second.p + w0, (size_t)std::min<uint64_t>(kb.second.len - w0, 1u << 30));
+                    if (w < 0) { if (errno == EINTR) continue; rc = XM_ERR_IO; err = std::string("write: ") + strerror(errno); break; }
+                    w0 += (uint64_t)w;
+                }
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                for (auto &kb : j.blocks) { kb.second.len = 0; done.push_back(kb.second); }
+                --in_flight;
+            }
+            cv.notify_all();
+        }
+    }
+    /* the blocks the bins hold now, to be written once the D2H lane has passed this point */
+    void push(cudaStream_t dl)
+    {
+        Job j;
+        cudaEventCreateWithFlags(&j.ev, cudaEventDisableTiming);
+        cudaEventRecord(j.ev, dl);
+        for (int b = 0; b < 6; ++b) { for (auto &k : c->bins[b]) j.blocks.push_back({b, k}); c->bins[b].clear(); }
+        { std::lock_guard<std::mutex> lk(mu); queue.push_back(std::move(j)); ++in_flight; }
+        cv.notify_all();
+    }
+    void reclaim()
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &k : done) c->pool.push_back(k);
+        done.clear();
+    }
+    /* at most `keep` steps' worth of blocks may be waiting for the descriptors */
+    void wait_below(size_t keep)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return in_flight <= keep; });
+    }
+    int finish()
+    {
+        wait_below(0);
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+        reclaim();
+        return rc;
+    }
+};
+
 /* out_fds == nullptr: keep the bins in host blocks (xm_get_output); else append each step's bytes to the descriptors */
 static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opts *opts, xm_result *res)
 {
@@ -458,18 +544,32 @@ static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opt
     DevIn dev[2];
     int rc;
     for (int s = 0; s < 2; ++s) {
-        for (int k = 0; k < 2; ++k) { if ((rc = reserve_dev(c, c->d_in[k][s], cap))) return rc; dev[s].buf[k] = c->d_in[k][s].p; }
-        dev[s].cap = cap;
-        if (!in[s].mem) {
-            if ((rc = reserve_host(c, c->h_stage[s], plan.chunk))) return rc;
-            in[s].stage = c->h_stage[s].p; in[s].stage_cap = plan.chunk;
+        for (int k = 0; k < 2; ++k) {
+            if ((rc = reserve_dev(c, c->d_in[k][s], cap)) || (rc = reserve_dev(c, c->d_stage[k][s], cap))) return rc;
+            dev[s].buf[k] = c->d_in[k][s].p; dev[s].stage[k] = c->d_stage[k][s].p;
         }
+        dev[s].cap = cap;
+    }
+    /* descriptor sources: a reader thread each, three pinned slots of one chunk */
+    FdFeeder feeders[2];
+    for (int s = 0; s < 2; ++s) {
+        if (!in[s].feed) continue;
+        FdFeeder &f = feeders[s];
+        f.fd = in[s].feed->fd; f.off = in[s].feed->off; f.len = in[s].len;
+        f.slot_cap = std::max<uint64_t>(std::min<uint64_t>(plan.chunk, in[s].len + 64), 64);
+        f.ring.resize(3);
+        for (int k = 0; k < 3; ++k) {
+            if ((rc = reserve_host(c, c->h_ring[s][k], f.slot_cap))) return rc;
+            f.ring[(size_t)k].p = c->h_ring[s][k].p;
+        }
+        in[s].feed = &f;
+        f.start();
     }
     uint64_t ocap[6];
     bin_bounds(cap, cap, opts->mode, opts->enabled_bins, ocap);
     uint8_t *outs[2][6];
     for (int k = 0; k < 2; ++k)
-        for (int b = 0; b < 6; ++b) { if ((rc = reserve_dev(c, c->d_out[k][b], ocap[b]))) return rc; outs[k][b] = c->d_out[k][b].p; }
+        for (int b = 0; b < 6; ++b) { if ((rc = reserve_dev(c, c->d_out[k][b], ocap[b]))) { for (auto &f : feeders) f.shutdown(); return rc; } outs[k][b] = c->d_out[k][b].p; }
     /* host blocks: a step's worth per block at most, small inputs get small blocks */
     uint64_t bound[6];
     bin_bounds(in[0].len, in[1].len, opts->mode, opts->enabled_bins, bound);
@@ -479,51 +579,52 @@ static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opt
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, c->be.st);
+    BinWriter *writer = out_fds ? new BinWriter(c, out_fds) : nullptr;
     int emit_rc = XM_OK;
-    auto emit = [&](int, int b, const uint8_t *d_src, uint64_t n) {
+    cudaEvent_t set_done[2];
+    bool set_used[2] = {false, false};
+    for (auto &e : set_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    auto emit = [&](int set, int b, const uint8_t *d_src, uint64_t n) {
         if (emit_rc) return;
+        if (b < 0) {
+            /* the step's D2H copies are all queued: mark the point, and let the writer have the blocks */
+            cudaEventRecord(set_done[set], c->dl);
+            set_used[set] = true;
+            if (writer) writer->push(c->dl);
+            return;
+        }
+        if (writer) writer->reclaim();
         emit_rc = bin_append_d2h(c, b, d_src, n);
     };
-    auto flush_fds = [&]() -> int {
-        /* the descriptors take each step's bytes as soon as they are on the host; blocks are reused */
-        if (cudaStreamSynchronize(c->dl) != cudaSuccess) return fail(c, XM_ERR_CUDA, "D2H copy failed");
-        for (int b = 0; b < 6; ++b) {
-            for (auto &k : c->bins[b]) {
-                uint64_t done = 0;
-                while (out_fds[b] >= 0 && done < k.len) {
-                    const ssize_t w = write(out_fds[b], k.p + done, (size_t)std::min<uint64_t>(k.len - done, 1u << 30));
-                    if (w < 0) { if (errno == EINTR) continue; return fail(c, XM_ERR_IO, std::string("write: ") + strerror(errno)); }
-                    done += (uint64_t)w;
-                }
-                k.len = 0;
-                c->pool.push_back(k);
-            }
-            c->bins[b].clear();
-        }
-        return XM_OK;
-    };
     int wait_rc = XM_OK;
-    auto emit_wait = [&](int) {
+    /* before output set `set` is written again: the D2H copies of the step that used it two steps ago are done (the
+     * copies of the step in between go on), and at most two steps' blocks are waiting for the descriptors */
+    auto emit_wait = [&](int set) {
         if (wait_rc) return;
-        if (out_fds) wait_rc = flush_fds();
-        else if (cudaStreamSynchronize(c->dl) != cudaSuccess) wait_rc = fail(c, XM_ERR_CUDA, "D2H copy failed");
+        if (set_used[set] && cudaEventSynchronize(set_done[set]) != cudaSuccess) wait_rc = fail(c, XM_ERR_CUDA, "D2H copy failed");
+        if (writer) writer->wait_below(2);
     };
     std::string msg;
     xm_opts o = *opts;
     o.skip_repeated &= 1;
     rc = walk_stream(c->be, c->scratch, in, dev, outs, ocap, o, c->debug, plan, emit, emit_wait, res, msg, (opts->skip_repeated >> 1) & 1);
+    for (auto &f : feeders) f.shutdown();
     c->err = msg;
     if (emit_rc) rc = emit_rc;
     if (wait_rc) rc = wait_rc;
-    if (rc != XM_ERR_CUDA && rc != XM_ERR_NOMEM) {
-        if (out_fds) { const int r2 = flush_fds(); if (r2) rc = r2; }
-        else if (cudaStreamSynchronize(c->dl) != cudaSuccess) rc = fail(c, XM_ERR_CUDA, "D2H copy failed");
+    for (auto &e : set_done) cudaEventDestroy(e);
+    if (writer) {
+        const int r2 = writer->finish();
+        if (r2 && (rc == XM_OK || (rc != XM_ERR_CUDA && rc != XM_ERR_NOMEM))) { rc = r2; c->err = writer->err; }
+        delete writer;
+    } else if (rc != XM_ERR_CUDA && rc != XM_ERR_NOMEM) {
+        if (cudaStreamSynchronize(c->dl) != cudaSuccess) rc = fail(c, XM_ERR_CUDA, "D2H copy failed");
     }
     cudaEventRecord(e1, c->be.st);
     cudaEventSynchronize(e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    res->ms_total = ms;                 /* the whole call: staging, kernels, the bins back on the host */
+    res->ms_total = ms;                 /* the whole call: staging, kernels, the bins back on the host (and written) */
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }
@@ -565,12 +666,14 @@ int xm_classify_fds(xm_ctx *c, int fd_prim, int64_t off_prim, int fd_sec, int64_
 {
     if (!c || !opts || !res || !out_fds) return XM_ERR_ARG;
     HostIn in[2];
+    FdFeeder where[2];                  /* descriptor and offset only: stream_walk sets the readers up */
     const int fds[2] = {fd_prim, fd_sec};
     const int64_t offs[2] = {off_prim, off_sec};
     for (int s = 0; s < 2; ++s) {
         const off_t end = lseek(fds[s], 0, SEEK_END);
         if (end < 0) return fail(c, XM_ERR_IO, std::string("input must be seekable: ") + strerror(errno));
-        in[s].fd = fds[s]; in[s].off = offs[s];
+        where[s].fd = fds[s]; where[s].off = offs[s];
+        in[s].feed = &where[s];
         in[s].len = (uint64_t)end > (uint64_t)offs[s] ? (uint64_t)end - (uint64_t)offs[s] : 0;
     }
     xm_opts o = *opts;
@@ -1003,6 +1106,40 @@ int xm_classify_sharded_host(xm_ctx *c, const void *prim, uint64_t prim_len, con
     for (int b = 0; b < 6; ++b)
         if (((opts->enabled_bins >> b) & 1u) && res->out_len[b]) { const int r2 = bin_append_d2h(c, b, c->d_out[0][b].p, res->out_len[b]); if (r2) return r2; }
     if (cudaStreamSynchronize(c->dl) != cudaSuccess) return fail(c, XM_ERR_CUDA, "D2H copy failed");
+    return rc;
+}
+
+int xm_copy_ceiling(xm_ctx *c, uint64_t h2d_bytes, uint64_t d2h_bytes, int reps, float *ms)
+{
+    if (!c || !ms || reps < 1) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    const uint64_t piece = 256ull << 20, span = 1ull << 30;
+    uint8_t *h[2] = {nullptr, nullptr}, *d[2] = {nullptr, nullptr};
+    int rc = XM_OK;
+    for (int k = 0; k < 2 && rc == XM_OK; ++k) {
+        if (cudaHostAlloc((void **)&h[k], span, cudaHostAllocDefault) != cudaSuccess || cudaMalloc((void **)&d[k], span) != cudaSuccess) { cudaGetLastError(); rc = fail(c, XM_ERR_NOMEM, "out of memory for the copy buffers"); }
+        else memset(h[k], 0x41 + k, span);
+    }
+    cudaEvent_t e0[2], e1[2];
+    for (int k = 0; k < 2; ++k) { cudaEventCreate(&e0[k]); cudaEventCreate(&e1[k]); }
+    float best = 0.f;
+    for (int r = 0; r < reps && rc == XM_OK; ++r) {
+        cudaStreamSynchronize(c->copy_st[0]); cudaStreamSynchronize(c->dl);
+        cudaEventRecord(e0[0], c->copy_st[0]); cudaEventRecord(e0[1], c->dl);
+        for (uint64_t at = 0; at < std::max(h2d_bytes, d2h_bytes); at += piece) {
+            const uint64_t o = at % span;
+            if (at < h2d_bytes) cudaMemcpyAsync(d[0] + o, h[0] + o, (size_t)std::min<uint64_t>(piece, h2d_bytes - at), cudaMemcpyHostToDevice, c->copy_st[0]);
+            if (at < d2h_bytes) cudaMemcpyAsync(h[1] + o, d[1] + o, (size_t)std::min<uint64_t>(piece, d2h_bytes - at), cudaMemcpyDeviceToHost, c->dl);
+        }
+        cudaEventRecord(e1[0], c->copy_st[0]); cudaEventRecord(e1[1], c->dl);
+        if (cudaEventSynchronize(e1[0]) != cudaSuccess || cudaEventSynchronize(e1[1]) != cudaSuccess) { rc = fail(c, XM_ERR_CUDA, "copy failed"); break; }
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, e0[0], e1[0]); cudaEventElapsedTime(&b, e0[1], e1[1]);
+        const float t = std::max(a, b);
+        if (r == 0 || t < best) best = t;
+    }
+    for (int k = 0; k < 2; ++k) { cudaEventDestroy(e0[k]); cudaEventDestroy(e1[k]); if (h[k]) cudaFreeHost(h[k]); if (d[k]) cudaFree(d[k]); }
+    *ms = best;
     return rc;
 }
 

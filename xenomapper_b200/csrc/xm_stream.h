@@ -4,13 +4,10 @@
  * appended in order.  This is what replaces the reference's lockstep reader
  * on real files (getReadPairs, xm.py:95-118, driven by main(), xm.py:702-740).
  *
- * Each step stages the next bytes of both streams behind whatever the
- * previous step left unconsumed (the "carry"), runs the resident walk on the
- * two device buffers and hands the bins' new bytes to the sink.
+ * Step k walks two device buffers, each = [carry of step k-1][new bytes]:
  *
- *   - A chunk that is not the end of its stream is cut after its last '\n',
- *     so a step only ever sees complete lines; the cut-off tail is sent again
- *     with the next chunk.
+ *   - New bytes are cut after their last '\n', so a step only ever sees
+ *     complete lines; the cut-off tail is sent again with the next chunk.
  *   - The two streams hold different numbers of records per byte.  A step
  *     yields n = min(records of both buffers); the surplus records of the
  *     longer buffer are carried (device-to-device) to the front of its next
@@ -22,6 +19,14 @@
  *   - The walk ends like the reference's (xm.py:105): at the first blank line
  *     or at the end of either stream.
  *
+ * The host-to-device copy of step k+1 never waits for the kernels of step k:
+ * new bytes go to a staging buffer on the device as soon as the host has them
+ * (their place in the walk buffer depends on the carry, which is only known
+ * when step k is done; moving them there is a device-to-device copy of a
+ * fraction of a millisecond).  Descriptor sources are read ahead by a thread
+ * of their own into a ring of pinned buffers (FdFeeder), so pread, H2D, the
+ * kernels, D2H and the writes of the bins all overlap.
+ *
  * Written against the same Backend interface as xm_walk.h plus
  *     int upload(void *dev_dst, const void *host_src, size_t n)   asynchronous H2D
  *     int upload_wait()
@@ -32,33 +37,15 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "xm_walk.h"
 
 namespace xm {
-
-/* one input stream on the host */
-struct HostIn {
-    const uint8_t *mem = nullptr;      /* memory source (pageable or pinned) ... */
-    uint64_t len = 0;
-    int fd = -1;                       /* ... or a seekable descriptor: bytes [off, off + len) */
-    int64_t off = 0;
-    uint8_t *stage = nullptr;          /* pinned staging for descriptor sources, `stage_cap` bytes */
-    uint64_t stage_cap = 0;
-    uint64_t pos = 0;                  /* next byte to send */
-};
-
-/* device side of one input stream: two buffers used alternately */
-struct DevIn {
-    uint8_t *buf[2] = {nullptr, nullptr};
-    uint64_t cap = 0;
-    uint64_t len = 0;                  /* bytes of the current buffer */
-};
-
-struct StreamPlan {
-    uint64_t chunk = 256ull << 20;     /* new bytes per stream and step */
-};
 
 /* bytes of [p, p + n) up to and including the last '\n', 0 if there is none */
 inline uint64_t cut_after_last_newline(const uint8_t *p, uint64_t n)
@@ -71,10 +58,120 @@ inline uint64_t cut_after_last_newline(const uint8_t *p, uint64_t n)
 int64_t xm_pread_all(int fd, void *dst, uint64_t n, int64_t at);      /* xm_api.cu / the emulation harness */
 
 /*
+ * Reads a descriptor ahead of the walk.  A thread of its own fills a ring of pinned slots; every slot holds whole
+ * lines only (the tail behind a slot's last newline opens the next slot), the last one whatever is left.
+ */
+struct FdFeeder {
+    struct Slot { uint8_t *p = nullptr; uint64_t n = 0, used = 0; bool last = false; int state = 0; /* 0 free, 1 filled, 2 drained (an H2D copy may still read it) */ };
+    int fd = -1;
+    int64_t off = 0;
+    uint64_t len = 0, slot_cap = 0;
+    std::vector<Slot> ring;
+    size_t head = 0;                    /* slot the walk takes from */
+    bool ended = false;                 /* the walk has taken the stream's last byte */
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool stop = false, failed = false, too_long = false;
+
+    void start() { th = std::thread([this] { run(); }); }
+    void run()
+    {
+        uint64_t pos = 0;               /* bytes of the source read so far */
+        std::vector<uint8_t> tail;
+        size_t k = 0;
+        for (;;) {
+            Slot *s;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || ring[k].state == 0; });
+                if (stop) return;
+                s = &ring[k];
+            }
+            uint64_t have = tail.size();
+            if (have) memcpy(s->p, tail.data(), have);
+            tail.clear();
+            const uint64_t want = std::min<uint64_t>(slot_cap - have, len - pos);
+            const int64_t got = want ? xm_pread_all(fd, s->p + have, want, off + (int64_t)pos) : 0;
+            if (got < 0) { std::lock_guard<std::mutex> lk(mu); failed = true; s->n = 0; s->last = true; s->state = 1; cv.notify_all(); return; }
+            if ((uint64_t)got < want) len = pos + (uint64_t)got;                 /* the file is shorter than announced */
+            pos += (uint64_t)got;
+            have += (uint64_t)got;
+            const bool eof = pos >= len;
+            uint64_t n = have;
+            if (!eof) {
+                n = cut_after_last_newline(s->p, have);
+                if (n == 0) { std::lock_guard<std::mutex> lk(mu); too_long = true; s->n = 0; s->last = true; s->state = 1; cv.notify_all(); return; }
+                tail.assign(s->p + n, s->p + have);
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                s->n = n; s->used = 0; s->last = eof; s->state = 1;
+            }
+            cv.notify_all();
+            if (eof) return;
+            k = (k + 1) % ring.size();
+        }
+    }
+    /* the bytes the walk may take next: pointer, count, and whether they are the stream's last */
+    bool peek(const uint8_t *&p, uint64_t &avail, bool &last)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return ring[head].state == 1; });
+        Slot &s = ring[head];
+        p = s.p + s.used; avail = s.n - s.used; last = s.last;
+        return !failed && !too_long;
+    }
+    void consume(uint64_t n)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        Slot &s = ring[head];
+        s.used += n;
+        if (s.used == s.n) {
+            if (s.last) ended = true;
+            else { s.state = 2; head = (head + 1) % ring.size(); }
+        }
+    }
+    /* every upload issued so far has completed: drained slots go back to the reader */
+    void release_drained()
+    {
+        { std::lock_guard<std::mutex> lk(mu); for (auto &s : ring) if (s.state == 2) s.state = 0; }
+        cv.notify_all();
+    }
+    void shutdown()
+    {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+};
+
+/* one input stream on the host */
+struct HostIn {
+    const uint8_t *mem = nullptr;      /* memory source (pageable or pinned) ... */
+    uint64_t len = 0;
+    FdFeeder *feed = nullptr;          /* ... or a descriptor read ahead by its own thread */
+    uint64_t pos = 0;                  /* next byte to send */
+    bool exhausted() const { return feed ? feed->ended : pos >= len; }
+};
+
+/* device side of one input stream: two walk buffers and two staging buffers used alternately */
+struct DevIn {
+    uint8_t *buf[2] = {nullptr, nullptr};
+    uint8_t *stage[2] = {nullptr, nullptr};
+    uint64_t cap = 0;                  /* of each of the four */
+    uint64_t len = 0;                  /* bytes of the current walk buffer */
+};
+
+struct StreamPlan {
+    uint64_t chunk = 256ull << 20;     /* new bytes per stream and step */
+};
+
+/*
  * The chunked walk.  `outs[set][b]` are two sets of six device output buffers of `out_cap[b]` bytes each;
- * `emit(set, bin, dev_ptr, nbytes)` is called for every bin with new bytes after a step and must have consumed
- * (or queued a copy of) them before the same set is written again two steps later -- `emit_wait(set)` is called
- * for that.  Returns an xm_status; *res holds the totals of the whole walk.
+ * `emit(set, bin, dev_ptr, nbytes)` is called for every bin with new bytes after a step, then once with bin -1, and
+ * must have consumed (or queued a copy of) them before the same set is written again two steps later --
+ * `emit_wait(set)` is called for that.  Returns an xm_status; *res holds the totals of the whole walk.
  */
 template <class BE, class Emit, class EmitWait>
 inline int walk_stream(BE &be, Scratch &sc, HostIn in[2], DevIn dev[2], uint8_t *const outs[2][6], const uint64_t out_cap[6],
@@ -83,51 +180,80 @@ inline int walk_stream(BE &be, Scratch &sc, HostIn in[2], DevIn dev[2], uint8_t 
 {
     memset(res, 0, sizeof *res);
     res->err_stream = -1;
-    uint64_t carry_off[2] = {0, 0}, carry_len[2] = {0, 0};      /* in the previous buffer */
+    uint64_t carry_off[2] = {0, 0}, carry_len[2] = {0, 0};      /* in the previous walk buffer */
+    uint64_t staged[2][2] = {{0, 0}, {0, 0}};                   /* [slot][stream]: bytes waiting in the staging buffer */
+    bool staged_final[2][2] = {{false, false}, {false, false}};
     bool final_sent[2] = {false, false};
     int halo = first_is_context ? 1 : 0;                      /* sharded walks: the caller's buffers open with the record before its range */
-    for (uint64_t step = 0;; ++step) {
-        const int cur = (int)(step & 1), prev = cur ^ 1;
-        uint64_t staged = 0;                                   /* new bytes this step, both streams */
-        /* stage: carry to the front, new bytes behind it */
+    int io_rc = XM_OK;
+
+    /* send the next bytes of both streams towards staging buffer `slot`; room[s]: what the next walk buffer can take
+     * behind its carry (the carry is not known yet: the whole of the buffer being walked is allowed for) */
+    auto stage_next = [&](int slot, const uint64_t room[2]) {
         for (int s = 0; s < 2; ++s) {
-            if (carry_len[s] && be.copy_dd(dev[s].buf[cur], dev[s].buf[prev] + carry_off[s], carry_len[s])) { errmsg = "carry copy failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
-            const uint64_t room = dev[s].cap - carry_len[s], remaining = in[s].len - in[s].pos;
-            uint64_t take = std::min<uint64_t>(std::min<uint64_t>(room, plan.chunk), remaining);
+            staged[slot][s] = 0; staged_final[slot][s] = false;
+            if (in[s].exhausted()) continue;
             const uint8_t *src = nullptr;
-            if (take) {
-                if (in[s].mem) src = in[s].mem + in[s].pos;
-                else {
-                    if (take > in[s].stage_cap) take = in[s].stage_cap;
-                    const int64_t got = xm_pread_all(in[s].fd, in[s].stage, take, in[s].off + (int64_t)in[s].pos);
-                    if (got < 0) { errmsg = "read failed"; return res->status = XM_ERR_IO; }
-                    if ((uint64_t)got < take) { in[s].len = in[s].pos + (uint64_t)got; take = (uint64_t)got; }     /* the file is shorter than announced */
-                    src = in[s].stage;
+            uint64_t avail = 0;
+            bool last_piece = false;
+            if (in[s].feed) {
+                if (!in[s].feed->peek(src, avail, last_piece)) {
+                    io_rc = in[s].feed->too_long ? XM_ERR_UNSUPPORTED : XM_ERR_IO;
+                    errmsg = in[s].feed->too_long ? "a line is longer than the staging buffer (" + std::to_string(in[s].feed->slot_cap) + " bytes)" : "read failed";
+                    return;
                 }
+            } else {
+                avail = in[s].len - in[s].pos;
+                src = in[s].mem + in[s].pos;
+                last_piece = true;
             }
-            const bool is_final = in[s].pos + take == in[s].len;
-            if (!is_final) {
+            uint64_t take = std::min<uint64_t>(std::min<uint64_t>(room[s], plan.chunk), avail);
+            if (!(last_piece && take == avail)) {
                 uint64_t cut = cut_after_last_newline(src, take);
-                if (cut == 0 && in[s].mem) {
+                if (cut == 0 && !in[s].feed) {
                     /* a line longer than the chunk: take it whole if the buffer has room for it */
-                    const uint64_t lim = std::min<uint64_t>(room, in[s].len - in[s].pos);
+                    const uint64_t lim = std::min<uint64_t>(room[s], avail);
                     const void *nl = lim > take ? memchr(src + take, '\n', lim - take) : nullptr;
                     if (nl) cut = (uint64_t)((const uint8_t *)nl - src) + 1;
                 }
-                if (cut == 0 && carry_len[s] == 0 && take > 0) {
-                    errmsg = "a line is longer than the staging buffer (" + std::to_string(dev[s].cap) + " bytes)";
-                    return res->status = XM_ERR_UNSUPPORTED;
-                }
                 take = cut;             /* 0: no complete line fits behind the carry this time; the other stream moves on */
             }
-            const bool is_final2 = in[s].pos + take == in[s].len;
-            if (take && be.upload(dev[s].buf[cur] + carry_len[s], src, take)) { errmsg = "H2D copy failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            if (take && be.upload(dev[s].stage[slot], src, take)) { io_rc = XM_ERR_CUDA; errmsg = "H2D copy failed: " + be.last_error(); return; }
+            staged[slot][s] = take;
+            staged_final[slot][s] = last_piece && take == avail;
+            if (in[s].feed) in[s].feed->consume(take);
             in[s].pos += take;
-            staged += take;
-            final_sent[s] = is_final2;
-            dev[s].len = carry_len[s] + take;
         }
+    };
+
+    {
+        const uint64_t room0[2] = {dev[0].cap, dev[1].cap};
+        stage_next(0, room0);
+        if (io_rc) { be.upload_wait(); return res->status = io_rc; }
+    }
+    for (uint64_t step = 0;; ++step) {
+        const int cur = (int)(step & 1), prev = cur ^ 1;
         if (be.upload_wait()) { errmsg = "H2D copy failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+        for (int s = 0; s < 2; ++s) if (in[s].feed) in[s].feed->release_drained();
+        /* this step's buffers: carry to the front, the staged bytes behind it */
+        uint64_t fresh_bytes = 0;
+        for (int s = 0; s < 2; ++s) {
+            if (carry_len[s] && be.copy_dd(dev[s].buf[cur], dev[s].buf[prev] + carry_off[s], carry_len[s])) { errmsg = "carry copy failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            const uint64_t take = staged[cur][s];
+            if (take && be.copy_dd(dev[s].buf[cur] + carry_len[s], dev[s].stage[cur], take)) { errmsg = "staging copy failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            dev[s].len = carry_len[s] + take;
+            fresh_bytes += take;
+            final_sent[s] = final_sent[s] || staged_final[cur][s] || (in[s].len == 0);
+        }
+        /* the next step's bytes leave the host now, while this step's kernels run */
+        uint64_t next_bytes = 0;
+        staged[prev][0] = staged[prev][1] = 0; staged_final[prev][0] = staged_final[prev][1] = false;
+        if (!in[0].exhausted() || !in[1].exhausted()) {
+            const uint64_t room[2] = {dev[0].cap - dev[0].len, dev[1].cap - dev[1].len};
+            stage_next(prev, room);
+            if (io_rc) { be.upload_wait(); return res->status = io_rc; }
+            next_bytes = staged[prev][0] + staged[prev][1];
+        }
         if (step >= 2) emit_wait(cur);
 
         /* walk the two buffers */
@@ -140,7 +266,7 @@ inline int walk_stream(BE &be, Scratch &sc, HostIn in[2], DevIn dev[2], uint8_t 
                                      outs[cur], out_cap, debug, &r, msg, &ctl);
         res->n_launches += r.n_launches;
         res->ms_scan += r.ms_scan; res->ms_classify += r.ms_classify; res->ms_total += r.ms_total;
-        if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM || rc == XM_ERR_ARG) { errmsg = msg; return res->status = rc; }
+        if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM || rc == XM_ERR_ARG) { be.upload_wait(); errmsg = msg; return res->status = rc; }
         const uint64_t n = r.n_records;                              /* includes the halo record */
         const uint64_t fresh = n - (uint64_t)(n ? halo : 0);
         for (int k = 0; k < 36; ++k) res->counts[k] += r.counts[k];
@@ -148,12 +274,14 @@ inline int walk_stream(BE &be, Scratch &sc, HostIn in[2], DevIn dev[2], uint8_t 
             if (r.out_len[b]) emit(cur, b, outs[cur][b], r.out_len[b]);
             res->out_len[b] += r.out_len[b];
         }
+        emit(cur, -1, nullptr, 0);                                   /* the step's bins are all handed over */
         if (rc != XM_OK) {
             /* a failing record: everything before it has been produced (the reference's streaming writes) */
             errmsg = msg;
             res->err_stream = r.err_stream;
             res->err_record = res->n_records + (r.err_record - (uint64_t)halo);
             res->n_records += r.err_record - (uint64_t)halo;
+            be.upload_wait();
             return res->status = rc;
         }
         res->n_records += fresh;
@@ -162,20 +290,22 @@ inline int walk_stream(BE &be, Scratch &sc, HostIn in[2], DevIn dev[2], uint8_t 
         for (int s = 0; s < 2; ++s) {
             const bool drained = ctl.n_stream[s] == n;                   /* every record of this buffer was yielded */
             if (drained && ctl.stopped[s]) done = true;
-            if (drained && final_sent[s] && in[s].pos == in[s].len) done = true;
+            if (drained && final_sent[s]) done = true;
         }
         for (int s = 0; s < 2; ++s) {
             const uint64_t last = s ? ctl.last_s : ctl.last_p;
             if (n > 0) res->bytes_in[s] += done ? (ctl.n_stream[s] == n ? ctl.end_off[s] : last) : last;
         }
-        if (done) break;
+        if (done) { be.upload_wait(); break; }
         if (fresh == 0 && (dev[0].len == dev[0].cap || dev[1].len == dev[1].cap)) {
+            be.upload_wait();
             errmsg = "no complete record fits the staging buffers";
             return res->status = XM_ERR_UNSUPPORTED;
         }
-        if (fresh == 0 && staged == 0) {
-            /* nothing was yielded and nothing new could be staged behind the carry: the next step would be this one
-             * again.  A line that does not fit the staging chunk of a descriptor source ends here. */
+        if (fresh == 0 && fresh_bytes == 0 && next_bytes == 0) {
+            /* nothing was yielded, nothing new was staged and nothing new is on its way: the next step would be this
+             * one again.  A line that does not fit a staging step ends here. */
+            be.upload_wait();
             errmsg = "a line is longer than the staging buffer (" + std::to_string(plan.chunk) + " bytes per step)";
             return res->status = XM_ERR_UNSUPPORTED;
         }
@@ -184,8 +314,7 @@ inline int walk_stream(BE &be, Scratch &sc, HostIn in[2], DevIn dev[2], uint8_t 
             carry_off[0] = ctl.last_p; carry_off[1] = ctl.last_s;
             halo = 1;
         } else {
-            carry_off[0] = carry_off[1] = 0;
-            halo = halo;            /* nothing was yielded: the buffers (halo included) are carried whole */
+            carry_off[0] = carry_off[1] = 0;            /* nothing was yielded: the buffers (halo included) are carried whole */
         }
         for (int s = 0; s < 2; ++s) carry_len[s] = dev[s].len - carry_off[s];
     }
