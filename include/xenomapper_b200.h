@@ -69,7 +69,9 @@ enum xm_status {
     XM_ERR_NOMEM = 6,
     XM_ERR_CUDA = 7,
     XM_ERR_ARG = 8,
-    XM_ERR_IO = 9
+    XM_ERR_IO = 9,
+    XM_ERR_INDEX = 10        /* IndexError of the header functions: an empty or header-only file, an empty header, a trailing @PG
+                                line without an ID (xm.py:40-43, :124-127) */
 };
 
 #define XM_READER_SKIP_REPEATED 1
@@ -165,6 +167,25 @@ int xm_count_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repea
  * the buffer's record count.  With the counts above this turns record-index partition points into byte ranges. */
 int xm_locate_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repeated, uint32_t n_queries,
                      const uint64_t *record_index, uint64_t *byte_offset);
+
+/* ---- headers -------------------------------------------------------------- */
+
+/* process_headers (xm.py:133-174) with get_sam_header (xm.py:36-46) and add_pg_tag (xm.py:120-131) on the raw
+ * bytes of the two SAM files: the leading '@' lines (universal newlines, valid UTF-8), Xenomapper's @PG line chained
+ * with PP: to a trailing @PG line, the @CO comment.  record_offset[k] is the BYTE offset of file k's first record --
+ * what xm_classify_fds takes; no tell()/seek() on a text layer is involved.  text[b] / text_len[b]: the header of
+ * output b (library-owned, valid until the calling thread's next header call); status[b]: XM_OK, or the error the
+ * reference raises when it renders that output's header (it renders them in bin order, enabled outputs only).
+ * Returns XM_OK, XM_ERR_INDEX (xm.py:40-43 on either input), XM_ERR_UNICODE or XM_ERR_IO.  No context needed. */
+typedef struct xm_headers {
+    uint64_t record_offset[2];
+    const char *text[6];
+    uint64_t text_len[6];
+    int32_t status[6];
+    int32_t failed_input;      /* which input the return code is about (0 primary, 1 secondary), -1 */
+} xm_headers;
+int xm_process_headers_fds(int fd_prim, int fd_sec, const char *version, xm_headers *out);
+int xm_process_headers_mem(const void *prim, uint64_t prim_len, const void *sec, uint64_t sec_len, const char *version, xm_headers *out);
 
 /* ---- the walk across the GPUs of one box (one process per GPU, NCCL inside the library) ------------ */
 

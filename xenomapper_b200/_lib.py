@@ -15,7 +15,7 @@ BINS = ("primary_specific", "secondary_specific", "primary_multi",
 MODE_SE, MODE_PE_LIBERAL, MODE_PE_CONSERVATIVE = 0, 1, 2
 SCORE_AS_XS, SCORE_AS_ZS, SCORE_CIGAR_NM = 0, 1, 2
 (XM_OK, XM_ERR_ASSERT, XM_ERR_VALUE, XM_ERR_RUNTIME, XM_ERR_UNICODE, XM_ERR_UNSUPPORTED,
- XM_ERR_NOMEM, XM_ERR_CUDA, XM_ERR_ARG, XM_ERR_IO) = range(10)
+ XM_ERR_NOMEM, XM_ERR_CUDA, XM_ERR_ARG, XM_ERR_IO, XM_ERR_INDEX) = range(11)
 DEBUG_FORCE_GENERIC, DEBUG_SMALL_TILES, DEBUG_ROWS = 1, 2, 4
 
 EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_classify_device",
@@ -24,7 +24,8 @@ EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_cla
            "xm_memcpy_d2d", "xm_dev_mem_info", "xm_set_debug", "xm_locate_device", "xm_classify_bam_host",
            "xm_bam_header_text", "xm_bam_render_host", "xm_bam_get_stats", "xm_get_walk_kernels",
            "xm_comm_unique_id", "xm_comm_init_rank", "xm_comm_destroy", "xm_comm_barrier", "xm_comm_allreduce_f64",
-           "xm_classify_sharded_device", "xm_classify_sharded_host", "xm_copy_ceiling")
+           "xm_classify_sharded_device", "xm_classify_sharded_host", "xm_copy_ceiling",
+           "xm_process_headers_fds", "xm_process_headers_mem")
 
 
 class Opts(C.Structure):
@@ -51,6 +52,11 @@ class ShardStats(C.Structure):
                 ("sent_bytes", C.c_uint64), ("align_ms", C.c_float), ("index_ms", C.c_float), ("sliver_ms", C.c_float),
                 ("walk_ms", C.c_float), ("comm_ms", C.c_float), ("total_ms", C.c_float), ("n_collectives", C.c_uint32),
                 ("first_bad_rank", C.c_int32)]
+
+
+class Headers(C.Structure):
+    _fields_ = [("record_offset", C.c_uint64 * 2), ("text", C.c_void_p * 6), ("text_len", C.c_uint64 * 6),
+                ("status", C.c_int32 * 6), ("failed_input", C.c_int32)]
 
 
 class BamStats(C.Structure):
@@ -107,6 +113,8 @@ def load():
     L.xm_bam_get_stats.argtypes = [vp, C.POINTER(BamStats), i]
     L.xm_get_walk_kernels.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.xm_copy_ceiling.argtypes = [vp, u64, u64, i, C.POINTER(C.c_float)]
+    L.xm_process_headers_fds.argtypes = [i, i, C.c_char_p, C.POINTER(Headers)]
+    L.xm_process_headers_mem.argtypes = [vp, u64, vp, u64, C.c_char_p, C.POINTER(Headers)]
     L.xm_comm_unique_id.argtypes = [vp]
     L.xm_comm_init_rank.argtypes = [vp, i, i, vp]
     L.xm_comm_destroy.argtypes = [vp]
@@ -134,6 +142,22 @@ def _host_ptr(buf):
         arr = (C.c_char * len(mv)).from_buffer(mv)
         return C.cast(arr, C.c_void_p), len(mv), arr
     return C.c_void_p(buf.ctypes.data), buf.nbytes, buf
+
+
+def process_headers(prim, sec, version):
+    """(rc, failed input, record offsets, six header texts, six statuses) of two SAM files given as descriptors
+    (ints) or bytes-like objects: xm_process_headers_fds / _mem (xm.py:36-46, 120-174 on raw bytes; no GPU needed)"""
+    L = load()
+    h = Headers()
+    if isinstance(prim, int):
+        rc = L.xm_process_headers_fds(prim, sec, version.encode(), C.byref(h))
+    else:
+        pa, pn, pk = _host_ptr(prim)
+        sa, sn, sk = _host_ptr(sec)
+        rc = L.xm_process_headers_mem(pa, pn, sa, sn, version.encode(), C.byref(h))
+        del pk, sk
+    texts = [C.string_at(h.text[b], h.text_len[b]) if rc == XM_OK and h.text_len[b] else b"" for b in range(6)]
+    return rc, h.failed_input, list(h.record_offset), texts, list(h.status)
 
 
 class Context:

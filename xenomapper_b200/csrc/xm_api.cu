@@ -8,6 +8,8 @@
  */
 #include <cuda_runtime.h>
 #include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -28,6 +30,7 @@
 #include "xm_stream.h"
 #include "xm_bam.h"
 #include "xm_shard.h"
+#include "xm_headers.h"
 #include "xm_nccl.h"
 
 using namespace xm;
@@ -451,6 +454,8 @@ static int bin_append_d2h(xm_ctx *c, int b, const uint8_t *d_src, uint64_t n)
     return XM_OK;
 }
 
+static int host_threads();
+
 /* The bins of a descriptor walk are written by a thread of their own: a step's blocks are queued behind the event
  * that marks the end of their D2H copies, written with write(2) in bin order, and handed back to the pool. */
 struct BinWriter {
@@ -466,7 +471,15 @@ struct BinWriter {
     bool stop = false;
     int rc = XM_OK;
     std::string err;
-    BinWriter(xm_ctx *ctx, const int *out_fds) : c(ctx), fds(out_fds) { th = std::thread([this] { run(); }); }
+    bool regular[6] = {false, false, false, false, false, false};      /* seekable regular files not opened for append */
+    BinWriter(xm_ctx *ctx, const int *out_fds) : c(ctx), fds(out_fds)
+    {
+        for (int b = 0; b < 6; ++b) {
+            struct stat sb;
+            if (fds[b] >= 0 && fstat(fds[b], &sb) == 0 && S_ISREG(sb.st_mode) && !(fcntl(fds[b], F_GETFL) & O_APPEND)) regular[b] = true;
+        }
+        th = std::thread([this] { run(); });
+    }
     void run()
     {
         cudaSetDevice(c->device);
@@ -484,6 +497,30 @@ struct BinWriter {
             for (auto &kb : j.blocks) {
                 uint64_t w0 = 0;
                 const int fd = fds[kb.first];
+                if (rc == XM_OK && fd >= 0 && regular[kb.first] && kb.second.len >= (32ull << 20)) {
+                    /* a regular file: the block goes out as pwrites side by side behind the descriptor's position */
+                    const off_t at = lseek(fd, 0, SEEK_CUR);
+                    if (at >= 0) {
+                        const int nt = std::max(1, std::min(8, host_threads() / 2));
+                        const uint64_t per = ((kb.second.len + (uint64_t)nt - 1) / (uint64_t)nt + 4095) & ~4095ull;
+                        std::vector<std::thread> th;
+                        std::vector<int> bad((size_t)nt, 0);
+                        for (int t = 0; t < nt; ++t)
+                            th.emplace_back([&, t] {
+                                uint64_t lo = (uint64_t)t * per;
+                                const uint64_t hi = std::min<uint64_t>(lo + per, kb.second.len);
+                                while (lo < hi) {
+                                    const ssize_t w = pwrite(fd, kb.second.p + lo, (size_t)std::min<uint64_t>(hi - lo, 1u << 30), at + (off_t)lo);
+                                    if (w < 0) { if (errno == EINTR) continue; bad[(size_t)t] = errno; return; }
+                                    lo += (uint64_t)w;
+                                }
+                            });
+                        for (auto &t : th) t.join();
+                        for (int e : bad) if (e && rc == XM_OK) { rc = XM_ERR_IO; err = std::string("write: ") + strerror(e); }
+                        if (rc == XM_OK && lseek(fd, at + (off_t)kb.second.len, SEEK_SET) < 0) { rc = XM_ERR_IO; err = std::string("lseek: ") + strerror(errno); }
+                        w0 = kb.second.len;
+                    }
+                }
                 while (rc == XM_OK && fd >= 0 && w0 < kb.second.len) {
                     const ssize_t w = write(fd, kb.second.p + w0, (size_t)std::min<uint64_t>(kb.second.len - w0, 1u << 30));
                     if (w < 0) { if (errno == EINTR) continue; rc = XM_ERR_IO; err = std::string("write: ") + strerror(errno); break; }
@@ -557,6 +594,7 @@ static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opt
         FdFeeder &f = feeders[s];
         f.fd = in[s].feed->fd; f.off = in[s].feed->off; f.len = in[s].len;
         f.slot_cap = std::max<uint64_t>(std::min<uint64_t>(plan.chunk, in[s].len + 64), 64);
+        f.threads = std::max(1, host_threads() / 4);
         f.ring.resize(3);
         for (int k = 0; k < 3; ++k) {
             if ((rc = reserve_host(c, c->h_ring[s][k], f.slot_cap))) return rc;
@@ -1141,6 +1179,60 @@ int xm_copy_ceiling(xm_ctx *c, uint64_t h2d_bytes, uint64_t d2h_bytes, int reps,
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(e0[k]); cudaEventDestroy(e1[k]); if (h[k]) cudaFreeHost(h[k]); if (d[k]) cudaFree(d[k]); }
     *ms = best;
     return rc;
+}
+
+/* ---- headers (xm_headers.h) ------------------------------------------------------------------------------------ */
+static thread_local HeaderPlan g_header_plan;
+
+static int headers_finish(std::vector<std::string> h[2], const char *version, xm_headers *out)
+{
+    for (int k = 0; k < 2; ++k)
+        for (auto &l : h[k])
+            if (!utf8_valid((const unsigned char *)l.data(), l.size())) { out->failed_input = k; g_create_error = "invalid UTF-8 in the header"; return XM_ERR_UNICODE; }
+    plan_headers(h, version && *version ? version : "1.0.2", g_header_plan);
+    for (int b = 0; b < 6; ++b) {
+        out->text[b] = g_header_plan.text[b].data();
+        out->text_len[b] = g_header_plan.text[b].size();
+        out->status[b] = g_header_plan.status[b];
+    }
+    return XM_OK;
+}
+
+int xm_process_headers_mem(const void *prim, uint64_t prim_len, const void *sec, uint64_t sec_len, const char *version, xm_headers *out)
+{
+    if (!out || (!prim && prim_len) || (!sec && sec_len)) return XM_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    out->failed_input = -1;
+    const void *src[2] = {prim, sec};
+    const uint64_t len[2] = {prim_len, sec_len};
+    std::vector<std::string> h[2];
+    for (int k = 0; k < 2; ++k) {
+        const int rc = sam_header_scan((const uint8_t *)src[k], len[k], true, h[k], out->record_offset[k]);
+        if (rc != HDR_OK) { out->failed_input = k; g_create_error = "no record after the header lines"; return rc; }
+    }
+    return headers_finish(h, version, out);
+}
+
+int xm_process_headers_fds(int fd_prim, int fd_sec, const char *version, xm_headers *out)
+{
+    if (!out) return XM_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    out->failed_input = -1;
+    const int fds[2] = {fd_prim, fd_sec};
+    std::vector<std::string> h[2];
+    for (int k = 0; k < 2; ++k) {
+        std::vector<uint8_t> buf;
+        for (uint64_t want = 1 << 16;; want *= 4) {
+            buf.resize(want);
+            const int64_t got = xm_pread_all(fds[k], buf.data(), want, 0);
+            if (got < 0) { out->failed_input = k; g_create_error = std::string("read failed: ") + strerror(errno); return XM_ERR_IO; }
+            const int rc = sam_header_scan(buf.data(), (uint64_t)got, (uint64_t)got < want, h[k], out->record_offset[k]);
+            if (rc == HDR_MORE) continue;
+            if (rc != HDR_OK) { out->failed_input = k; g_create_error = "no record after the header lines"; return rc; }
+            break;
+        }
+    }
+    return headers_finish(h, version, out);
 }
 
 }  // extern "C"

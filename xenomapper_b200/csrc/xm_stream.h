@@ -57,6 +57,30 @@ inline uint64_t cut_after_last_newline(const uint8_t *p, uint64_t n)
 /* read n bytes of a descriptor source at absolute offset `at` into dst; returns bytes read or -1 */
 int64_t xm_pread_all(int fd, void *dst, uint64_t n, int64_t at);      /* xm_api.cu / the emulation harness */
 
+/* the same with `threads` preads side by side (page-cache and tmpfs reads are memcpy-bound per thread) */
+inline int64_t xm_pread_parallel(int fd, void *dst, uint64_t n, int64_t at, int threads)
+{
+    const uint64_t min_part = 8ull << 20;
+    if (threads <= 1 || n < 2 * min_part) return xm_pread_all(fd, dst, n, at);
+    const uint64_t parts = std::min<uint64_t>((uint64_t)threads, n / min_part);
+    const uint64_t per = ((n + parts - 1) / parts + 4095) & ~4095ull;
+    std::vector<int64_t> got(parts, 0);
+    std::vector<std::thread> th;
+    for (uint64_t k = 0; k < parts; ++k) {
+        const uint64_t lo = k * per, m = lo < n ? std::min<uint64_t>(per, n - lo) : 0;
+        th.emplace_back([=, &got] { got[k] = m ? xm_pread_all(fd, (uint8_t *)dst + lo, m, at + (int64_t)lo) : 0; });
+    }
+    for (auto &t : th) t.join();
+    int64_t total = 0;
+    for (uint64_t k = 0; k < parts; ++k) {
+        if (got[k] < 0) return -1;
+        total += got[k];
+        const uint64_t lo = k * per, m = lo < n ? std::min<uint64_t>(per, n - lo) : 0;
+        if ((uint64_t)got[k] < m) break;           /* the file ends inside this part: what the later parts read is not contiguous */
+    }
+    return total;
+}
+
 /*
  * Reads a descriptor ahead of the walk.  A thread of its own fills a ring of pinned slots; every slot holds whole
  * lines only (the tail behind a slot's last newline opens the next slot), the last one whatever is left.
@@ -66,6 +90,7 @@ struct FdFeeder {
     int fd = -1;
     int64_t off = 0;
     uint64_t len = 0, slot_cap = 0;
+    int threads = 1;                    /* preads side by side per slot */
     std::vector<Slot> ring;
     size_t head = 0;                    /* slot the walk takes from */
     bool ended = false;                 /* the walk has taken the stream's last byte */
@@ -92,7 +117,7 @@ struct FdFeeder {
             if (have) memcpy(s->p, tail.data(), have);
             tail.clear();
             const uint64_t want = std::min<uint64_t>(slot_cap - have, len - pos);
-            const int64_t got = want ? xm_pread_all(fd, s->p + have, want, off + (int64_t)pos) : 0;
+            const int64_t got = want ? xm_pread_parallel(fd, s->p + have, want, off + (int64_t)pos, threads) : 0;
             if (got < 0) { std::lock_guard<std::mutex> lk(mu); failed = true; s->n = 0; s->last = true; s->state = 1; cv.notify_all(); return; }
             if ((uint64_t)got < want) len = pos + (uint64_t)got;                 /* the file is shorter than announced */
             pos += (uint64_t)got;

@@ -1,12 +1,12 @@
 """
 xenomapper_b200.sharded -- the read-binning walk across the GPUs of one box.
 
-One process per GPU (`torchrun --nproc-per-node N -m xenomapper_b200.xenomapper ...`, or any
-launcher that sets RANK / WORLD_SIZE / LOCAL_RANK).  The walk itself, its NCCL communicator
+One process per GPU, started by any launcher that sets RANK / WORLD_SIZE / LOCAL_RANK
+(`python -m <launcher> --nproc-per-node N -m xenomapper_b200.xenomapper ...`).  The walk itself, its NCCL communicator
 and every collective live inside libxenomapper_b200.so (csrc/xm_shard.h): this module only
 
   * ferries the 128-byte NCCL id from rank 0 to the other ranks (a file in the launch's
-    scratch directory -- one box, one file system; no torch, no MPI),
+    scratch directory -- one box, one file system; no framework, no MPI),
   * gives every rank its BYTE shard of the two record regions, bytes [size*r/W, size*(r+1)/W),
     cut anywhere: the library moves the line heads, context lines and record slivers between
     neighbours and walks the RECORDS the rank's primary shard holds (the reference's lockstep
@@ -26,7 +26,7 @@ from . import _lib
 
 class Rendezvous:
     """publish(name, blob) on one rank, fetch(name) on the others.  Files live in a directory keyed by the launch
-    (XM_COMM_DIR, else MASTER_PORT + the launcher's pid, which all ranks of one torchrun share)."""
+    (XM_COMM_DIR, else MASTER_PORT + the launcher's pid, which all ranks of one launch share)."""
 
     def __init__(self, rank, world, directory=None, timeout=120.0):
         self.rank, self.world, self.timeout = rank, world, timeout

@@ -25,7 +25,9 @@ import io
 import os
 import re
 import sys
+import stat
 import textwrap
+import weakref
 from collections import Counter
 
 from . import _lib
@@ -78,11 +80,56 @@ def add_pg_tag(sam_header_list, comment=None):
     return out
 
 
+_RECORD_OFFSET = weakref.WeakKeyDictionary()     # input file -> byte offset of its first record, as the library found it
+
+
+def _regular_fd(f):
+    try:
+        fd = f.fileno()
+        return fd if stat.S_ISREG(os.fstat(fd).st_mode) else None
+    except (AttributeError, OSError, ValueError):
+        return None
+
+
+def _process_headers_native(file1, file2, outs):
+    """process_headers on the raw bytes of two regular files, inside the library (xm_process_headers_fds): headers,
+    @PG / @CO lines and the byte offset of the first record, without tell() cookies.  Returns False when the inputs
+    are not plain files at their start (the Python text path below handles those)."""
+    fds = [_regular_fd(file1), _regular_fd(file2)]
+    if None in fds:
+        return False
+    try:
+        if file1.tell() != 0 or file2.tell() != 0:
+            return False
+    except (OSError, ValueError):
+        return False
+    rc, bad, offsets, texts, status = _lib.process_headers(fds[0], fds[1], __version__)
+    if rc == _lib.XM_ERR_INDEX:
+        raise IndexError('string index out of range')                    # ''[0] in get_sam_header, xm.py:40-43
+    if rc == _lib.XM_ERR_UNICODE:
+        raise UnicodeDecodeError('utf-8', b'', 0, 1, 'invalid start byte in the header of input {0}'.format(bad + 1))
+    if rc != _lib.XM_OK:
+        raise XenomapperLibraryError('header processing failed ({0})'.format(rc))
+    for k, f in enumerate((file1, file2)):
+        f.seek(offsets[k])                                               # the reference leaves both files at their first record
+        _RECORD_OFFSET[f] = offsets[k]
+    for b, out in enumerate(outs):
+        if b and not out:
+            continue                                                     # primary_specific is always printed (None = stdout)
+        if status[b] == _lib.XM_ERR_INDEX:
+            raise IndexError('list index out of range')                 # add_pg_tag on an empty header / @PG without ID, xm.py:124-127
+        print(texts[b].decode('utf-8'), end='', file=out)
+    return True
+
+
 def process_headers(file1, file2, primary_specific=sys.stdout, secondary_specific=None,
                     primary_multi=None, secondary_multi=None, unassigned=None, unresolved=None, bam=False):
     """Write each enabled output's header.  Mirrors xm.py:133-174: primary-species
     header for primary_*, unassigned and unresolved; secondary-species header
-    for secondary_*."""
+    for secondary_*.  Plain SAM files at their start go through the library."""
+    outs = (primary_specific, secondary_specific, primary_multi, secondary_multi, unassigned, unresolved)
+    if not bam and _process_headers_native(file1, file2, outs):
+        return
     reader = get_bam_header if bam else get_sam_header
     h1, h2 = reader(file1), reader(file2)
     print('\n'.join(add_pg_tag(h1, comment='species specific reads')), file=primary_specific)
@@ -309,7 +356,6 @@ def _descriptors(readpairs, outputs):
     """((fd, byte offset) of both inputs, six output descriptors) when every file involved is a real one, else None.
     Text inputs must sit where only whole lines were read (after process_headers): then tell() is the byte offset
     of the first record, which is checked against the raw bytes."""
-    import stat
     ins = []
     for f in (readpairs.sam1, readpairs.sam2):
         try:
@@ -319,6 +365,9 @@ def _descriptors(readpairs, outputs):
             pos = f.tell()
         except (AttributeError, OSError, ValueError):
             return None
+        if _RECORD_OFFSET.get(f) == pos:
+            ins.append((fd, pos))             # where the library's header pass left it: a byte offset by construction
+            continue
         if not isinstance(pos, int) or pos < 0 or pos > os.fstat(fd).st_size:
             return None
         if pos > 0 and os.pread(fd, 1, pos - 1) != b"\n":
@@ -444,9 +493,8 @@ def main(argv=None):
 
 
 def _main_sharded(args, tag_func, outs, skip):
-    """`torchrun --nproc-per-node N -m xenomapper_b200.xenomapper ...` (or any launcher that sets RANK, WORLD_SIZE
-    and LOCAL_RANK): one process per GPU, each walks the records of its byte shard (xenomapper_b200/sharded.py,
-    csrc/xm_shard.h; NCCL inside the library, no torch here).  Outputs must be regular files: every rank writes
+    """Started once per GPU by a launcher that sets RANK, WORLD_SIZE and LOCAL_RANK: each process walks the
+    records of its byte shard (xenomapper_b200/sharded.py, csrc/xm_shard.h; NCCL inside the library).  Outputs must be regular files: every rank writes
     its part of each bin in place behind the header."""
     import json
     from . import sharded
@@ -469,13 +517,16 @@ def _main_sharded(args, tag_func, outs, skip):
                 hdr_len[b] = os.fstat(f.fileno()).st_size
         rv.publish("header_len", json.dumps(hdr_len).encode())
     else:
-        get_sam_header(args.primary_sam), get_sam_header(args.secondary_sam)
         hdr_len = json.loads(rv.fetch("header_len").decode())
+    # byte offset of each input's first record: the library's header pass on the raw bytes, on every rank
+    with open(args.primary_sam.name, "rb") as fp, open(args.secondary_sam.name, "rb") as fs:
+        hrc, _, rec_off, _, _ = _lib.process_headers(fp.fileno(), fs.fileno(), __version__)
+    if hrc != _lib.XM_OK:
+        raise IndexError('string index out of range')
     mode = _lib.MODE_SE if not args.paired else (_lib.MODE_PE_CONSERVATIVE if args.conservative else _lib.MODE_PE_LIBERAL)
     enabled = sum(1 << b for b, f in enumerate(files) if f)
     with open(args.primary_sam.name, "rb") as fp, open(args.secondary_sam.name, "rb") as fs:
-        res = sharded.sharded_walk(ctx, rank, world, fp.fileno(), _byte_offset(args.primary_sam), fs.fileno(),
-                                   _byte_offset(args.secondary_sam), mode=mode, score_src=_SCORE_SRC[tag_func], skip=skip,
+        res = sharded.sharded_walk(ctx, rank, world, fp.fileno(), rec_off[0], fs.fileno(), rec_off[1], mode=mode, score_src=_SCORE_SRC[tag_func], skip=skip,
                                    min_score=args.min_score, enabled_bins=enabled)
     sharded.write_outputs(res, [f.fileno() if f else -1 for f in files], hdr_len)
     ctx.comm_barrier()
@@ -489,17 +540,6 @@ def _main_sharded(args, tag_func, outs, skip):
             counts = res["counts"]
         output_summary(_counter(_R, mode != _lib.MODE_SE))
     ctx.close()
-
-
-def _byte_offset(textfile):
-    """byte offset of the first record: the length of the leading '@' lines (what get_sam_header consumes)"""
-    with open(textfile.name, 'rb') as raw:
-        off = 0
-        for line in raw:
-            if not line.startswith(b'@'):
-                break
-            off += len(line)
-    return off
 
 
 if __name__ == '__main__':
