@@ -168,6 +168,18 @@ int xm_count_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repea
 int xm_locate_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repeated, uint32_t n_queries,
                      const uint64_t *record_index, uint64_t *byte_offset);
 
+/* The same with options.  XM_OUT_BGZF: every bin is written as BGZF (blocked gzip, SAM/BAM specification section
+ * 4.1: members of at most 64 KiB of SAM text with the BC extra field) instead of plain text -- what the reference
+ * leaves to `| samtools view -bS` (README.md:138).  The walk appends members only; the caller writes its header
+ * with xm_bgzf_write before the call and ends each file with xm_bgzf_write(fd, NULL, 0, 1) after it.  Additive:
+ * without the flag the six files are the reference's SAM text byte for byte.  gunzip(output) == that text. */
+#define XM_OUT_BGZF 1u
+int xm_classify_fds_ex(xm_ctx *ctx, int fd_prim, int64_t off_prim, int fd_sec, int64_t off_sec,
+                       const int out_fds[6], const xm_opts *opts, uint32_t out_flags, xm_result *res);
+/* len bytes as BGZF members appended to fd (deflated by the host thread pool); eof != 0: the 28-byte end-of-file
+ * member behind them.  No context needed. */
+int xm_bgzf_write(int fd, const void *data, uint64_t len, int eof);
+
 /* ---- headers -------------------------------------------------------------- */
 
 /* process_headers (xm.py:133-174) with get_sam_header (xm.py:36-46) and add_pg_tag (xm.py:120-131) on the raw

@@ -139,3 +139,31 @@ def test_chunked_walk_refuses_a_line_longer_than_the_chunk(where):
     r2 = _emu.classify(p2, s2, chunk=chunk)
     ref = oracle.classify(p2, s2)
     assert r2["status"] == 0 and r2["outputs"] == ref["outputs"] and r2["counts"] == ref["counts"]
+
+
+def test_qname_assert_compares_bytes_not_only_hashes(tmp_path):
+    """The cross-stream QNAME assert (xm.py:106) joins the streams by a 64-bit hash and then compares the bytes.  A build
+    whose hash depends on the name's length only (-DXM_WEAK_HASH: every pair of equally long names collides) must
+    still raise AssertionError at the first record whose names differ, and walk clean inputs unchanged."""
+    import subprocess
+    from oracle import oracle
+    so = str(tmp_path / "libxm_emu_weak.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-DXM_WEAK_HASH", "-o", so, _emu.SRC])
+    saved_so, saved_lib = _emu.SO, _emu._lib
+    try:
+        _emu.SO, _emu._lib = so, None
+        os_utime = __import__("os").utime
+        os_utime(so)                                  # newer than the sources: _emu.lib() loads it as it is
+        p, s = _fixed_width_pair(400, 256)
+        ref = oracle.classify(p, s)
+        r = _emu.classify(p, s)
+        assert r["status"] == 0 and r["outputs"] == ref["outputs"]
+        bad = bytearray(s)
+        at = bad.index(b"\n", len(bad) // 2) + 1
+        bad[at + 3] = ord("X")                        # same length, different name: the weak hashes still agree
+        ref = oracle.classify(p, bytes(bad))
+        r = _emu.classify(p, bytes(bad))
+        assert ref["err"] == 1 and r["status"] == 1, r["message"]
+        assert r["outputs"] == ref["outputs"]
+    finally:
+        _emu.SO, _emu._lib = saved_so, saved_lib

@@ -216,3 +216,43 @@ def test_cuda_row_walk_selection_and_fallback(ctx):
         assert ERR[rc] == "AssertionError" and ref["err"] == 1
         assert outs == ref["outputs"]
     ctx.set_debug(0)
+
+
+def test_cuda_qname_assert_compares_bytes(tmp_path):
+    """the weak-hash twin of the library (every pair of equally long QNAMEs collides): all three walks -- fused, rows,
+    exact -- must still raise AssertionError where two names differ, and walk clean input unchanged"""
+    import json
+    import os
+    import subprocess
+    import sys
+    from xenomapper_b200 import _lib
+    weak = os.path.join(os.path.dirname(_lib.LIB_PATH), "libxenomapper_b200_weakhash.so")
+    assert os.path.exists(weak), "python -m xenomapper_b200.build makes it"
+    script = r'''
+import json, sys
+from oracle import oracle
+from xenomapper_b200 import _lib, synth
+ctx = _lib.Context(0)
+out = {}
+for name, debug in (("fused", 0), ("rows", 4), ("exact", 1)):
+    ctx.set_debug(debug)
+    p, s = synth.generate(30000, seed=31, style=1)
+    o = ctx.opts(1, 0, False)
+    rc, res, outs = ctx.classify_host(p, s, o)
+    ref = oracle.classify(p, s, mode=1)
+    clean_ok = rc == 0 and outs == ref["outputs"] and list(res.counts) == ref["counts"]
+    sb = bytearray(bytes(s))
+    at = sb.index(b"\n", len(sb) // 2) + 1
+    sb[at + 5] = ord("Z") if sb[at + 5] != ord("Z") else ord("Y")
+    rc, res, outs = ctx.classify_host(p, bytes(sb), o)
+    ref = oracle.classify(p, bytes(sb), mode=1)
+    out[name] = dict(clean_ok=clean_ok, rc=rc, ref_err=ref["err"], prefix_ok=outs == ref["outputs"], kernels=ctx.walk_kernels())
+print(json.dumps(out))
+'''
+    r = subprocess.run([sys.executable, "-c", script], cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       env=dict(os.environ, XM_LIB_PATH=weak), capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    res = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    for name, v in res.items():
+        assert v["clean_ok"], (name, v)
+        assert v["rc"] == 1 and v["ref_err"] == 1 and v["prefix_ok"], (name, v)

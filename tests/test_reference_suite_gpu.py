@@ -137,3 +137,33 @@ def test_cli_on_real_files_streams_through_descriptors(tmp_path, name, flags, ch
     e = case["expect"]
     assert [G.sha(o.read_bytes()) for o in outs] == e["full_sha256"]
     assert G.sha(r.stderr) == e["summary_sha256"]
+
+
+@pytest.mark.parametrize("name,flags", [("fixture_se_mode0_src0_skip1_min-inf", []), ("fixture_pe_mode1_src0_skip0_min-inf", ["--paired"])])
+@pytest.mark.parametrize("chunk", [None, "3000"])
+def test_cli_bgzf_outputs_inflate_to_the_reference_files(tmp_path, name, flags, chunk):
+    """--bgzf (additive): every output is BGZF; gunzip gives the reference CLI's file, header included, and
+    the file ends with the 28-byte end-of-file member"""
+    import gzip
+    import os
+    import subprocess
+    import sys
+    if name not in G.BY_NAME:
+        pytest.skip("no such golden")
+    case = G.BY_NAME[name]
+    key = case["input"]["key"]
+    p, s = tmp_path / "h.sam", tmp_path / "m.sam"
+    p.write_bytes(G.fixture_bytes(key, "primary")); s.write_bytes(G.fixture_bytes(key, "secondary"))
+    outs = [tmp_path / (b + ".sam.gz") for b in G.BINS]
+    cmd = [sys.executable, "-m", "xenomapper_b200.xenomapper", "--primary_sam", str(p), "--secondary_sam", str(s), "--bgzf"] + flags
+    for b, o in zip(G.BINS, outs):
+        cmd += ["--" + b, str(o)]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **({"XM_CHUNK_BYTES": chunk} if chunk else {}))
+    r = subprocess.run(cmd, cwd=root, capture_output=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr.decode()
+    e = case["expect"]
+    raw = [o.read_bytes() for o in outs]
+    assert all(x.endswith(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")) for x in raw)
+    assert [G.sha(gzip.decompress(x)) for x in raw] == e["full_sha256"]
+    assert G.sha(r.stderr) == e["summary_sha256"]

@@ -25,7 +25,8 @@ EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_cla
            "xm_bam_header_text", "xm_bam_render_host", "xm_bam_get_stats", "xm_get_walk_kernels",
            "xm_comm_unique_id", "xm_comm_init_rank", "xm_comm_destroy", "xm_comm_barrier", "xm_comm_allreduce_f64",
            "xm_classify_sharded_device", "xm_classify_sharded_host", "xm_copy_ceiling",
-           "xm_process_headers_fds", "xm_process_headers_mem")
+           "xm_process_headers_fds", "xm_process_headers_mem", "xm_classify_fds_ex", "xm_bgzf_write")
+OUT_BGZF = 1
 
 
 class Opts(C.Structure):
@@ -113,6 +114,8 @@ def load():
     L.xm_bam_get_stats.argtypes = [vp, C.POINTER(BamStats), i]
     L.xm_get_walk_kernels.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.xm_copy_ceiling.argtypes = [vp, u64, u64, i, C.POINTER(C.c_float)]
+    L.xm_classify_fds_ex.argtypes = [vp, i, C.c_int64, i, C.c_int64, C.POINTER(i), C.POINTER(Opts), C.c_uint32, C.POINTER(Result)]
+    L.xm_bgzf_write.argtypes = [i, vp, u64, i]
     L.xm_process_headers_fds.argtypes = [i, i, C.c_char_p, C.POINTER(Headers)]
     L.xm_process_headers_mem.argtypes = [vp, u64, vp, u64, C.c_char_p, C.POINTER(Headers)]
     L.xm_comm_unique_id.argtypes = [vp]
@@ -142,6 +145,15 @@ def _host_ptr(buf):
         arr = (C.c_char * len(mv)).from_buffer(mv)
         return C.cast(arr, C.c_void_p), len(mv), arr
     return C.c_void_p(buf.ctypes.data), buf.nbytes, buf
+
+
+def bgzf_write(fd, data=b"", eof=False):
+    """data as BGZF members appended to fd; eof: the empty end-of-file member behind them"""
+    L = load()
+    a, n, keep = _host_ptr(data) if data else (None, 0, None)
+    rc = L.xm_bgzf_write(fd, a, n, int(bool(eof)))
+    if rc != XM_OK:
+        raise XenomapperLibraryError("xm_bgzf_write failed (%d): %s" % (rc, L.xm_last_error(None).decode()))
 
 
 def process_headers(prim, sec, version):
@@ -347,10 +359,12 @@ class Context:
         self.lib.xm_bam_get_stats(self.h, C.byref(st), int(reset))
         return st
 
-    def classify_fds(self, fd_prim, off_prim, fd_sec, off_sec, out_fds, opts):
+    def classify_fds(self, fd_prim, off_prim, fd_sec, off_sec, out_fds, opts, out_flags=0):
+        """out_flags=OUT_BGZF: the bins leave as BGZF members (bgzf_write puts the header in front and the end-of-file
+        member behind them)"""
         res = Result()
         fds = (C.c_int * 6)(*out_fds)
-        rc = self.lib.xm_classify_fds(self.h, fd_prim, off_prim, fd_sec, off_sec, fds, C.byref(opts), C.byref(res))
+        rc = self.lib.xm_classify_fds_ex(self.h, fd_prim, off_prim, fd_sec, off_sec, fds, C.byref(opts), out_flags, C.byref(res))
         self._check(rc, "xm_classify_fds")
         return rc, res
 

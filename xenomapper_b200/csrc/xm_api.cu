@@ -31,6 +31,7 @@
 #include "xm_bam.h"
 #include "xm_shard.h"
 #include "xm_headers.h"
+#include "xm_bgzf.h"
 #include "xm_nccl.h"
 
 using namespace xm;
@@ -472,7 +473,8 @@ struct BinWriter {
     int rc = XM_OK;
     std::string err;
     bool regular[6] = {false, false, false, false, false, false};      /* seekable regular files not opened for append */
-    BinWriter(xm_ctx *ctx, const int *out_fds) : c(ctx), fds(out_fds)
+    bool bgzf = false;                      /* XM_OUT_BGZF: the blocks leave as BGZF members */
+    BinWriter(xm_ctx *ctx, const int *out_fds, bool as_bgzf = false) : c(ctx), fds(out_fds), bgzf(as_bgzf)
     {
         for (int b = 0; b < 6; ++b) {
             struct stat sb;
@@ -497,6 +499,19 @@ struct BinWriter {
             for (auto &kb : j.blocks) {
                 uint64_t w0 = 0;
                 const int fd = fds[kb.first];
+                if (bgzf) {
+                    if (rc == XM_OK && fd >= 0 && kb.second.len) {
+                        std::vector<uint8_t> z;
+                        if (!bgzf_compress(kb.second.p, kb.second.len, bgzf_level(), host_threads(), z)) { rc = XM_ERR_IO; err = "deflate failed"; }
+                        uint64_t zw = 0;
+                        while (rc == XM_OK && zw < z.size()) {
+                            const ssize_t w = write(fd, z.data() + zw, (size_t)std::min<uint64_t>(z.size() - zw, 1u << 30));
+                            if (w < 0) { if (errno == EINTR) continue; rc = XM_ERR_IO; err = std::string("write: ") + strerror(errno); break; }
+                            zw += (uint64_t)w;
+                        }
+                    }
+                    continue;
+                }
                 if (rc == XM_OK && fd >= 0 && regular[kb.first] && kb.second.len >= (32ull << 20)) {
                     /* a regular file: the block goes out as pwrites side by side behind the descriptor's position */
                     const off_t at = lseek(fd, 0, SEEK_CUR);
@@ -569,7 +584,7 @@ struct BinWriter {
 };
 
 /* out_fds == nullptr: keep the bins in host blocks (xm_get_output); else append each step's bytes to the descriptors */
-static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opts *opts, xm_result *res)
+static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opts *opts, xm_result *res, uint32_t out_flags = 0)
 {
     cudaSetDevice(c->device);
     recycle_bins(c);
@@ -594,7 +609,7 @@ static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opt
         FdFeeder &f = feeders[s];
         f.fd = in[s].feed->fd; f.off = in[s].feed->off; f.len = in[s].len;
         f.slot_cap = std::max<uint64_t>(std::min<uint64_t>(plan.chunk, in[s].len + 64), 64);
-        f.threads = std::max(1, host_threads() / 4);
+        f.threads = std::max(1, host_threads() / 2);         /* page-cache reads are memcpy-bound per thread */
         f.ring.resize(3);
         for (int k = 0; k < 3; ++k) {
             if ((rc = reserve_host(c, c->h_ring[s][k], f.slot_cap))) return rc;
@@ -617,7 +632,7 @@ static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opt
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, c->be.st);
-    BinWriter *writer = out_fds ? new BinWriter(c, out_fds) : nullptr;
+    BinWriter *writer = out_fds ? new BinWriter(c, out_fds, (out_flags & XM_OUT_BGZF) != 0) : nullptr;
     int emit_rc = XM_OK;
     cudaEvent_t set_done[2];
     bool set_used[2] = {false, false};
@@ -702,6 +717,27 @@ int xm_get_output(xm_ctx *c, int bin, const void **data, uint64_t *len)
 int xm_classify_fds(xm_ctx *c, int fd_prim, int64_t off_prim, int fd_sec, int64_t off_sec, const int out_fds[6],
                     const xm_opts *opts, xm_result *res)
 {
+    return xm_classify_fds_ex(c, fd_prim, off_prim, fd_sec, off_sec, out_fds, opts, 0, res);
+}
+
+int xm_bgzf_write(int fd, const void *data, uint64_t len, int eof)
+{
+    if (fd < 0 || (!data && len)) return XM_ERR_ARG;
+    std::vector<uint8_t> z;
+    if (len && !bgzf_compress((const uint8_t *)data, len, bgzf_level(), host_threads(), z)) { g_create_error = "deflate failed"; return XM_ERR_IO; }
+    if (eof) z.insert(z.end(), BGZF_EOF, BGZF_EOF + sizeof BGZF_EOF);
+    uint64_t at = 0;
+    while (at < z.size()) {
+        const ssize_t w = write(fd, z.data() + at, (size_t)std::min<uint64_t>(z.size() - at, 1u << 30));
+        if (w < 0) { if (errno == EINTR) continue; g_create_error = std::string("write: ") + strerror(errno); return XM_ERR_IO; }
+        at += (uint64_t)w;
+    }
+    return XM_OK;
+}
+
+int xm_classify_fds_ex(xm_ctx *c, int fd_prim, int64_t off_prim, int fd_sec, int64_t off_sec, const int out_fds[6],
+                       const xm_opts *opts, uint32_t out_flags, xm_result *res)
+{
     if (!c || !opts || !res || !out_fds) return XM_ERR_ARG;
     HostIn in[2];
     FdFeeder where[2];                  /* descriptor and offset only: stream_walk sets the readers up */
@@ -718,7 +754,7 @@ int xm_classify_fds(xm_ctx *c, int fd_prim, int64_t off_prim, int fd_sec, int64_
     uint32_t en = 0;
     for (int b = 0; b < 6; ++b) if (out_fds[b] >= 0) en |= 1u << b;
     o.enabled_bins = en;
-    return stream_walk(c, in, out_fds, &o, res);
+    return stream_walk(c, in, out_fds, &o, res, out_flags);
 }
 
 /* ---- BAM input (xm_bam.h) ------------------------------------------------------------------ */

@@ -171,8 +171,13 @@ XM_HD uint32_t fmix32(uint32_t x)
 }
 XM_HD void hash_final(Hash2 &h, uint32_t len)
 {
+#ifdef XM_WEAK_HASH
+    /* test builds: every QNAME of one length collides, so only the byte compare behind the hash can tell names apart */
+    h.a = len; h.b = ~len;
+#else
     h.a = fmix32(h.a ^ len);
     h.b = fmix32(h.b ^ (len * 0x9e3779b1u));
+#endif
 }
 
 /* ---- decimal integers: the device grammar [+-]?[0-9]+, |v| < 2^31 ------ */

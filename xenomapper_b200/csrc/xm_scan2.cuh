@@ -361,6 +361,24 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
 #ifndef XM_CLS2_OCC
 #define XM_CLS2_OCC 4
 #endif
+/* the len + 1 bytes at p and at s are equal (a QNAME and the separator behind it); both readable to the next
+ * multiple of 16 past their buffers' ends */
+__device__ __forceinline__ bool qnames_equal_bytes(const uint8_t *p, const uint8_t *s, uint32_t len)
+{
+    const uint32_t *pw = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3), *sw = (const uint32_t *)((uintptr_t)s & ~(uintptr_t)3);
+    const uint32_t shp = (uint32_t)((uintptr_t)p & 3u) * 8u, shs = (uint32_t)((uintptr_t)s & 3u) * 8u;
+    const uint32_t n = len + 1u;
+    uint32_t plo = __ldg(pw), slo = __ldg(sw);
+#pragma unroll 1
+    for (uint32_t done = 0, j = 1; done < n; done += 4u, ++j) {
+        const uint32_t phi = __ldg(pw + j), shi = __ldg(sw + j);
+        uint32_t x = __funnelshift_r(plo, phi, shp) ^ __funnelshift_r(slo, shi, shs);
+        if (n - done < 4u) x &= (1u << (8u * (n - done))) - 1u;
+        if (x) return false;
+        plo = phi; slo = shi;
+    }
+    return true;
+}
 constexpr int CLS2_LINES = 64;            /* lines (with the context line) a span may hold: two batches */
 
 template <class C>
@@ -449,7 +467,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
             if (mine) {
                 S.as[warp][k] = L.as; S.xs[warp][k] = L.xs; S.h1[warp][k] = L.h1; S.h2[warp][k] = L.h2;
                 S.so[warp][k] = L.s | (L.outlen << 16);
-                S.q[warp][k] = (same ? 1u : 0u);              /* all later phases need of the QNAME */
+                S.q[warp][k] = (same ? 1u : 0u) | (L.qlen << 1);   /* all later phases need of the QNAME: repeats the line before, length */
                 S.rank[warp][k] = yield ? (uint16_t)(count + (uint32_t)__popc(ym & ((1u << lane) - 1u))) : (uint16_t)0xffff;
             }
             count += (uint32_t)__popc(ym);
@@ -513,7 +531,9 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
             if (valid) {
                 const uint4 sr = a.sc.rec[gi];
                 const uint32_t smeta = a.sc.meta[gi];
-                if ((smeta >> META_LEN_BITS) || sr.z != S.h1[warp][k] || sr.w != S.h2[warp][k]) mismatch = true;     /* dirty / failing secondary line, QNAME assert: exact kernel */
+                if ((smeta & META_FLAGS) || sr.z != S.h1[warp][k] || sr.w != S.h2[warp][k]) mismatch = true;     /* dirty / failing secondary line, QNAME assert: exact kernel */
+                /* equal hashes are not yet equal names (xm.py:106 compares the strings): the bytes, separator included */
+                else if (!qnames_equal_bytes(win + (S.so[warp][k] & 0xffffu), a.S.p + a.sc.start[gi], S.q[warp][k] >> 1)) mismatch = true;
                 slen = smeta & META_LEN_MASK;
                 st = mapping_state(S.as[warp][k], S.xs[warp][k], (int32_t)sr.x, (int32_t)sr.y, a.thr);
                 so = S.so[warp][k];
@@ -540,7 +560,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
                         const bool pside = st == PS || st == PM || st == UA || st == UR, sside = st == SS || st == SM || st == UR;
                         plen = pside ? outlen : 0u; sbytes = sside ? slen : 0u; src = so & 0xffffu;
                     }
-                } else if (!skip && S.q[warp][k] && pvalid && gi > 0) {
+                } else if (!skip && (S.q[warp][k] & 1u) && pvalid && gi > 0) {
                     key = (uint32_t)(pst * 6 + st);
                     bin = (uint32_t)(a.mode == MODE_PE_CONSERVATIVE ? pair_bin_conservative(pst, st) : pair_bin_liberal(pst, st));
                     const bool pside = bin == PS || bin == PM || bin == UA || bin == UR, sside = bin == SS || bin == SM || bin == UR;

@@ -254,6 +254,17 @@ XM_HD uint64_t prev_line_start(const uint32_t *nlm, const uint8_t *glob, uint64_
     return p;
 }
 
+/* the primary QNAME [pq, pq + qlen) equals the first token of the secondary line that starts at sstart */
+XM_HD bool qname_equals_secondary(const Reader &rd, uint64_t pq, uint32_t qlen, const StreamBuf &S, uint64_t sstart)
+{
+    uint64_t q = sstart;
+    while (q < S.len && S.p[q] != '\n' && is_ascii_space(S.p[q])) ++q;
+    if (q + qlen > S.len) return false;
+    for (uint32_t k = 0; k < qlen; ++k)
+        if (S.p[q + k] != rd.at(pq + k)) return false;
+    return q + qlen == S.len || is_ascii_space(S.p[q + qlen]);
+}
+
 template <class C>
 struct Front {
     Geo geo;
@@ -822,6 +833,11 @@ XM_HD void classify_tile(TileCtx<C> &T, const ClassifyArgs &a, uint32_t tile)
                 /* text the device does not tokenise like the reference comes first: nothing derived from it can be trusted */
                 if ((L.flags | sflags) & F_TEXT) ec = EC_TEXT;
                 else if (sr.z != L.h1 || sr.w != L.h2) ec = EC_ASSERT;     /* xm.py:106 */
+                else {
+                    /* equal hashes are not yet equal names: the reference compares the strings */
+                    const Reader rd_{T.m.win, a.P.p, fr.geo.g0, fr.geo.wbytes, a.P.len};
+                    if (!qname_equals_secondary(rd_, fr.geo.g0 + L.qs, L.qlen, a.S, a.sc.start[gi])) ec = EC_ASSERT;
+                }
                 if (ec) report_error(a.g, gi, ec, (ec == EC_TEXT && !(L.flags & F_TEXT)) ? 1 : 0);
                 int ev, evs;
                 eval_error(L.flags, sflags, ev, evs);

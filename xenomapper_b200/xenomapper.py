@@ -321,6 +321,8 @@ def _walk(mode, readpairs, outputs, min_score, tag_func):
         skip = readpairs.skip_repeated_reads
         fds = _descriptors(readpairs, outputs)      # before anything is read from the inputs
         if not fds:
+            if getattr(readpairs, "bgzf", False):
+                raise NotImplementedError("BGZF output needs regular input files and outputs with descriptors")
             prim, sec = readpairs.record_regions()
     else:
         prim, sec = _serialise_pairs(readpairs)
@@ -335,7 +337,7 @@ def _walk(mode, readpairs, outputs, min_score, tag_func):
         # real files on both sides (the CLI): the library streams them through pinned staging and appends each bin to
         # its descriptor in record order (xm_classify_fds); nothing passes through Python
         (fd1, off1), (fd2, off2), out_fds = fds
-        rc, res = ctx.classify_fds(fd1, off1, fd2, off2, out_fds, opts)
+        rc, res = ctx.classify_fds(fd1, off1, fd2, off2, out_fds, opts, _lib.OUT_BGZF if getattr(readpairs, "bgzf", False) else 0)
         if rc != _lib.XM_OK:
             _raise_for(rc, ctx, res)
         return _counter(res, mode != _lib.MODE_SE)
@@ -454,6 +456,8 @@ def command_line_interface(argv=None):
     a('--min_score', type=float, default=NEG_INF, help='scores less than or equal to this count as unmapped')
     a('--cigar_scores', action='store_true', help='score = -6*NM -5*gap opens -3*gap bases -2*soft clipped bases, from CIGAR and NM')
     a('--use_zs', action='store_true', help='take the next-best score from ZS instead of XS (HISAT)')
+    a('--bgzf', action='store_true', help='write the outputs as BGZF (blocked gzip of the SAM text, what bgzip writes) instead of '
+                                          'plain SAM; not an option of the reference, which leaves compression to a pipe')
     a('--version', action='store_true', help='print version information and exit')
     args = p.parse_args(argv)
     if args.version:
@@ -478,6 +482,8 @@ def main(argv=None):
         if not args.primary_sam:
             raise NotImplementedError("the sharded walk (one process per GPU) takes SAM inputs")
         return _main_sharded(args, tag_func, outs, skip)
+    if args.bgzf:
+        return _main_bgzf(args, tag_func, outs, skip)
     if args.primary_sam:
         process_headers(args.primary_sam, args.secondary_sam, **outs)
         pairs = getReadPairs(args.primary_sam, args.secondary_sam, skip_repeated_reads=skip)
@@ -489,6 +495,32 @@ def main(argv=None):
     for f in outs.values():
         if f:
             f.flush()
+    output_summary(counts)
+
+
+def _main_bgzf(args, tag_func, outs, skip):
+    """--bgzf: headers and bins leave as BGZF members (xm_bgzf_write, xm_classify_fds_ex with XM_OUT_BGZF).
+    gunzip of every output equals what the command writes without the flag."""
+    import io
+    if not args.primary_sam:
+        raise NotImplementedError("--bgzf takes SAM inputs")
+    files = {k: f for k, f in outs.items() if f}
+    for k, f in files.items():
+        if _regular_fd(f) is None and not hasattr(f, "fileno"):
+            raise ValueError("--bgzf writes through descriptors: {0} has none".format(k))
+    texts = {k: io.StringIO() for k in files}
+    process_headers(args.primary_sam, args.secondary_sam, **{k: texts.get(k) for k in outs})
+    for k, f in files.items():
+        f.flush()
+        _lib.bgzf_write(f.fileno(), texts[k].getvalue().encode())
+    pairs = getReadPairs(args.primary_sam, args.secondary_sam, skip_repeated_reads=skip)
+    pairs.bgzf = True
+    walk = main_single_end if not args.paired else (conservative_main_paired_end if args.conservative else main_paired_end)
+    try:
+        counts = walk(pairs, min_score=args.min_score, tag_func=tag_func, **outs)
+    finally:
+        for f in files.values():
+            _lib.bgzf_write(f.fileno(), eof=True)
     output_summary(counts)
 
 
