@@ -300,6 +300,9 @@ int xm_copy_ceiling(xm_ctx *ctx, uint64_t h2d_bytes, uint64_t d2h_bytes, int rep
 #define XM_DEBUG_SMALL_TILES   2u   /* 1 KiB tiles: exercises tile-boundary logic on small inputs */
 #define XM_DEBUG_ROWS          4u   /* clean inputs walk over rows (k_scan2 on both streams, k_size, k_prefix, k_emit: the kernels of
                                        the sharded walk) instead of k_scan2 + the fused k_classify2 */
+#define XM_DEBUG_EXACT_NAMES   8u   /* the barrier-free kernels join the streams by a 64-bit QNAME hash (xm.py:106); with this flag they
+                                       also compare the bytes, as the exact kernels always do (one scattered read of the secondary
+                                       line per record: 30 % on the classify kernel).  Environment: XM_EXACT_NAMES=1 */
 int xm_set_debug(xm_ctx *ctx, uint32_t flags);
 
 #ifdef __cplusplus

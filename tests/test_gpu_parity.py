@@ -219,8 +219,9 @@ def test_cuda_row_walk_selection_and_fallback(ctx):
 
 
 def test_cuda_qname_assert_compares_bytes(tmp_path):
-    """the weak-hash twin of the library (every pair of equally long QNAMEs collides): all three walks -- fused, rows,
-    exact -- must still raise AssertionError where two names differ, and walk clean input unchanged"""
+    """the weak-hash twin of the library (every pair of equally long QNAMEs collides): the exact kernels, and the two
+    barrier-free walks with XM_DEBUG_EXACT_NAMES, must still raise AssertionError where two names differ, and walk
+    clean input unchanged"""
     import json
     import os
     import subprocess
@@ -234,7 +235,7 @@ from oracle import oracle
 from xenomapper_b200 import _lib, synth
 ctx = _lib.Context(0)
 out = {}
-for name, debug in (("fused", 0), ("rows", 4), ("exact", 1)):
+for name, debug in (("fused", 8), ("rows", 4 | 8), ("exact", 1)):          # 8 = XM_DEBUG_EXACT_NAMES
     ctx.set_debug(debug)
     p, s = synth.generate(30000, seed=31, style=1)
     o = ctx.opts(1, 0, False)

@@ -16,7 +16,7 @@ MODE_SE, MODE_PE_LIBERAL, MODE_PE_CONSERVATIVE = 0, 1, 2
 SCORE_AS_XS, SCORE_AS_ZS, SCORE_CIGAR_NM = 0, 1, 2
 (XM_OK, XM_ERR_ASSERT, XM_ERR_VALUE, XM_ERR_RUNTIME, XM_ERR_UNICODE, XM_ERR_UNSUPPORTED,
  XM_ERR_NOMEM, XM_ERR_CUDA, XM_ERR_ARG, XM_ERR_IO, XM_ERR_INDEX) = range(11)
-DEBUG_FORCE_GENERIC, DEBUG_SMALL_TILES, DEBUG_ROWS = 1, 2, 4
+DEBUG_FORCE_GENERIC, DEBUG_SMALL_TILES, DEBUG_ROWS, DEBUG_EXACT_NAMES = 1, 2, 4, 8
 
 EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_classify_device",
            "xm_classify_host", "xm_get_output", "xm_classify_fds", "xm_count_device", "xm_dev_alloc",

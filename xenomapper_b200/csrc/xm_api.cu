@@ -289,6 +289,8 @@ int xm_set_debug(xm_ctx *c, uint32_t flags)
     /* XM_ROWS=1 in the environment: every context walks over rows (benchmarks of the sharded walk's kernels) */
     static const bool rows = [] { const char *e = getenv("XM_ROWS"); return e && e[0] == '1'; }();
     if (rows) c->debug |= DBG_ROWS;
+    static const bool exact = [] { const char *e = getenv("XM_EXACT_NAMES"); return e && e[0] == '1'; }();
+    if (exact) c->debug |= DBG_EXACT_NAMES;
     return XM_OK;
 }
 

@@ -113,6 +113,7 @@ struct EmitArgs {
     SCompact rp, rs;                  /* rows of the primary / secondary stream, already offset to the walk's record 0 */
     uint64_t n;                       /* records to walk */
     int32_t mode, skip, halo;
+    int32_t exact_names;              /* behind equal QNAME hashes compare the bytes too (XM_DEBUG_EXACT_NAMES) */
     long long thr;
     uint32_t enabled;
     Globals *g;
@@ -142,7 +143,7 @@ struct ClassifyArgs {
     uint32_t debug;
 };
 
-constexpr uint32_t DBG_FORCE_GENERIC = 1, DBG_SMALL_TILES = 2, DBG_ROWS = 4;
+constexpr uint32_t DBG_FORCE_GENERIC = 1, DBG_SMALL_TILES = 2, DBG_ROWS = 4, DBG_EXACT_NAMES = 8;
 
 /* tile geometry: one line per thread */
 template <int TILE_, int HALO_, int THREADS_>

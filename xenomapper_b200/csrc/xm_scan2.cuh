@@ -532,8 +532,9 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_CLS2_OCC) k_classify2(const 
                 const uint4 sr = a.sc.rec[gi];
                 const uint32_t smeta = a.sc.meta[gi];
                 if ((smeta & META_FLAGS) || sr.z != S.h1[warp][k] || sr.w != S.h2[warp][k]) mismatch = true;     /* dirty / failing secondary line, QNAME assert: exact kernel */
-                /* equal hashes are not yet equal names (xm.py:106 compares the strings): the bytes, separator included */
-                else if (!qnames_equal_bytes(win + (S.so[warp][k] & 0xffffu), a.S.p + a.sc.start[gi], S.q[warp][k] >> 1)) mismatch = true;
+                /* equal 64-bit hashes are taken for equal names; XM_DEBUG_EXACT_NAMES compares the bytes,
+                 * separator included, as the exact kernel always does: one scattered read of the secondary line per record */
+                else if ((a.debug & DBG_EXACT_NAMES) && !qnames_equal_bytes(win + (S.so[warp][k] & 0xffffu), a.S.p + a.sc.start[gi], S.q[warp][k] >> 1)) mismatch = true;
                 slen = smeta & META_LEN_MASK;
                 st = mapping_state(S.as[warp][k], S.xs[warp][k], (int32_t)sr.x, (int32_t)sr.y, a.thr);
                 so = S.so[warp][k];

@@ -168,7 +168,6 @@ inline int walk_sharded(BE &be, CM &cm, ShardScratch &sc, const ShardBuf in[2], 
                         const uint64_t out_cap[6], uint32_t debug, xm_result *res, xm_shard_stats *st, std::string &err,
                         OutAlloc alloc_out = OutAlloc())
 {
-    (void)debug;
     memset(res, 0, sizeof *res);
     memset(st, 0, sizeof *st);
     res->err_stream = -1;
@@ -513,7 +512,7 @@ inline int walk_sharded(BE &be, CM &cm, ShardScratch &sc, const ShardBuf in[2], 
         ea.rp.start = sc.r[0].rows.start + first_row[0]; ea.rp.rec = sc.r[0].rows.rec + first_row[0]; ea.rp.meta = sc.r[0].rows.meta + first_row[0];
         ea.rs.start = sc.r[1].rows.start + first_row[1]; ea.rs.rec = sc.r[1].rows.rec + first_row[1]; ea.rs.meta = sc.r[1].rows.meta + first_row[1];
         ea.n = n_walk;
-        ea.mode = o.mode; ea.skip = skip ? 1 : 0; ea.halo = (n_walk && has_ctx(r)) ? 1 : 0;
+        ea.mode = o.mode; ea.skip = skip ? 1 : 0; ea.halo = (n_walk && has_ctx(r)) ? 1 : 0; ea.exact_names = (debug & DBG_EXACT_NAMES) ? 1 : 0;
         ea.thr = score_threshold(o.min_score); ea.enabled = o.enabled_bins & 0x3f; ea.g = sc.g;
         ea.ntiles = (uint32_t)((n_walk + EM_TILE - 1) / EM_TILE);
         if ((uint64_t)ea.ntiles + 1 > sc.cap_tot) {

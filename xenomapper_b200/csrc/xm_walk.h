@@ -378,7 +378,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
                 EmitArgs ea;
                 memset(&ea, 0, sizeof ea);
                 ea.P = P; ea.S = S; ea.rp = sc.scp; ea.rs = sc.sc; ea.n = n;
-                ea.mode = o.mode; ea.skip = sa.skip; ea.halo = ctl ? ctl->halo : 0;
+                ea.mode = o.mode; ea.skip = sa.skip; ea.halo = ctl ? ctl->halo : 0; ea.exact_names = (debug & DBG_EXACT_NAMES) ? 1 : 0;
                 ea.thr = ca.thr; ea.enabled = ca.enabled; ea.g = sc.g; ea.tile_tot = sc.tile_tot;
                 ea.ntiles = (uint32_t)((n + EM_TILE - 1) / EM_TILE);
                 for (int b = 0; b < 6; ++b) { ea.out[b] = ca.out[b]; ea.out_cap[b] = ca.out_cap[b]; }
