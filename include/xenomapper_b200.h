@@ -176,6 +176,14 @@ int xm_locate_device(xm_ctx *ctx, const void *d_buf, uint64_t len, int skip_repe
 #define XM_OUT_BGZF 1u
 int xm_classify_fds_ex(xm_ctx *ctx, int fd_prim, int64_t off_prim, int fd_sec, int64_t off_sec,
                        const int out_fds[6], const xm_opts *opts, uint32_t out_flags, xm_result *res);
+/* Two aligner streams in, six bins out, in one call: header processing (xm_process_headers_fds) and the walk, for
+ * inputs that cannot seek -- pipes from an aligner, process substitutions, sockets (the reference needs seekable
+ * files: xm.py:586-587 -- SURVEY 8f-4).  Both headers are read from the descriptors themselves, every enabled
+ * output gets its header (xm.py:133-174; as BGZF members and ended by the end-of-file member with XM_OUT_BGZF),
+ * then the records are walked as they arrive.  Seekable files are accepted too (they are read from their start).
+ * Returns XM_ERR_INDEX / XM_ERR_UNICODE for the header errors of xm_process_headers_fds. */
+int xm_classify_streams(xm_ctx *ctx, int fd_prim, int fd_sec, const int out_fds[6], const xm_opts *opts,
+                        uint32_t out_flags, const char *version, xm_result *res);
 /* len bytes as BGZF members appended to fd (deflated by the host thread pool); eof != 0: the 28-byte end-of-file
  * member behind them.  No context needed. */
 int xm_bgzf_write(int fd, const void *data, uint64_t len, int eof);

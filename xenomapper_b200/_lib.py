@@ -25,7 +25,7 @@ EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_cla
            "xm_bam_header_text", "xm_bam_render_host", "xm_bam_get_stats", "xm_get_walk_kernels",
            "xm_comm_unique_id", "xm_comm_init_rank", "xm_comm_destroy", "xm_comm_barrier", "xm_comm_allreduce_f64",
            "xm_classify_sharded_device", "xm_classify_sharded_host", "xm_copy_ceiling",
-           "xm_process_headers_fds", "xm_process_headers_mem", "xm_classify_fds_ex", "xm_bgzf_write")
+           "xm_process_headers_fds", "xm_process_headers_mem", "xm_classify_fds_ex", "xm_bgzf_write", "xm_classify_streams")
 OUT_BGZF = 1
 
 
@@ -116,6 +116,7 @@ def load():
     L.xm_copy_ceiling.argtypes = [vp, u64, u64, i, C.POINTER(C.c_float)]
     L.xm_classify_fds_ex.argtypes = [vp, i, C.c_int64, i, C.c_int64, C.POINTER(i), C.POINTER(Opts), C.c_uint32, C.POINTER(Result)]
     L.xm_bgzf_write.argtypes = [i, vp, u64, i]
+    L.xm_classify_streams.argtypes = [vp, i, i, C.POINTER(i), C.POINTER(Opts), C.c_uint32, C.c_char_p, C.POINTER(Result)]
     L.xm_process_headers_fds.argtypes = [i, i, C.c_char_p, C.POINTER(Headers)]
     L.xm_process_headers_mem.argtypes = [vp, u64, vp, u64, C.c_char_p, C.POINTER(Headers)]
     L.xm_comm_unique_id.argtypes = [vp]
@@ -366,6 +367,15 @@ class Context:
         fds = (C.c_int * 6)(*out_fds)
         rc = self.lib.xm_classify_fds_ex(self.h, fd_prim, off_prim, fd_sec, off_sec, fds, C.byref(opts), out_flags, C.byref(res))
         self._check(rc, "xm_classify_fds")
+        return rc, res
+
+    def classify_streams(self, fd_prim, fd_sec, out_fds, opts, version, out_flags=0):
+        """headers + walk in one call for inputs that cannot seek (pipes): xm_classify_streams"""
+        res = Result()
+        fds = (C.c_int * 6)(*out_fds)
+        rc = self.lib.xm_classify_streams(self.h, fd_prim, fd_sec, fds, C.byref(opts), out_flags, version.encode(), C.byref(res))
+        if rc != XM_ERR_INDEX:
+            self._check(rc, "xm_classify_streams")
         return rc, res
 
     def count_device(self, d_buf, n, skip_repeated=False):

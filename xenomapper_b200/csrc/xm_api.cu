@@ -610,6 +610,7 @@ static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opt
         if (!in[s].feed) continue;
         FdFeeder &f = feeders[s];
         f.fd = in[s].feed->fd; f.off = in[s].feed->off; f.len = in[s].len;
+        f.seekable = in[s].feed->seekable; f.pre.swap(in[s].feed->pre);
         f.slot_cap = std::max<uint64_t>(std::min<uint64_t>(plan.chunk, in[s].len + 64), 64);
         f.threads = std::max(1, host_threads() / 2);         /* page-cache reads are memcpy-bound per thread */
         f.ring.resize(3);
@@ -1271,6 +1272,70 @@ int xm_process_headers_fds(int fd_prim, int fd_sec, const char *version, xm_head
         }
     }
     return headers_finish(h, version, out);
+}
+
+/* ---- two streams in, six bins out (pipes) --------------------------------------------------------------------- */
+static int write_all(int fd, const void *p, uint64_t n)
+{
+    uint64_t at = 0;
+    while (at < n) {
+        const ssize_t w = write(fd, (const uint8_t *)p + at, (size_t)std::min<uint64_t>(n - at, 1u << 30));
+        if (w < 0) { if (errno == EINTR) continue; return -1; }
+        at += (uint64_t)w;
+    }
+    return 0;
+}
+
+int xm_classify_streams(xm_ctx *c, int fd_prim, int fd_sec, const int out_fds[6], const xm_opts *opts, uint32_t out_flags,
+                        const char *version, xm_result *res)
+{
+    if (!c || !opts || !res || !out_fds) return XM_ERR_ARG;
+    memset(res, 0, sizeof *res);
+    const int fds[2] = {fd_prim, fd_sec};
+    FdFeeder where[2];
+    HostIn in[2];
+    std::vector<std::string> h[2];
+    /* the headers come off the descriptors themselves; what was read behind them opens the record stream */
+    for (int s = 0; s < 2; ++s) {
+        std::vector<uint8_t> buf;
+        bool eof = false;
+        uint64_t offset = 0;
+        for (;;) {
+            const size_t at = buf.size();
+            buf.resize(at + (1 << 16));
+            ssize_t r;
+            do { r = read(fds[s], buf.data() + at, 1 << 16); } while (r < 0 && errno == EINTR);
+            if (r < 0) return res->status = fail(c, XM_ERR_IO, std::string("read failed: ") + strerror(errno));
+            buf.resize(at + (size_t)r);
+            if (r == 0) eof = true;
+            const int rc = sam_header_scan(buf.data(), buf.size(), eof, h[s], offset);
+            if (rc == HDR_MORE) continue;
+            if (rc != HDR_OK) return res->status = fail(c, rc, "no record after the header lines of input " + std::to_string(s + 1));
+            break;
+        }
+        for (auto &l : h[s]) if (!utf8_valid((const unsigned char *)l.data(), l.size())) return res->status = fail(c, XM_ERR_UNICODE, "invalid UTF-8 in the header");
+        where[s].fd = fds[s]; where[s].off = 0; where[s].seekable = false;
+        where[s].pre.assign(buf.begin() + (long)offset, buf.end());
+        in[s].feed = &where[s];
+        in[s].len = eof ? (uint64_t)where[s].pre.size() : (~0ull >> 2);        /* unknown until the writer closes its end */
+    }
+    HeaderPlan plan;
+    plan_headers(h, version && *version ? version : "1.0.2", plan);
+    uint32_t en = 0;
+    for (int b = 0; b < 6; ++b) {
+        if (out_fds[b] < 0) continue;
+        en |= 1u << b;
+        if (plan.status[b] != HDR_OK) return res->status = fail(c, plan.status[b], "header of output " + std::to_string(b) + " cannot be made (xm.py:124-127)");
+        const int w = (out_flags & XM_OUT_BGZF) ? xm_bgzf_write(out_fds[b], plan.text[b].data(), plan.text[b].size(), 0)
+                                                : write_all(out_fds[b], plan.text[b].data(), plan.text[b].size());
+        if (w) return res->status = fail(c, XM_ERR_IO, std::string("write: ") + strerror(errno));
+    }
+    xm_opts o = *opts;
+    o.enabled_bins = en;
+    const int rc = stream_walk(c, in, out_fds, &o, res, out_flags);
+    if (out_flags & XM_OUT_BGZF)
+        for (int b = 0; b < 6; ++b) if (out_fds[b] >= 0) xm_bgzf_write(out_fds[b], nullptr, 0, 1);
+    return rc;
 }
 
 }  // extern "C"

@@ -217,7 +217,8 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
 }
 
 
-template <class C>
+/* WANT_SAME / COUNT_ONLY: ScanArgs::want_same / count_only as compile-time switches (the plain scan keeps its code) */
+template <class C, bool WANT_SAME, bool COUNT_ONLY>
 __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const ScanArgs a)
 {
     __shared__ uint32_t s_tbm[C::WARPS][C::NWW], s_nlm[C::WARPS][C::NWW];
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
     const uint32_t tile = blockIdx.x;
     const uint64_t span_lo = ((uint64_t)tile * C::WARPS + (uint64_t)warp) * (uint64_t)C::SPAN;
     const bool skip = a.skip != 0;
-    const bool need_prev = skip || a.want_same != 0;      /* the line before the span's first is looked at (run heads, META_SAME) */
+    const bool need_prev = skip || WANT_SAME;             /* the line before the span's first is looked at (run heads, META_SAME) */
     uint32_t *tbm = s_tbm[warp], *nlm = s_nlm[warp];
     uint16_t *trk = s_trk[warp], *starts = s_start[warp];
     const SpanInfo si = span_front<C, true>(a.S, span_lo, need_prev, tbm, nlm, trk, starts);
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
         count += (uint32_t)__popc(ym);
         Rrec[b] = make_uint4((uint32_t)L.as, (uint32_t)L.xs, L.h1, L.h2);
         Rs[b] = L.s;
-        Rmeta[b] = (L.outlen & META_LEN_MASK) | ((L.flags & 0x3fu) << META_LEN_BITS) | (same ? META_SAME : 0u);
+        Rmeta[b] = (L.outlen & META_LEN_MASK) | ((L.flags & 0x3fu) << META_LEN_BITS) | ((WANT_SAME && same) ? META_SAME : 0u);
     }
     if (bad) { count = 0; if (lane == 0) a.g->pad = 1u; }      /* Globals::pad doubles as the fallback flag */
 
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
          * before this one have long published theirs */
         if (threadIdx.x == 0) dev_publish1(a.chain1, tile, total, false);
     }
-    if (!bad && !a.count_only) {
+    if (!bad && !COUNT_ONLY) {
 #pragma unroll
         for (int b = 0; b < MAXB; ++b) {
             const uint32_t k = (uint32_t)(32 * b + lane);
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(C::WARPS * 32, XM_SCAN2_OCC) k_scan2(const Sca
             const unsigned long long gi = base + rank[b];
             if (gi < a.sc_cap) {
                 a.sc.start[gi] = a.start_bias + win0 + Rs[b];
-                if (!a.count_only) { a.sc.rec[gi] = Rrec[b]; a.sc.meta[gi] = Rmeta[b]; }
+                if (!COUNT_ONLY) { a.sc.rec[gi] = Rrec[b]; a.sc.meta[gi] = Rmeta[b]; }
             }
         }
     }
@@ -694,7 +695,9 @@ static cudaError_t launch_scan2_t(ScanArgs a, cudaStream_t st)
 {
     const uint64_t nt = (a.S.len + C::TILE - 1) / C::TILE;
     a.ntiles = (uint32_t)nt;
-    k_scan2<C><<<(unsigned)nt, C::WARPS * 32, 0, st>>>(a);
+    if (a.count_only) k_scan2<C, false, true><<<(unsigned)nt, C::WARPS * 32, 0, st>>>(a);
+    else if (a.want_same) k_scan2<C, true, false><<<(unsigned)nt, C::WARPS * 32, 0, st>>>(a);
+    else k_scan2<C, false, false><<<(unsigned)nt, C::WARPS * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_scan2(const ScanArgs &a, cudaStream_t st) { return launch_scan2_t<Scan2Sec>(a, st); }

@@ -34,7 +34,9 @@
  * so that the CPU emulation harness of the tests runs the same logic.
  */
 #pragma once
+#include <errno.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <condition_variable>
@@ -91,6 +93,8 @@ struct FdFeeder {
     int64_t off = 0;
     uint64_t len = 0, slot_cap = 0;
     int threads = 1;                    /* preads side by side per slot */
+    bool seekable = true;               /* false: a pipe or socket, read() in order, length unknown until it ends */
+    std::vector<uint8_t> pre;           /* bytes already taken from a pipe (behind its header): the stream starts with them */
     std::vector<Slot> ring;
     size_t head = 0;                    /* slot the walk takes from */
     bool ended = false;                 /* the walk has taken the stream's last byte */
@@ -104,6 +108,7 @@ struct FdFeeder {
     {
         uint64_t pos = 0;               /* bytes of the source read so far */
         std::vector<uint8_t> tail;
+        tail.swap(pre);                 /* a pipe's first bytes were read with its header */
         size_t k = 0;
         for (;;) {
             Slot *s;
@@ -116,10 +121,21 @@ struct FdFeeder {
             uint64_t have = tail.size();
             if (have) memcpy(s->p, tail.data(), have);
             tail.clear();
+            if (have > slot_cap) { std::lock_guard<std::mutex> lk(mu); too_long = true; s->n = 0; s->last = true; s->state = 1; cv.notify_all(); return; }
             const uint64_t want = std::min<uint64_t>(slot_cap - have, len - pos);
-            const int64_t got = want ? xm_pread_parallel(fd, s->p + have, want, off + (int64_t)pos, threads) : 0;
+            int64_t got = 0;
+            if (want && seekable) got = xm_pread_parallel(fd, s->p + have, want, off + (int64_t)pos, threads);
+            else if (want) {
+                /* a pipe: whatever arrives, until the slot is full or the writer closes its end */
+                while ((uint64_t)got < want) {
+                    const ssize_t r = read(fd, s->p + have + (uint64_t)got, (size_t)std::min<uint64_t>(want - (uint64_t)got, 1u << 30));
+                    if (r < 0) { if (errno == EINTR) continue; got = -1; break; }
+                    if (r == 0) break;
+                    got += r;
+                }
+            }
             if (got < 0) { std::lock_guard<std::mutex> lk(mu); failed = true; s->n = 0; s->last = true; s->state = 1; cv.notify_all(); return; }
-            if ((uint64_t)got < want) len = pos + (uint64_t)got;                 /* the file is shorter than announced */
+            if ((uint64_t)got < want) len = pos + (uint64_t)got;                 /* the source ends here (a pipe's length is only known now) */
             pos += (uint64_t)got;
             have += (uint64_t)got;
             const bool eof = pos >= len;

@@ -482,6 +482,8 @@ def main(argv=None):
         if not args.primary_sam:
             raise NotImplementedError("the sharded walk (one process per GPU) takes SAM inputs")
         return _main_sharded(args, tag_func, outs, skip)
+    if args.primary_sam and (_regular_fd(args.primary_sam) is None or _regular_fd(args.secondary_sam) is None):
+        return _main_streams(args, tag_func, outs, skip)
     if args.bgzf:
         return _main_bgzf(args, tag_func, outs, skip)
     if args.primary_sam:
@@ -496,6 +498,29 @@ def main(argv=None):
         if f:
             f.flush()
     output_summary(counts)
+
+
+def _main_streams(args, tag_func, outs, skip):
+    """Inputs that cannot seek -- pipes from two aligners, process substitutions (the reference refuses them,
+    xm.py:586-587): headers and walk in one library call on the descriptors themselves (xm_classify_streams)."""
+    files = [outs[k] for k in outs]
+    fds = []
+    for f in files:
+        if f:
+            f.flush()
+            fds.append(f.fileno())
+        else:
+            fds.append(-1)
+    mode = _lib.MODE_SE if not args.paired else (_lib.MODE_PE_CONSERVATIVE if args.conservative else _lib.MODE_PE_LIBERAL)
+    ctx = _lib.default_context()
+    opts = ctx.opts(mode, _SCORE_SRC[tag_func], skip, float(args.min_score), sum(1 << b for b, f in enumerate(fds) if f >= 0))
+    rc, res = ctx.classify_streams(args.primary_sam.fileno(), args.secondary_sam.fileno(), fds, opts, __version__,
+                                   _lib.OUT_BGZF if args.bgzf else 0)
+    if rc == _lib.XM_ERR_INDEX:
+        raise IndexError('string index out of range')
+    if rc != _lib.XM_OK:
+        _raise_for(rc, ctx, res)
+    output_summary(_counter(res, mode != _lib.MODE_SE))
 
 
 def _main_bgzf(args, tag_func, outs, skip):
