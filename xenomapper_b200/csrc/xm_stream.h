@@ -118,11 +118,12 @@ struct FdFeeder {
                 if (stop) return;
                 s = &ring[k];
             }
-            uint64_t have = tail.size();
+            /* what is left over from before (the tail behind the last slot's final newline; a pipe's first bytes) comes
+             * first, as much of it as fits */
+            uint64_t have = std::min<uint64_t>(tail.size(), slot_cap);
             if (have) memcpy(s->p, tail.data(), have);
-            tail.clear();
-            if (have > slot_cap) { std::lock_guard<std::mutex> lk(mu); too_long = true; s->n = 0; s->last = true; s->state = 1; cv.notify_all(); return; }
-            const uint64_t want = std::min<uint64_t>(slot_cap - have, len - pos);
+            tail.erase(tail.begin(), tail.begin() + (long)have);
+            const uint64_t want = tail.empty() ? std::min<uint64_t>(slot_cap - have, len - pos) : 0;
             int64_t got = 0;
             if (want && seekable) got = xm_pread_parallel(fd, s->p + have, want, off + (int64_t)pos, threads);
             else if (want) {
@@ -138,12 +139,12 @@ struct FdFeeder {
             if ((uint64_t)got < want) len = pos + (uint64_t)got;                 /* the source ends here (a pipe's length is only known now) */
             pos += (uint64_t)got;
             have += (uint64_t)got;
-            const bool eof = pos >= len;
+            const bool eof = pos >= len && tail.empty();
             uint64_t n = have;
             if (!eof) {
                 n = cut_after_last_newline(s->p, have);
                 if (n == 0) { std::lock_guard<std::mutex> lk(mu); too_long = true; s->n = 0; s->last = true; s->state = 1; cv.notify_all(); return; }
-                tail.assign(s->p + n, s->p + have);
+                tail.insert(tail.begin(), s->p + n, s->p + have);
             }
             {
                 std::lock_guard<std::mutex> lk(mu);
