@@ -879,43 +879,184 @@ int xm_bam_render_host(xm_ctx *c, const void *bam, uint64_t len, const void **te
     return XM_OK;
 }
 
+/* BAM as a source of the chunked walk: each call inflates the next BGZF blocks on the host (thread pool), follows the
+ * record chain, uploads the whole records and renders them as SAM text straight into the walk's staging buffer.  What
+ * is resident at any time is one batch, not the file: the inflated size of a BAM no longer has to fit the GPU. */
+struct BamProducer : DevSource {
+    xm_ctx *c = nullptr;
+    int s = 0;
+    const uint8_t *bam = nullptr;
+    uint64_t bam_len = 0;
+    std::vector<BgzfBlock> blocks;
+    size_t blk = 0;
+    bool have_header = false;
+    uint64_t left = 0;                  /* bytes of an incomplete record at the front of the pinned buffer */
+    uint32_t n_ref = 0;
+    uint8_t *d_names = nullptr;
+    /* a batch that was inflated but did not fit the room it was offered: rendered by the next call */
+    bool pending = false;
+    std::vector<uint64_t> pend_rec;
+    uint64_t pend_have = 0, pend_end = 0, full_cap = 0;
+
+    int next(uint8_t *dev_dst, uint64_t max_bytes, uint64_t &n_out, bool &final, std::string &err) override
+    {
+        n_out = 0; final = false;
+        if (max_bytes == 0) return XM_OK;
+        cudaStream_t st = c->be.st;
+        const uint64_t budget = std::max<uint64_t>(max_bytes / 6, 1u << 16);          /* a BAM byte renders to at most ~5 text bytes */
+        std::vector<uint64_t> rec;
+        uint64_t have = left, cursor = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            uint64_t o = 0;
+            int rc = XM_OK;
+            bool again = false;
+            if (pending) { rec.swap(pend_rec); have = pend_have; o = pend_end; pending = false; again = true; goto render; }
+            {
+            /* the next blocks, up to the budget (at least one) */
+            size_t last = blk;
+            uint64_t add = 0;
+            while (last < blocks.size() && (last == blk || add + blocks[last].out_len <= budget)) add += blocks[last++].out_len;
+            if ((rc = reserve_host_keep(have + add + 64))) { err = c->err; return rc; }
+            if (last > blk) {
+                std::string e;
+                if (!bgzf_inflate(bam, blocks, blk, last, c->h_bam[s].p + have - blocks[blk].out_off, host_threads(), e)) { err = "BAM input: " + e; return XM_ERR_IO; }
+            }
+            have += add;
+            blk = last;
+            uint8_t *h = c->h_bam[s].p;
+            if (!have_header) {
+                BamIndex ix;
+                std::string e;
+                if (!bam_index(h, have, ix, true, e)) {
+                    if (blk < blocks.size()) continue;            /* the header goes on in the next blocks */
+                    err = "BAM input: " + e; return XM_ERR_IO;
+                }
+                have_header = true;
+                cursor = ix.first_record;
+                n_ref = (uint32_t)ix.ref_off.size() - 1;
+                const uint64_t ref_bytes = ix.ref_off.size() * 4 + ix.ref_names.size() + 16;
+                if ((rc = reserve_dev(c, c->d_bam_ref[s], ref_bytes))) { err = c->err; return rc; }
+                cudaMemcpyAsync(c->d_bam_ref[s].p, ix.ref_off.data(), ix.ref_off.size() * 4, cudaMemcpyHostToDevice, st);
+                d_names = c->d_bam_ref[s].p + ix.ref_off.size() * 4;
+                if (!ix.ref_names.empty()) cudaMemcpyAsync(d_names, ix.ref_names.data(), ix.ref_names.size(), cudaMemcpyHostToDevice, st);
+                cudaStreamSynchronize(st);
+            }
+            /* whole records in [cursor, have) */
+            o = cursor;
+            while (o + 4 <= have) {
+                const uint32_t bs = rd_u32(h + o);
+                if (bs < 32) { err = "corrupt BAM record"; return XM_ERR_IO; }
+                if (o + 4 + (uint64_t)bs > have) break;
+                rec.push_back(o);
+                o += 4 + (uint64_t)bs;
+            }
+            if (rec.empty() && blk < blocks.size()) { cursor = o; continue; }       /* a record larger than the batch: take more blocks */
+            if (blk == blocks.size() && o != have) { err = "truncated BAM record at the end of the file"; return XM_ERR_IO; }
+            }
+        render:
+            uint8_t *h = c->h_bam[s].p;
+            final = blk == blocks.size();
+            const uint64_t n = rec.size();
+            if (!again) {
+                c->bam_stats.inflate_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                c->bam_stats.inflated_bytes += have - left;
+                c->bam_stats.records += n;
+            }
+            if (n) {
+                const uint64_t lo = rec[0], hi = o, nb = (n + 1023) / 1024;
+                for (auto &r : rec) r -= lo;
+                if ((rc = reserve_dev(c, c->d_bam[s], hi - lo + 64)) || (rc = reserve_dev(c, c->d_bam_rec[s], n * 8)) ||
+                    (rc = reserve_dev(c, c->d_bam_len[s], n * 8 + 16)) || (rc = reserve_dev(c, c->d_bam_sum[s], nb * 8 + 16))) { err = c->err; return rc; }
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0); cudaEventCreate(&e1);
+                cudaMemcpyAsync(c->d_bam[s].p, h + lo, hi - lo, cudaMemcpyHostToDevice, st);
+                cudaMemcpyAsync(c->d_bam_rec[s].p, rec.data(), n * 8, cudaMemcpyHostToDevice, st);
+                unsigned long long *d_err = (unsigned long long *)(c->d_bam_sum[s].p + nb * 8);
+                const unsigned long long no_err = BAM_NO_ERROR;
+                cudaMemcpyAsync(d_err, &no_err, 8, cudaMemcpyHostToDevice, st);
+                BamDev B;
+                B.data = c->d_bam[s].p; B.rec = (const uint64_t *)c->d_bam_rec[s].p; B.n = n;
+                B.ref_off = (const uint32_t *)c->d_bam_ref[s].p; B.ref_names = d_names; B.n_ref = n_ref;
+                uint32_t *d_len = (uint32_t *)c->d_bam_len[s].p, *d_loff = d_len + n + (n & 1);
+                cudaEventRecord(e0, st);
+                k_bam_len<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(B, d_len, d_err);
+                k_bam_scan_blocks<<<(unsigned)nb, 1024, 0, st>>>(d_len, n, d_loff, (unsigned long long *)c->d_bam_sum[s].p);
+                std::vector<unsigned long long> sums(nb + 1);
+                cudaMemcpyAsync(sums.data(), c->d_bam_sum[s].p, (nb + 1) * 8, cudaMemcpyDeviceToHost, st);
+                if (cudaStreamSynchronize(st) != cudaSuccess) { err = "BAM length kernels failed"; return XM_ERR_CUDA; }
+                if (sums[nb] != BAM_NO_ERROR) {
+                    cudaEventDestroy(e0); cudaEventDestroy(e1);
+                    if ((sums[nb] & 0xff) == BAM_E_FLOAT) { err = "a BAM record has a float aux value (f or B:f): not rendered on the device"; return XM_ERR_UNSUPPORTED; }
+                    err = "corrupt BAM record"; return XM_ERR_IO;
+                }
+                unsigned long long run = 0;
+                for (uint64_t k = 0; k < nb; ++k) { const unsigned long long v = sums[k]; sums[k] = run; run += v; }
+                if (run > max_bytes) {
+                    cudaEventDestroy(e0); cudaEventDestroy(e1);
+                    if (max_bytes >= full_cap) { err = "BAM records render to more text than a staging step holds"; return XM_ERR_UNSUPPORTED; }
+                    /* offered less than a whole step (the walk buffer is full of carried records): keep the batch for the next call */
+                    for (auto &r : rec) r += lo;
+                    pend_rec.swap(rec); pend_have = have; pend_end = o; pending = true;
+                    final = false;
+                    return XM_OK;
+                }
+                cudaMemcpyAsync(c->d_bam_sum[s].p, sums.data(), nb * 8, cudaMemcpyHostToDevice, st);
+                k_bam_render<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(B, d_loff, (const unsigned long long *)c->d_bam_sum[s].p, dev_dst);
+                cudaEventRecord(e1, st);
+                if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "BAM render kernel failed"; return XM_ERR_CUDA; }
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+                c->bam_stats.render_ms += ms;
+                c->bam_stats.text_bytes += run;
+                c->bam_stats.n_launches += 3;
+                n_out = run;
+            }
+            /* the incomplete record stays for the next call */
+            left = have - o;
+            if (left) memmove(h, h + o, left);
+            return XM_OK;
+        }
+    }
+    /* pinned buffer of the inflated batch, grown without losing the bytes at its front */
+    int reserve_host_keep(uint64_t need)
+    {
+        HostBuf &b = c->h_bam[s];
+        if (need <= b.cap && b.p) return XM_OK;
+        uint8_t *np_ = nullptr;
+        const uint64_t cap = std::max<uint64_t>(need, b.cap * 2);
+        if (cudaHostAlloc((void **)&np_, cap + 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(c, XM_ERR_NOMEM, "cudaHostAlloc: out of memory"); }
+        if (b.p) { if (left) memcpy(np_, b.p, left); cudaFreeHost(b.p); }
+        b.p = np_; b.cap = cap;
+        return XM_OK;
+    }
+};
+
 int xm_classify_bam_host(xm_ctx *c, const void *prim_bam, uint64_t prim_len, const void *sec_bam, uint64_t sec_len,
                          const xm_opts *opts, xm_result *res)
 {
     if (!c || !opts || !res || !prim_bam || !sec_bam) return XM_ERR_ARG;
     cudaSetDevice(c->device);
-    recycle_bins(c);
     memset(res, 0, sizeof *res);
-    uint8_t *d_txt[2] = {nullptr, nullptr};
-    uint64_t n_txt[2] = {0, 0};
-    int rc;
-    if ((rc = bam_to_device_text(c, prim_bam, prim_len, 0, &d_txt[0], &n_txt[0]))) return res->status = rc;
-    if ((rc = bam_to_device_text(c, sec_bam, sec_len, 1, &d_txt[1], &n_txt[1]))) return res->status = rc;
-    xm_opts o = *opts;
-    o.skip_repeated &= 1;
-    std::string msg;
-    /* sizing pass (nothing is written), then the walk into exactly sized bins */
-    uint8_t *none[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    uint64_t cap[6] = {0, 0, 0, 0, 0, 0};
-    xm_result dry;
-    rc = walk_resident(c->be, c->scratch, StreamBuf{d_txt[0], n_txt[0]}, StreamBuf{d_txt[1], n_txt[1]}, o, none, cap, c->debug, &dry, msg);
-    if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM) { c->err = msg; return res->status = rc; }
-    uint8_t *outs[6];
-    for (int b = 0; b < 6; ++b) {
-        cap[b] = ((o.enabled_bins >> b) & 1u) ? dry.out_len[b] : 0;
-        if ((rc = reserve_dev(c, c->d_out[0][b], cap[b] + 16))) return res->status = rc;
-        outs[b] = c->d_out[0][b].p;
+    BamProducer prod[2];
+    HostIn in[2];
+    const void *src[2] = {prim_bam, sec_bam};
+    const uint64_t len[2] = {prim_len, sec_len};
+    const uint32_t launches0 = c->bam_stats.n_launches;
+    for (int s = 0; s < 2; ++s) {
+        prod[s].c = c; prod[s].s = s; prod[s].bam = (const uint8_t *)src[s]; prod[s].bam_len = len[s];
+        uint64_t total = 0;
+        std::string err;
+        if (!bgzf_scan(prod[s].bam, len[s], prod[s].blocks, total, err)) return res->status = fail(c, XM_ERR_IO, "BAM input: " + err);
+        c->bam_stats.bam_bytes += len[s];
+        in[s].prod = &prod[s];
+        in[s].len = total * 3 + 4096;                   /* an estimate of the text: sizes the staging steps of small files */
     }
-    rc = walk_resident(c->be, c->scratch, StreamBuf{d_txt[0], n_txt[0]}, StreamBuf{d_txt[1], n_txt[1]}, o, outs, cap, c->debug, res, msg);
-    c->err = msg;
-    res->n_launches += dry.n_launches + c->bam_stats.n_launches;
-    if (rc == XM_ERR_CUDA || rc == XM_ERR_NOMEM) return rc;
-    uint64_t biggest = 4096;
-    for (int b = 0; b < 6; ++b) biggest = std::max<uint64_t>(biggest, res->out_len[b]);
-    c->block_bytes = std::min<uint64_t>(biggest, 256ull << 20);
-    for (int b = 0; b < 6; ++b)
-        if (((o.enabled_bins >> b) & 1u) && res->out_len[b]) { const int r2 = bin_append_d2h(c, b, outs[b], res->out_len[b]); if (r2) return r2; }
-    if (cudaStreamSynchronize(c->dl) != cudaSuccess) return fail(c, XM_ERR_CUDA, "D2H copy failed");
+    const uint64_t step = std::max<uint64_t>(std::min<uint64_t>(chunk_bytes(), std::max(in[0].len, in[1].len) + 64), 64);     /* stream_walk's chunk */
+    prod[0].full_cap = prod[1].full_cap = step;
+    const int rc = stream_walk(c, in, nullptr, opts, res);
+    res->n_launches += c->bam_stats.n_launches - launches0;
     return rc;
 }
 

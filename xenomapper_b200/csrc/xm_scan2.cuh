@@ -65,6 +65,16 @@ struct SpanInfo {
  * (Round 2 tried a three-pass version -- bare mask steps, 512-byte tail steps, one index pass per span -- with
  * 15 % fewer instructions: 10 % slower in k_scan2, 1.5 % faster in k_classify2; these kernels are paced by the
  * dependent latencies a warp strings together, not by its instruction count.  profiles/r02_kernel_experiments.md) */
+#ifdef XM_ASCII_MASKS
+__device__ __forceinline__ void masks16_ascii(const uint4 v, uint32_t &W, uint32_t &T, uint32_t &acc)
+{
+    auto wf = [](uint32_t w) { return ~(w + 0x5f5f5f5fu) & 0x80808080u; };               /* byte + 0x5f: bit 7 set iff byte >= 0x21 */
+    acc |= v.x | v.y;
+    acc |= v.z | v.w;
+    W = pack16(wf(v.x), wf(v.y), wf(v.z), wf(v.w));
+    T = pack16(tab_mask_loose(v.x), tab_mask_loose(v.y), tab_mask_loose(v.z), tab_mask_loose(v.w));
+}
+#endif
 template <class C, bool SPLIT>
 __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span_lo, bool need_prev, uint32_t *tbm, uint32_t *nlm, uint16_t *trk, uint16_t *starts)
 {
@@ -102,6 +112,9 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
     for (;;) {
     nst = 0; tab_run = 0; j0 = 0; j1 = 0; bad = false;
     bool adj = false;
+#ifdef XM_ASCII_MASKS
+    uint32_t hi_acc = 0;
+#endif
     if (live) {
         if (win0 == 0) { if (lane == 0) starts[0] = 0; nst = 1; }      /* the stream's first byte opens a line */
         /* two consecutive 32-byte words per lane and step (2 KiB per warp), so the scan, the shuffles and the loop
@@ -129,11 +142,21 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
                 const uint4 v2 = (INTERIOR || off + 32u < lim16) ? ld_src16(win + off + 32u, false) : filler;
                 const uint4 v3 = (INTERIOR || off + 48u < lim16) ? ld_src16(win + off + 48u, false) : filler;
                 uint32_t Wa, Ta, Wb, Tb;
+#ifdef XM_ASCII_MASKS
+                /* W by one add and one logic operation per word: exact while every byte is below 0x80; the words are ORed
+                 * into hi_acc and a span that saw a byte >= 0x80 gives up before its masks are used */
+                masks16_ascii(v0, Wa, Ta, hi_acc);
+                masks16_ascii(v1, Wb, Tb, hi_acc);
+                W0 = Wa | (Wb << 16); T0 = Ta | (Tb << 16);
+                masks16_ascii(v2, Wa, Ta, hi_acc);
+                masks16_ascii(v3, Wb, Tb, hi_acc);
+#else
                 masks16_span(v0, Wa, Ta);
                 masks16_span(v1, Wb, Tb);
                 W0 = Wa | (Wb << 16); T0 = Ta | (Tb << 16);
                 masks16_span(v2, Wa, Ta);
                 masks16_span(v3, Wb, Tb);
+#endif
                 W1 = Wa | (Wb << 16); T1 = Ta | (Tb << 16);
                 if (!INTERIOR && off + 64u > wbytes) {         /* the window's last words: bytes past its end do not count */
                     const uint32_t valid = wbytes - off;       /* 1..63 */
@@ -182,7 +205,11 @@ __device__ __forceinline__ SpanInfo span_front(const StreamBuf &B, uint64_t span
             if (SPLIT && step_end <= wbytes && step_end <= lastp) step(std::true_type{}, wb);
             else step(std::false_type{}, wb);
         }
+#ifdef XM_ASCII_MASKS
+        adj = __any_sync(0xffffffffu, adj || (hi_acc & 0x80808080u));
+#else
         adj = __any_sync(0xffffffffu, adj);
+#endif
         if (nst > (uint32_t)C::LQ || adj) bad = true;
     }
     __syncwarp();

@@ -188,13 +188,22 @@ struct FdFeeder {
     }
 };
 
+/* a source that puts whole lines straight into a device buffer (BAM input: inflate on the host, render on the GPU) */
+struct DevSource {
+    virtual ~DevSource() {}
+    /* up to max_bytes of SAM text into dev_dst; n = bytes written, final = the stream ends with them.  Returns an xm_status. */
+    virtual int next(uint8_t *dev_dst, uint64_t max_bytes, uint64_t &n, bool &final, std::string &err) = 0;
+    bool ended = false;
+};
+
 /* one input stream on the host */
 struct HostIn {
     const uint8_t *mem = nullptr;      /* memory source (pageable or pinned) ... */
     uint64_t len = 0;
-    FdFeeder *feed = nullptr;          /* ... or a descriptor read ahead by its own thread */
+    FdFeeder *feed = nullptr;          /* ... or a descriptor read ahead by its own thread ... */
+    DevSource *prod = nullptr;         /* ... or a producer of device-resident text */
     uint64_t pos = 0;                  /* next byte to send */
-    bool exhausted() const { return feed ? feed->ended : pos >= len; }
+    bool exhausted() const { return prod ? prod->ended : (feed ? feed->ended : pos >= len); }
 };
 
 /* device side of one input stream: two walk buffers and two staging buffers used alternately */
@@ -235,6 +244,16 @@ inline int walk_stream(BE &be, Scratch &sc, HostIn in[2], DevIn dev[2], uint8_t 
         for (int s = 0; s < 2; ++s) {
             staged[slot][s] = 0; staged_final[slot][s] = false;
             if (in[s].exhausted()) continue;
+            if (in[s].prod) {
+                uint64_t n = 0;
+                bool fin = false;
+                const int prc = in[s].prod->next(dev[s].stage[slot], std::min<uint64_t>(room[s], plan.chunk), n, fin, errmsg);
+                if (prc) { io_rc = prc; return; }
+                staged[slot][s] = n; staged_final[slot][s] = fin;
+                in[s].prod->ended = fin;
+                in[s].pos += n;
+                continue;
+            }
             const uint8_t *src = nullptr;
             uint64_t avail = 0;
             bool last_piece = false;
