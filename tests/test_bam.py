@@ -127,3 +127,72 @@ def test_bam_walk_on_synthetic_pairs_equals_the_oracle(ctx, style, mode, score, 
     assert rc == 0, ctx.error()
     assert list(res.counts) == ref["counts"]
     assert outs == ref["outputs"]
+
+
+def _literal_bam(aux_bytes):
+    """A one-record BAM built byte by byte from the layout tables of the SAM/BAM specification (section 4.2: the
+    alignment record, 4.2.4: auxiliary data) -- literal hex for every aux value, no encoder shared with
+    tests/_bamwriter.py.  Record: read `r1`, unmapped (refID -1, pos -1, FLAG 4), l_seq 4 = ACGT, quals 30 31 32 33."""
+    import struct
+    import zlib
+    read_name = b"r1\0"
+    core = struct.pack("<iiBBHHHIiii", -1, -1, len(read_name), 0, 4680, 0, 4, 4, -1, -1, 0)   # refID pos l_read_name mapq bin n_cigar flag l_seq next_refID next_pos tlen
+    seq = bytes([0x12, 0x48])                   # A=1 C=2 | G=4 T=8 (section 4.2.3: "=ACMGRSVTWYHKDBN")
+    qual = bytes([30, 31, 32, 33])
+    body = core + read_name + seq + qual + aux_bytes
+    rec = struct.pack("<I", len(body)) + body
+    text = b"@HD\tVN:1.6\n"
+    payload = b"BAM\1" + struct.pack("<I", len(text)) + text + struct.pack("<I", 0) + rec
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    data = co.compress(payload) + co.flush()
+    block = (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(data) + 25) + data +
+             struct.pack("<II", zlib.crc32(payload), len(payload)))
+    return block + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+# aux bytes (tag, type, little-endian value) -> the SAM text the specification prescribes (section 1.5: every
+# integer type prints as `i`; section 4.2.4: A one character, Z / H NUL-terminated, B: sub-type, count, values)
+AUX_VECTORS = [
+    (bytes.fromhex("5841 63 fe"), "XA:i:-2"),                                   # c  int8
+    (bytes.fromhex("5842 43 ff"), "XB:i:255"),                                  # C  uint8
+    (bytes.fromhex("5843 73 0080"), "XC:i:-32768"),                             # s  int16
+    (bytes.fromhex("5844 53 ffff"), "XD:i:65535"),                              # S  uint16
+    (bytes.fromhex("5845 69 ffffffff"), "XE:i:-1"),                             # i  int32
+    (bytes.fromhex("5846 69 00000080"), "XF:i:-2147483648"),
+    (bytes.fromhex("5847 49 ffffffff"), "XG:i:4294967295"),                     # I  uint32
+    (bytes.fromhex("5848 41 7a"), "XH:A:z"),                                    # A  printable character
+    (bytes.fromhex("5849 5a 68656c6c6f20776f726c64 00"), "XI:Z:hello world"),   # Z  string with a space
+    (bytes.fromhex("584a 48 314145333031 00"), "XJ:H:1AE301"),                  # H  hex string (the specification's own example value)
+    (bytes.fromhex("584b 42 63 03000000 01ff7f"), "XK:B:c,1,-1,127"),           # B:c
+    (bytes.fromhex("584c 42 43 02000000 00ff"), "XL:B:C,0,255"),                # B:C
+    (bytes.fromhex("584d 42 73 02000000 0080ff7f"), "XM:B:s,-32768,32767"),     # B:s
+    (bytes.fromhex("584e 42 53 01000000 ffff"), "XN:B:S,65535"),                # B:S
+    (bytes.fromhex("584f 42 69 02000000 ffffffff00000080"), "XO:B:i,-1,-2147483648"),   # B:i
+    (bytes.fromhex("5850 42 49 01000000 ffffffff"), "XP:B:I,4294967295"),       # B:I
+    (bytes.fromhex("5851 42 43 00000000"), "XQ:B:C"),                           # an empty array
+]
+
+
+@pytest.mark.gpu
+def test_gpu_renders_literal_aux_vectors(ctx):
+    """every aux type the renderer prints, from hand-written bytes: pins c s S i I A H B:* (the fixture twins only
+    hold C and Z) against the specification's tables rather than against the test-side writer"""
+    for raw, text in AUX_VECTORS:
+        line = ctx.bam_render_host(_literal_bam(raw))
+        assert line == b"r1\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\t?@AB\t" + text.encode() + b"\n", (raw.hex(), line)
+    allraw = b"".join(r for r, _ in AUX_VECTORS)
+    alltext = "\t".join(t for _, t in AUX_VECTORS)
+    assert ctx.bam_render_host(_literal_bam(allraw)) == b"r1\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\t?@AB\t" + alltext.encode() + b"\n"
+    assert ctx.bam_render_host(_literal_bam(b"")) == b"r1\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\t?@AB\n"
+
+
+def test_literal_bam_is_well_formed():
+    """the hand-built container inflates with Python's gzip and carries the record it claims (no GPU)"""
+    import gzip
+    import struct
+    raw = gzip.decompress(_literal_bam(AUX_VECTORS[0][0]))
+    assert raw[:4] == b"BAM\1"
+    l_text = struct.unpack_from("<I", raw, 4)[0]
+    assert raw[8:8 + l_text] == b"@HD\tVN:1.6\n"
+    block_size = struct.unpack_from("<I", raw, 8 + l_text + 4)[0]
+    assert 8 + l_text + 4 + 4 + block_size == len(raw)
