@@ -49,6 +49,7 @@ struct EmuBackend {
     int zero(void *p, size_t n) { memset(p, 0, n); return 0; }
     int write(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
     int read(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
+    int read_words(const void *const src[], int n, unsigned long long *dst) { for (int k = 0; k < n; ++k) memcpy(dst + k, src[k], 8); return 0; }
     int sync() { return 0; }
     int upload(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
     int upload_wait() { return 0; }

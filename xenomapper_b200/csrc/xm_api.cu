@@ -63,6 +63,15 @@ struct DeviceBackend {
     int zero(void *p, size_t n) { return n ? chk(cudaMemsetAsync(p, 0, n, st)) : 0; }
     int write(void *d, const void *s, size_t n) { return chk(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st)) || chk(cudaStreamSynchronize(st)); }
     int read(void *d, const void *s, size_t n) { return chk(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st)) || chk(cudaStreamSynchronize(st)); }
+    unsigned long long *h_words = nullptr;        /* pinned landing place of read_words */
+    int read_words(const void *const src[], int n, unsigned long long *dst)
+    {
+        if (!h_words && chk(cudaHostAlloc((void **)&h_words, 64 * 8, cudaHostAllocDefault))) return 1;
+        for (int k = 0; k < n; ++k) if (chk(cudaMemcpyAsync(h_words + k, src[k], 8, cudaMemcpyDeviceToHost, st))) return 1;
+        if (chk(cudaStreamSynchronize(st))) return 1;
+        for (int k = 0; k < n; ++k) dst[k] = h_words[k];
+        return 0;
+    }
     int sync() { return chk(cudaStreamSynchronize(st)); }
     void tick(int k) { cudaEventRecord(ev[k], st); }
     float elapsed(int a, int b)
@@ -277,6 +286,7 @@ void xm_destroy(xm_ctx *c)
     for (auto &b : c->pool) cudaFreeHost(b.p);
     if (c->dl) cudaStreamDestroy(c->dl);
     for (int k = 0; k < 6; ++k) if (c->be.ev[k]) cudaEventDestroy(c->be.ev[k]);
+    if (c->be.h_words) cudaFreeHost(c->be.h_words);
     if (c->be.st) cudaStreamDestroy(c->be.st);
     for (auto s : c->copy_st) if (s) cudaStreamDestroy(s);
     delete c;

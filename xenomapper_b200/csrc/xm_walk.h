@@ -12,6 +12,7 @@
  *     int   zero(void *, size_t)
  *     int   fill64(void *, unsigned long long v, size_t n)
  *     int   read(void *host_dst, const void *src, size_t)     (D2H, synchronous)
+ *     int   read_words(const void *const src[], int n, unsigned long long *dst)   n 8-byte words in one round trip
  *     int   write(void *dst, const void *host_src, size_t)    (H2D, synchronous)
  *     std::string last_error()
  *     int   scan(const ScanArgs &, bool small)
@@ -395,10 +396,10 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
                 res->ms_kernel[0] = be.elapsed(3, 4); res->ms_kernel[1] = be.elapsed(4, 1); res->ms_kernel[2] = be.elapsed(1, 5); res->ms_kernel[3] = be.elapsed(5, 2);
                 /* what the fused kernels leave in Globals and the code below reads */
                 if (n > 0) {
-                    unsigned long long p0 = 0, p1 = 0;
-                    be.read(&p0, sc.scp.start, 8);
-                    be.read(&p1, sc.scp.start + n, 8);
-                    G.bytes_in[0] = p1 - p0;
+                    const void *at[2] = {sc.scp.start, sc.scp.start + n};
+                    unsigned long long v[2] = {0, 0};
+                    be.read_words(at, 2, v);
+                    G.bytes_in[0] = v[1] - v[0];
                 }
                 rows_walk = true;
                 break;
@@ -496,23 +497,22 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
             ctl->end_off[k] = G.end_off[k];
             ctl->stopped[k] = G.end_off[k] < (k ? S.len : P.len);
         }
-        if (ctl->want_tail && n > 0) {
-            unsigned long long v = 0;
-            be.read(&v, (rows_walk ? sc.scp.start : sc.p_start) + (n - 1), 8); ctl->last_p = v;
-            be.read(&v, sc.sc.start + (n - 1), 8); ctl->last_s = v;
-        }
+    }
+    /* the few words of the row arrays the host still needs, in one round trip: where the last yielded record of each
+     * stream starts (chunked walks carry from there), first and one-past-last offset of the secondary rows */
+    if (n > 0) {
+        const bool tail = ctl && ctl->want_tail;
+        const void *at[4] = {sc.sc.start, sc.sc.start + n, sc.sc.start + (n - 1), (rows_walk ? sc.scp.start : (tail ? sc.p_start : sc.sc.start)) + (n - 1)};
+        unsigned long long v[4] = {0, 0, 0, 0};
+        be.read_words(at, tail ? 4 : 2, v);
+        res->bytes_in[1] = v[1] - v[0];
+        if (tail) { ctl->last_s = v[2]; ctl->last_p = v[3]; }
     }
     for (int k = 0; k < 2; ++k)
         if (G.n_stream[k] > 1000 && G.end_off[k] > 0) sc.line_bytes[k] = (double)G.end_off[k] / (double)G.n_stream[k];
     for (int k = 0; k < 36; ++k) res->counts[k] = G.counts[k];
     for (int b = 0; b < 6; ++b) res->out_len[b] = G.out_len[b];
     res->bytes_in[0] = G.bytes_in[0];
-    if (n > 0) {
-        unsigned long long s0 = 0, s1 = 0;
-        be.read(&s0, sc.sc.start, 8);
-        be.read(&s1, sc.sc.start + n, 8);
-        res->bytes_in[1] = s1 - s0;
-    }
     for (int b = 0; b < 6; ++b)
         if (((o.enabled_bins >> b) & 1u) && G.out_len[b] > out_cap[b]) {
             errmsg = "output buffer too small for bin " + std::to_string(b);
