@@ -17,15 +17,70 @@ sys.path.insert(0, ROOT)
 DIR = os.path.join(ROOT, "tmp_bam")
 
 
-def make(n):
+def _make_part(args):
+    """records [lo, lo + n) of both files as raw BAM record bytes, written to part files (one worker process)"""
+    lo, n, k, hdr1, hdr2 = args
     from tests import _bamwriter
-    from tests.test_bam import FULL_HEADER
     from xenomapper_b200 import synth
+    p, s = synth.generate(n, seed=7, style=synth.STYLE_PE_BOWTIE2, first=lo)
+    for name, text, hdr in (("p", p, hdr1), ("s", s, hdr2)):
+        refs = [dict(t.split(":", 1) for t in line.split("\t")[1:])["SN"] for line in hdr.split("\n") if line.startswith("@SQ")]
+        ref_ids = {r: i for i, r in enumerate(refs)}
+        raw = bytearray()
+        for line in bytes(text).decode().split("\n"):
+            if line:
+                raw += _bamwriter.record(line, ref_ids)
+        open(os.path.join(DIR, "%s.part%04d" % (name, k)), "wb").write(raw)
+    return k
+
+
+def _bgzf_part(args):
+    from tests import _bamwriter
+    path, lo, hi, level = args
+    with open(path, "rb") as f:
+        f.seek(lo)
+        data = f.read(hi - lo)
+    out = _bamwriter.bgzf(data, level=level)
+    return out[:-28]                       # without the end-of-file member
+
+
+def make(n, procs=None):
+    """N records per file; record conversion and deflate spread over `procs` processes"""
+    import multiprocessing as mp
+    import struct
+    from tests.test_bam import FULL_HEADER
     os.makedirs(DIR, exist_ok=True)
-    p, s = synth.generate(n, seed=7, style=synth.STYLE_PE_BOWTIE2)
+    procs = procs or min(os.cpu_count() or 1, 32)
     hdr2 = FULL_HEADER.replace("SN:chr", "SN:").replace("SN:M\t", "SN:MT\t")
-    open(os.path.join(DIR, "p.bam"), "wb").write(_bamwriter.sam_to_bam(FULL_HEADER, bytes(p), level=6))
-    open(os.path.join(DIR, "s.bam"), "wb").write(_bamwriter.sam_to_bam(hdr2, bytes(s), level=6))
+    per = (n + procs - 1) // procs
+    per += per & 1                             # pairs stay together
+    jobs = [(lo, min(per, n - lo), k, FULL_HEADER, hdr2) for k, lo in enumerate(range(0, n, per))]
+    with mp.get_context("fork").Pool(procs) as pool:
+        pool.map(_make_part, jobs)
+        for name, hdr in (("p", FULL_HEADER), ("s", hdr2)):
+            refs = []
+            for line in hdr.split("\n"):
+                if line.startswith("@SQ"):
+                    d = dict(t.split(":", 1) for t in line.split("\t")[1:])
+                    refs.append((d["SN"], int(d["LN"])))
+            text = hdr.encode()
+            raw_path = os.path.join(DIR, name + ".raw")
+            with open(raw_path, "wb") as f:
+                f.write(b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs)))
+                for rn, ln in refs:
+                    f.write(struct.pack("<i", len(rn) + 1) + rn.encode() + b"\0" + struct.pack("<i", ln))
+                for k in range(len(jobs)):
+                    part = os.path.join(DIR, "%s.part%04d" % (name, k))
+                    f.write(open(part, "rb").read())
+                    os.unlink(part)
+            size = os.path.getsize(raw_path)
+            step = 0xff00 * 64
+            pieces = pool.map(_bgzf_part, [(raw_path, lo, min(lo + step, size), 1) for lo in range(0, size, step)])
+            with open(os.path.join(DIR, name + ".bam"), "wb") as f:
+                for piece in pieces:
+                    f.write(piece)
+                f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+            os.unlink(raw_path)
 
 
 def main():

@@ -163,6 +163,7 @@ def get_tag_with_ZS_as_XS(sam_line, tag='AS'):
 
 
 _CIGAR_OP = re.compile(r'([0-9]+)([MIDNSHPX=])')
+_UNIVERSAL_NEWLINE = re.compile(r'\r\n|\r|\n')
 
 
 def get_cigarbased_AS_tag(sam_line, tag='AS'):
@@ -226,8 +227,9 @@ class ReadPairs:
 
     def __iter__(self):
         p, s = self.record_regions()
-        l1 = iter(p.decode('utf-8', 'surrogateescape').split('\n'))
-        l2 = iter(s.decode('utf-8', 'surrogateescape').split('\n'))
+        # lines end as the reference's 'rt' files end them (universal newlines: "\n", "\r\n" or a lone "\r")
+        l1 = iter(_UNIVERSAL_NEWLINE.split(p.decode('utf-8', 'surrogateescape')))
+        l2 = iter(_UNIVERSAL_NEWLINE.split(s.decode('utf-8', 'surrogateescape')))
         a, b = next(l1, '').split(), next(l2, '').split()
         while a and b:
             assert a[0] == b[0]
