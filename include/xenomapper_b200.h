@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define XM_ABI_VERSION 5
+#define XM_ABI_VERSION 6
 
 /* States and bins share one numbering: the order of the reference's output
  * arguments (xm.py:291-297).  counts[] is indexed [state] for single-end and
@@ -271,10 +271,13 @@ int xm_bam_header_text(const void *bam, uint64_t len, char *dst, uint64_t cap, u
  * until the next BAM call): what iterating getBamReadPairs needs. */
 int xm_bam_render_host(xm_ctx *ctx, const void *bam, uint64_t len, const void **text, uint64_t *text_len);
 typedef struct xm_bam_stats {
-    double inflate_s;        /* host wall time: BGZF scan + inflate + record chain */
-    float render_ms;         /* device time of the three BAM kernels */
+    double inflate_s;        /* wall time from the BGZF bytes to record offsets on the device: upload, inflate, record chain */
+    float render_ms;         /* device time of the three BAM text kernels */
     uint32_t n_launches;
     uint64_t bam_bytes, inflated_bytes, text_bytes, records;
+    double upload_s;         /* of inflate_s: pageable host memory -> device (the compressed bytes) */
+    float inflate_ms;        /* device time of k_bgzf_inflate */
+    uint32_t chain_repairs;  /* segments of the record chain whose guessed entry was not the true one */
 } xm_bam_stats;
 int xm_bam_get_stats(xm_ctx *ctx, xm_bam_stats *out, int reset);
 

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "xm_emu.cpp")
 SO = os.path.join(HERE, "emu", "libxm_emu.so")
 DEPS = [SRC] + [os.path.join(ROOT, "xenomapper_b200", "csrc", f) for f in
-                ("xm_common.h", "xm_parse.h", "xm_tile.h", "xm_walk.h", "xm_stream.h", "xm_shard.h")] + [os.path.join(ROOT, "include", "xenomapper_b200.h")]
+                ("xm_common.h", "xm_parse.h", "xm_tile.h", "xm_walk.h", "xm_stream.h", "xm_shard.h", "xm_inflate.h", "xm_bamchain.h")] + [os.path.join(ROOT, "include", "xenomapper_b200.h")]
 
 
 class Opts(C.Structure):
@@ -68,6 +68,13 @@ def lib():
                                                  ALL_GATHER_FN, EXCHANGE_FN, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
                                                  C.POINTER(Result), C.POINTER(ShardStats), C.c_char_p, C.c_size_t]
         _lib.xm_emu_classify_sharded.restype = C.c_int
+        _lib.xm_emu_inflate.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        _lib.xm_emu_inflate.restype = C.c_int
+        _lib.xm_emu_crc32.argtypes = [C.c_void_p, C.c_uint32]
+        _lib.xm_emu_crc32.restype = C.c_uint32
+        _lib.xm_emu_bam_chain.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.c_uint64,
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        _lib.xm_emu_bam_chain.restype = C.c_int64
     return _lib
 
 
@@ -129,3 +136,36 @@ def classify_sharded(prim, sec, rank, world, all_gather, exchange, mode=0, score
     return dict(status=rc, outputs=outs, counts=list(r.counts), n_records=int(r.n_records), err_record=int(r.err_record),
                 out_offset=list(st.out_offset), out_total=list(st.out_total), records=(int(st.rec_lo), int(st.rec_hi)),
                 sliver_bytes=int(st.sliver_bytes), message=err.value.decode())
+
+
+def inflate(deflate_stream, out_len, misalign=0):
+    """csrc/xm_inflate.h inflate_raw on the CPU: (status, bytes).  The stream is placed `misalign` bytes behind a 16-byte
+    boundary, with the 12 readable bytes behind it the decoder's word fetches may touch."""
+    L = lib()
+    raw = bytes(deflate_stream)
+    buf = C.create_string_buffer(len(raw) + 64)
+    base = C.addressof(buf)
+    at = base + ((16 - base % 16) % 16) + misalign
+    C.memmove(at, raw, len(raw))
+    out = C.create_string_buffer(max(1, out_len))
+    rc = L.xm_emu_inflate(at, len(raw), out, out_len)
+    return rc, out.raw[:out_len]
+
+
+def crc32(data):
+    data = bytes(data)
+    buf = C.create_string_buffer(data, max(1, len(data)))
+    return int(lib().xm_emu_crc32(buf, len(data)))
+
+
+def bam_chain(inflated, first, n_ref, seg_bytes=16384):
+    """record offsets of an inflated BAM stream by the segment-parallel chain: (offsets, end, repaired segments); None: corrupt"""
+    data = bytes(inflated)
+    buf = C.create_string_buffer(data, len(data) + 64)
+    cap = len(data) // 36 + 16
+    rec = (C.c_uint64 * cap)()
+    end, rep = C.c_uint64(), C.c_uint32()
+    n = lib().xm_emu_bam_chain(buf, len(data), seg_bytes, first, n_ref, rec, cap, C.byref(end), C.byref(rep))
+    if n < 0:
+        return None
+    return list(rec[:n]), int(end.value), int(rep.value)

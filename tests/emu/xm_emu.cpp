@@ -325,3 +325,44 @@ extern "C" int xm_emu_classify_sharded(const void *prim, uint64_t plen, const vo
     if (errbuf && errcap) { strncpy(errbuf, msg.c_str(), errcap - 1); errbuf[errcap - 1] = 0; }
     return rc;
 }
+
+/* ---- BGZF inflate and the BAM record chain (csrc/xm_inflate.h, csrc/xm_bamchain.h) on the CPU ------------------------ */
+#include "../../xenomapper_b200/csrc/xm_inflate.h"
+#include "../../xenomapper_b200/csrc/xm_bamchain.h"
+
+/* `in` must be readable from the aligned word below it to 12 bytes past its end */
+extern "C" int xm_emu_inflate(const void *in, uint32_t in_len, void *out, uint32_t out_len)
+{
+    std::vector<xm::InflateTables> t(1);
+    return xm::inflate_raw((const uint8_t *)in, in_len, (uint8_t *)out, out_len, t[0]);
+}
+
+extern "C" uint32_t xm_emu_crc32(const void *p, uint32_t n) { return xm::crc32_by_lanes((const uint8_t *)p, n); }
+
+/* the parallel chain, one emulated thread per segment; returns the number of records (-1: corrupt, -2: rec[] too small) */
+extern "C" int64_t xm_emu_bam_chain(const void *data, uint64_t have, uint64_t seg_bytes, uint64_t first, uint32_t n_ref, uint64_t *rec,
+                                    uint64_t cap, uint64_t *end, uint32_t *repaired)
+{
+    using namespace xm;
+    const uint8_t *d = (const uint8_t *)data;
+    const uint32_t n_seg = (uint32_t)((have + seg_bytes - 1) / seg_bytes);
+    std::vector<ChainSeg> seg(n_seg);
+    std::vector<uint64_t> base(n_seg + 1);
+    for (uint32_t k = 0; k < n_seg; ++k) {
+        const uint64_t lo = (uint64_t)k * seg_bytes, hi = std::min(lo + seg_bytes, have);
+        if (lo + seg_bytes <= first) { seg[k] = ChainSeg{CHAIN_NONE, CHAIN_NONE, 0, 0}; continue; }
+        seg[k] = chain_segment(d, have, lo, hi, k == first / seg_bytes ? first : CHAIN_NONE, n_ref);
+    }
+    uint64_t n_rec = 0;
+    auto repair = [&](uint32_t k, uint64_t entry) {
+        const uint64_t lo = (uint64_t)k * seg_bytes, hi = std::min(lo + seg_bytes, have);
+        return chain_segment(d, have, lo, hi, entry, n_ref);
+    };
+    if (!chain_confirm(seg.data(), base.data(), n_seg, seg_bytes, first, have, repair, *end, n_rec, *repaired)) return -1;
+    if (n_rec > cap) return -2;
+    for (uint32_t k = 0; k < n_seg; ++k) {
+        const uint64_t lo = (uint64_t)k * seg_bytes, hi = std::min(lo + seg_bytes, have);
+        if (seg[k].count) chain_emit(d, have, hi, seg[k].entry, seg[k].count, rec + base[k]);
+    }
+    return (int64_t)n_rec;
+}

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared_functions():
         assert hasattr(L, name), "libxenomapper_b200.so does not export " + name
-    assert _lib.load().xm_abi_version() == 5
+    assert _lib.load().xm_abi_version() == 6
     assert sorted(_lib.EXPORTS) == declared_functions()
 
 

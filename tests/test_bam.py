@@ -4,6 +4,7 @@ The reference cannot run its own BAM path here (samtools is absent, xm.py:48-93 
 is the fixture twins: paired_end_testdata_{human,mouse}.bam decode to exactly the .sam files next to them, so the
 expected outputs are the SAM goldens (which the unmodified reference produced)."""
 import io
+import os
 
 import pytest
 
@@ -196,3 +197,80 @@ def test_literal_bam_is_well_formed():
     assert raw[8:8 + l_text] == b"@HD\tVN:1.6\n"
     block_size = struct.unpack_from("<I", raw, 8 + l_text + 4)[0]
     assert 8 + l_text + 4 + 4 + block_size == len(raw)
+
+
+# ---- BGZF inflate and record chain on the device (csrc/xm_inflate.h, csrc/xm_bamchain.h) ---------------------------------
+def _long_text(n=6000, seed=77):
+    from xenomapper_b200 import synth
+    p, _ = synth.generate(n, seed=seed, style=1)
+    lines = bytes(p).split(b"\n")
+    f = lines[n // 2].split(b"\t")
+    f[5], f[9], f[10] = b"70000M", b"ACGT" * 17500, b"I" * 70000          # one record longer than a BGZF block and a small window
+    lines[n // 2] = b"\t".join(f)
+    return b"\n".join(lines)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("window,seg", [(70000, 512), (300000, 4096), (1 << 30, 16384)])
+@pytest.mark.parametrize("level", [0, 1, 9])
+def test_device_inflate_in_windows_equals_the_text(ctx, monkeypatch, window, seg, level):
+    """windows smaller than the file (records, and one giant record, straddle them), segments smaller than a record,
+    stored / fast / best DEFLATE"""
+    text = _long_text()
+    bam = _bamwriter.sam_to_bam(FULL_HEADER, text, level=level)
+    monkeypatch.setenv("XM_BAM_WINDOW", str(window))
+    monkeypatch.setenv("XM_BAM_SEG", str(seg))
+    ctx.bam_stats(reset=True)
+    assert ctx.bam_render_host(bam) == text
+    st = ctx.bam_stats()
+    assert st.records == text.count(b"\n") and st.inflated_bytes > len(text) // 3
+    assert st.inflate_ms > 0 or os.environ.get("XM_BAM_INFLATE") == "host"
+    monkeypatch.setenv("XM_BAM_INFLATE", "host")
+    assert ctx.bam_render_host(bam) == text                            # zlib on the host: the same text
+
+
+@pytest.mark.gpu
+def test_device_inflate_with_a_header_longer_than_the_window(ctx, monkeypatch):
+    header = "@HD\tVN:1.0\n" + "".join("@SQ\tSN:contig_%06d\tLN:%d\n" % (k, 1000 + k) for k in range(9000))
+    text = b"".join(b"r%d\t0\tcontig_%06d\t%d\t30\t4M\t*\t0\t0\tACGT\tIIII\tAS:i:-%d\n" % (k, k % 9000, k + 1, k % 7 + 1) for k in range(3000))
+    bam = _bamwriter.sam_to_bam(header, text)
+    monkeypatch.setenv("XM_BAM_WINDOW", "65536")
+    assert ctx.bam_render_host(bam) == text
+
+
+@pytest.mark.gpu
+def test_device_inflate_refuses_damaged_blocks(ctx):
+    from xenomapper_b200 import _lib
+    text = _long_text(2000)
+    bam = bytearray(_bamwriter.sam_to_bam(FULL_HEADER, text, level=6))
+    assert ctx.bam_render_host(bytes(bam)) == text
+    second = int.from_bytes(bam[16:18], "little") + 1                    # BSIZE of the first block: the second starts behind it
+    for at in (second + 18 + 40, second + 18 + 400):                     # inside the second block's DEFLATE data
+        bad = bytearray(bam)
+        bad[at] ^= 0x10
+        with pytest.raises(_lib.XenomapperLibraryError, match="does not inflate"):
+            ctx.bam_render_host(bytes(bad))
+    bsize2 = int.from_bytes(bam[second + 16:second + 18], "little") + 1
+    bad = bytearray(bam)
+    bad[second + bsize2 - 8] ^= 1                                        # the block's CRC-32
+    with pytest.raises(_lib.XenomapperLibraryError, match="does not inflate"):
+        ctx.bam_render_host(bytes(bad))
+    assert ctx.bam_render_host(bytes(bam)) == text                       # the context is still usable
+
+
+@pytest.mark.gpu
+def test_bam_walk_with_small_windows_equals_the_big_one(ctx, monkeypatch):
+    from xenomapper_b200 import _lib, synth
+    p, s = synth.generate(30000, seed=43, style=1)
+    hdr2 = FULL_HEADER.replace("SN:chr", "SN:").replace("SN:M\t", "SN:MT\t")
+    bam_p, bam_s = _bamwriter.sam_to_bam(FULL_HEADER, bytes(p), level=6), _bamwriter.sam_to_bam(hdr2, bytes(s), level=6)
+    opts = _lib.Context.opts(_lib.MODE_PE_LIBERAL, _lib.SCORE_CIGAR_NM, False, -40.0)
+    rc, res, outs = ctx.classify_bam_host(bam_p, bam_s, opts)
+    assert rc == 0, ctx.error()
+    rc2, res2, outs2 = ctx.classify_host(p, s, opts)
+    assert outs == outs2 and list(res.counts) == list(res2.counts)
+    monkeypatch.setenv("XM_BAM_WINDOW", "200000")
+    monkeypatch.setenv("XM_CHUNK_BYTES", "300000")
+    rc3, res3, outs3 = ctx.classify_bam_host(bam_p, bam_s, opts)
+    assert rc3 == 0, ctx.error()
+    assert outs3 == outs and list(res3.counts) == list(res.counts)

@@ -62,7 +62,8 @@ class Headers(C.Structure):
 
 class BamStats(C.Structure):
     _fields_ = [("inflate_s", C.c_double), ("render_ms", C.c_float), ("n_launches", C.c_uint32), ("bam_bytes", C.c_uint64),
-                ("inflated_bytes", C.c_uint64), ("text_bytes", C.c_uint64), ("records", C.c_uint64)]
+                ("inflated_bytes", C.c_uint64), ("text_bytes", C.c_uint64), ("records", C.c_uint64),
+                ("upload_s", C.c_double), ("inflate_ms", C.c_float), ("chain_repairs", C.c_uint32)]
 
 
 class XenomapperLibraryError(RuntimeError):

@@ -29,6 +29,8 @@
 #include "xm_walk.h"
 #include "xm_stream.h"
 #include "xm_bam.h"
+#include "xm_inflate.h"
+#include "xm_bamchain.h"
 #include "xm_shard.h"
 #include "xm_headers.h"
 #include "xm_bgzf.h"
@@ -193,6 +195,7 @@ struct xm_ctx {
     /* BAM input: inflated streams (pinned), device copies, record tables, rendered SAM text */
     HostBuf h_bam[2];
     DevBuf d_bam[2], d_bam_rec[2], d_bam_ref[2], d_bam_len[2], d_bam_sum[2], d_bam_text[2];
+    DevBuf d_bam_comp[2], d_bam_tab[2], d_bam_seg[2];      /* compressed window, its block table, the chain's segments */
     std::vector<uint8_t> bam_text_host;
     xm_bam_stats bam_stats{};
     /* the walk across GPUs (xm_shard.h): communicator, row scratch, shard staging of the host entry point */
@@ -281,7 +284,7 @@ void xm_destroy(xm_ctx *c)
     for (auto &s : c->d_out) for (auto &b : s) if (b.p) cudaFree(b.p);
     for (auto &b : c->h_stage) if (b.p) cudaFreeHost(b.p);
     for (auto &b : c->h_bam) if (b.p) cudaFreeHost(b.p);
-    for (auto *arr : {c->d_bam, c->d_bam_rec, c->d_bam_ref, c->d_bam_len, c->d_bam_sum, c->d_bam_text}) for (int k = 0; k < 2; ++k) if (arr[k].p) cudaFree(arr[k].p);
+    for (auto *arr : {c->d_bam, c->d_bam_rec, c->d_bam_ref, c->d_bam_len, c->d_bam_sum, c->d_bam_text, c->d_bam_comp, c->d_bam_tab, c->d_bam_seg}) for (int k = 0; k < 2; ++k) if (arr[k].p) cudaFree(arr[k].p);
     for (auto &v : c->bins) for (auto &b : v) cudaFreeHost(b.p);
     for (auto &b : c->pool) cudaFreeHost(b.p);
     if (c->dl) cudaStreamDestroy(c->dl);
@@ -779,75 +782,8 @@ static int host_threads()
     return (int)std::min<unsigned>(h ? h : 1, 32);
 }
 
-/* inflate, index, upload and render one BAM file: its records as SAM text in device memory (slot s) */
-static int bam_to_device_text(xm_ctx *c, const void *bam, uint64_t len, int s, uint8_t **d_text, uint64_t *text_len)
-{
-    *d_text = nullptr; *text_len = 0;
-    std::string err;
-    std::vector<BgzfBlock> blocks;
-    uint64_t total = 0;
-    const auto t0 = std::chrono::steady_clock::now();
-    if (!bgzf_scan((const uint8_t *)bam, len, blocks, total, err)) return fail(c, XM_ERR_IO, "BAM input: " + err);
-    int rc;
-    if ((rc = reserve_host(c, c->h_bam[s], total))) return rc;
-    if (!bgzf_inflate((const uint8_t *)bam, blocks, 0, blocks.size(), c->h_bam[s].p, host_threads(), err)) return fail(c, XM_ERR_IO, "BAM input: " + err);
-    BamIndex ix;
-    if (!bam_index(c->h_bam[s].p, total, ix, false, err)) return fail(c, XM_ERR_IO, "BAM input: " + err);
-    c->bam_stats.inflate_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    c->bam_stats.bam_bytes += len;
-    c->bam_stats.inflated_bytes += total;
-    const uint64_t n = ix.rec.size();
-    c->bam_stats.records += n;
-    if (!n) return XM_OK;
-    const uint64_t nb = (n + 1023) / 1024;
-    const uint64_t ref_bytes = ix.ref_off.size() * 4 + ix.ref_names.size() + 16;
-    if ((rc = reserve_dev(c, c->d_bam[s], total)) || (rc = reserve_dev(c, c->d_bam_rec[s], n * 8)) || (rc = reserve_dev(c, c->d_bam_ref[s], ref_bytes)) ||
-        (rc = reserve_dev(c, c->d_bam_len[s], n * 8 + 16)) || (rc = reserve_dev(c, c->d_bam_sum[s], nb * 8 + 16))) return rc;
-    cudaStream_t st = c->be.st;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    XM_CUDA(c, cudaMemcpyAsync(c->d_bam[s].p, c->h_bam[s].p, total, cudaMemcpyHostToDevice, st), "H2D copy");
-    XM_CUDA(c, cudaMemcpyAsync(c->d_bam_rec[s].p, ix.rec.data(), n * 8, cudaMemcpyHostToDevice, st), "H2D copy");
-    XM_CUDA(c, cudaMemcpyAsync(c->d_bam_ref[s].p, ix.ref_off.data(), ix.ref_off.size() * 4, cudaMemcpyHostToDevice, st), "H2D copy");
-    uint8_t *d_names = c->d_bam_ref[s].p + ix.ref_off.size() * 4;
-    if (!ix.ref_names.empty()) XM_CUDA(c, cudaMemcpyAsync(d_names, ix.ref_names.data(), ix.ref_names.size(), cudaMemcpyHostToDevice, st), "H2D copy");
-    unsigned long long *d_err = (unsigned long long *)(c->d_bam_sum[s].p + nb * 8);
-    const unsigned long long no_err = BAM_NO_ERROR;
-    XM_CUDA(c, cudaMemcpyAsync(d_err, &no_err, 8, cudaMemcpyHostToDevice, st), "H2D copy");
-    BamDev B;
-    B.data = c->d_bam[s].p; B.rec = (const uint64_t *)c->d_bam_rec[s].p; B.n = n;
-    B.ref_off = (const uint32_t *)c->d_bam_ref[s].p; B.ref_names = d_names; B.n_ref = (uint32_t)ix.ref_off.size() - 1;
-    uint32_t *d_len = (uint32_t *)c->d_bam_len[s].p, *d_loff = d_len + n + (n & 1);
-    cudaEventRecord(e0, st);
-    k_bam_len<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(B, d_len, d_err);
-    k_bam_scan_blocks<<<(unsigned)nb, 1024, 0, st>>>(d_len, n, d_loff, (unsigned long long *)c->d_bam_sum[s].p);
-    std::vector<unsigned long long> sums(nb + 1);
-    XM_CUDA(c, cudaMemcpyAsync(sums.data(), c->d_bam_sum[s].p, (nb + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H copy");
-    XM_CUDA(c, cudaStreamSynchronize(st), "BAM length kernels");
-    if (sums[nb] != BAM_NO_ERROR) {
-        const unsigned long long rec = sums[nb] >> 8;
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        if ((sums[nb] & 0xff) == BAM_E_FLOAT) return fail(c, XM_ERR_UNSUPPORTED, "BAM record " + std::to_string(rec) + " has a float aux value (f or B:f): not rendered on the device");
-        return fail(c, XM_ERR_IO, "BAM record " + std::to_string(rec) + " is corrupt");
-    }
-    unsigned long long run = 0;
-    for (uint64_t k = 0; k < nb; ++k) { const unsigned long long v = sums[k]; sums[k] = run; run += v; }
-    if ((rc = reserve_dev(c, c->d_bam_text[s], run))) return rc;
-    XM_CUDA(c, cudaMemcpyAsync(c->d_bam_sum[s].p, sums.data(), nb * 8, cudaMemcpyHostToDevice, st), "H2D copy");
-    k_bam_render<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(B, d_loff, (const unsigned long long *)c->d_bam_sum[s].p, c->d_bam_text[s].p);
-    cudaEventRecord(e1, st);
-    XM_CUDA(c, cudaStreamSynchronize(st), "BAM render kernel");
-    XM_CUDA(c, cudaGetLastError(), "BAM render kernel");
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    c->bam_stats.render_ms += ms;
-    c->bam_stats.text_bytes += run;
-    c->bam_stats.n_launches += 3;
-    *d_text = c->d_bam_text[s].p;
-    *text_len = run;
-    return XM_OK;
-}
+/* one BAM file as SAM text in device memory (slot s); defined behind BamProducer */
+static int bam_to_device_text(xm_ctx *c, const void *bam, uint64_t len, int s, uint8_t **d_text, uint64_t *text_len);
 
 int xm_bam_header_text(const void *bam, uint64_t len, char *dst, uint64_t cap, uint64_t *needed)
 {
@@ -889,6 +825,25 @@ int xm_bam_render_host(xm_ctx *c, const void *bam, uint64_t len, const void **te
     return XM_OK;
 }
 
+static uint64_t bam_window_bytes()
+{
+    const char *e = getenv("XM_BAM_WINDOW");
+    if (e && *e) { const long long v = atoll(e); if (v > 0) return (uint64_t)v; }
+    return 1ull << 30;
+}
+static uint64_t bam_seg_bytes()
+{
+    const char *e = getenv("XM_BAM_SEG");
+    if (e && *e) { const long long v = atoll(e); if (v >= 64) return (uint64_t)v; }
+    return 16384;
+}
+static bool bam_inflate_on_host()
+{
+    const char *e = getenv("XM_BAM_INFLATE");
+    return e && !strcmp(e, "host");
+}
+static int upload_shard(xm_ctx *c, uint8_t *d_dst, const uint8_t *src, uint64_t n);
+
 /* BAM as a source of the chunked walk: each call inflates the next BGZF blocks on the host (thread pool), follows the
  * record chain, uploads the whole records and renders them as SAM text straight into the walk's staging buffer.  What
  * is resident at any time is one batch, not the file: the inflated size of a BAM no longer has to fit the GPU. */
@@ -908,7 +863,7 @@ struct BamProducer : DevSource {
     std::vector<uint64_t> pend_rec;
     uint64_t pend_have = 0, pend_end = 0, full_cap = 0;
 
-    int next(uint8_t *dev_dst, uint64_t max_bytes, uint64_t &n_out, bool &final, std::string &err) override
+    int next_host(uint8_t *dev_dst, uint64_t max_bytes, uint64_t &n_out, bool &final, std::string &err)
     {
         n_out = 0; final = false;
         if (max_bytes == 0) return XM_OK;
@@ -1012,7 +967,7 @@ struct BamProducer : DevSource {
                     return XM_OK;
                 }
                 cudaMemcpyAsync(c->d_bam_sum[s].p, sums.data(), nb * 8, cudaMemcpyHostToDevice, st);
-                k_bam_render<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(B, d_loff, (const unsigned long long *)c->d_bam_sum[s].p, dev_dst);
+                k_bam_render<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(B, 0, n, d_loff, (const unsigned long long *)c->d_bam_sum[s].p, dev_dst);
                 cudaEventRecord(e1, st);
                 if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "BAM render kernel failed"; return XM_ERR_CUDA; }
                 float ms = 0.f;
@@ -1029,6 +984,262 @@ struct BamProducer : DevSource {
             return XM_OK;
         }
     }
+
+    /* ---- the device path: windows of BGZF blocks inflated by k_bgzf_inflate, the record chain by k_bam_chain ----------- */
+    bool host_mode = false;             /* XM_BAM_INFLATE=host: zlib on host threads (the round-1 path, kept for comparison) */
+    uint64_t inflated_total = 0;
+    uint64_t skip = 0;                  /* header bytes of the inflated stream that are still ahead */
+    uint64_t have_d = 0, win_end = 0;   /* inflated bytes in d_bam[s]; end of the last whole record among them */
+    uint64_t n_rec = 0, r_next = 0;     /* records of the window; the next one to render */
+    uint64_t cut_off = 0;               /* text bytes of r_next's group of 1024 that are rendered already */
+    std::vector<unsigned long long> sums;      /* text bytes of each group of 1024 records of the window */
+
+    /* block table, header (leading blocks inflated on the host: a few KiB), reference names to the device */
+    int open(std::string &err)
+    {
+        host_mode = bam_inflate_on_host();
+        std::string e;
+        if (!bgzf_scan(bam, bam_len, blocks, inflated_total, e)) { err = "BAM input: " + e; return XM_ERR_IO; }
+        c->bam_stats.bam_bytes += bam_len;
+        if (host_mode) return XM_OK;
+        for (size_t take = std::min<size_t>(blocks.size(), 4);; take = std::min(blocks.size(), take * 4)) {
+            const uint64_t bytes = take < blocks.size() ? blocks[take].out_off : inflated_total;
+            std::vector<uint8_t> buf(bytes + 16);
+            if (!bgzf_inflate(bam, blocks, 0, take, buf.data(), host_threads(), e)) { err = "BAM input: " + e; return XM_ERR_IO; }
+            BamIndex ix;
+            if (bam_index(buf.data(), bytes, ix, true, e)) {
+                have_header = true;
+                skip = ix.first_record;
+                n_ref = (uint32_t)ix.ref_off.size() - 1;
+                const uint64_t ref_bytes = ix.ref_off.size() * 4 + ix.ref_names.size() + 16;
+                int rc;
+                if ((rc = reserve_dev(c, c->d_bam_ref[s], ref_bytes))) { err = c->err; return rc; }
+                cudaMemcpyAsync(c->d_bam_ref[s].p, ix.ref_off.data(), ix.ref_off.size() * 4, cudaMemcpyHostToDevice, c->be.st);
+                d_names = c->d_bam_ref[s].p + ix.ref_off.size() * 4;
+                if (!ix.ref_names.empty()) cudaMemcpyAsync(d_names, ix.ref_names.data(), ix.ref_names.size(), cudaMemcpyHostToDevice, c->be.st);
+                if (cudaStreamSynchronize(c->be.st) != cudaSuccess) { err = "H2D copy failed"; return XM_ERR_CUDA; }
+                return XM_OK;
+            }
+            if (take == blocks.size()) { err = "BAM input: " + e; return XM_ERR_IO; }
+        }
+    }
+
+    /* the next window: what is left of the last one moves to the front, the next blocks are inflated behind it, the chain is
+     * followed and the text length of every record is found */
+    int load_window(std::string &err)
+    {
+        cudaStream_t st = c->be.st;
+        const auto t0 = std::chrono::steady_clock::now();
+        int rc;
+        const uint64_t left = have_d - win_end;
+        size_t last = blk;
+        uint64_t add = 0;
+        const uint64_t W = bam_window_bytes();
+        while (last < blocks.size() && (last == blk || add + blocks[last].out_len <= W)) add += blocks[last++].out_len;
+        DevBuf &D = c->d_bam[s];
+        if (left && left + add + 64 <= D.cap && left <= win_end) {
+            cudaMemcpyAsync(D.p, D.p + win_end, left, cudaMemcpyDeviceToDevice, st);
+        } else {
+            uint8_t *tmp = nullptr;
+            if (left) {
+                if (cudaMalloc((void **)&tmp, left) != cudaSuccess) { cudaGetLastError(); err = "cudaMalloc: out of memory"; return XM_ERR_NOMEM; }
+                cudaMemcpyAsync(tmp, D.p + win_end, left, cudaMemcpyDeviceToDevice, st);
+                cudaStreamSynchronize(st);
+            }
+            if ((rc = reserve_dev(c, D, std::max<uint64_t>(left + add + 64, std::min<uint64_t>(W, inflated_total) + 64)))) { if (tmp) cudaFree(tmp); err = c->err; return rc; }
+            if (left) { cudaMemcpyAsync(D.p, tmp, left, cudaMemcpyDeviceToDevice, st); cudaStreamSynchronize(st); cudaFree(tmp); }
+        }
+        const size_t nblk = last - blk;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        unsigned long long *d_status = nullptr;
+        if (nblk) {
+            const uint64_t c0 = blocks[blk].in_off, c1 = blocks[last - 1].in_off + blocks[last - 1].in_len;
+            if ((rc = reserve_dev(c, c->d_bam_comp[s], c1 - c0 + 64)) || (rc = reserve_dev(c, c->d_bam_tab[s], nblk * sizeof(BgzfDev) + 16))) { err = c->err; return rc; }
+            const auto tu = std::chrono::steady_clock::now();
+            if ((rc = upload_shard(c, c->d_bam_comp[s].p, bam + c0, c1 - c0))) { err = c->err; return rc; }
+            c->bam_stats.upload_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - tu).count();
+            std::vector<BgzfDev> tab(nblk);
+            for (size_t k = 0; k < nblk; ++k) {
+                const BgzfBlock &b = blocks[blk + k];
+                tab[k].in_off = b.in_off - c0 + b.hdr_len;
+                tab[k].in_len = b.in_len - b.hdr_len - 8;
+                tab[k].out_off = left + (b.out_off - blocks[blk].out_off);
+                tab[k].out_len = b.out_len;
+                tab[k].crc = rd_u32(bam + b.in_off + b.in_len - 8);
+                tab[k].pad = 0;
+            }
+            cudaMemcpyAsync(c->d_bam_tab[s].p, tab.data(), nblk * sizeof(BgzfDev), cudaMemcpyHostToDevice, st);
+            d_status = (unsigned long long *)(c->d_bam_tab[s].p + nblk * sizeof(BgzfDev));
+            const unsigned long long none = ~0ull;
+            cudaMemcpyAsync(d_status, &none, 8, cudaMemcpyHostToDevice, st);
+            cudaEventRecord(e0, st);
+            k_bgzf_inflate<<<(unsigned)((nblk + INF_WARPS - 1) / INF_WARPS), INF_WARPS * 32, 0, st>>>(c->d_bam_comp[s].p, (const BgzfDev *)c->d_bam_tab[s].p,
+                                                                                                   (uint32_t)nblk, D.p, d_status, 1);
+            cudaEventRecord(e1, st);
+            unsigned long long status = 0;
+            cudaMemcpyAsync(&status, d_status, 8, cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "the BGZF inflate kernel failed"; return XM_ERR_CUDA; }
+            if (status != ~0ull) { err = "BAM input: BGZF block does not inflate (corrupt data or CRC mismatch)"; return XM_ERR_IO; }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            c->bam_stats.inflate_ms += ms;
+            c->bam_stats.n_launches += 1;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        have_d = left + add;
+        blk = last;
+        c->bam_stats.inflated_bytes += add;
+        n_rec = 0; r_next = 0; win_end = 0; cut_off = 0;
+        uint64_t first = 0;
+        if (skip) {
+            if (skip >= have_d) {            /* nothing but header so far */
+                skip -= have_d; have_d = 0;
+                c->bam_stats.inflate_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                return XM_OK;
+            }
+            first = skip; skip = 0;
+        }
+        /* the record chain (xm_bamchain.h) */
+        const uint64_t SEG = bam_seg_bytes();
+        const uint32_t n_seg = (uint32_t)((have_d + SEG - 1) / SEG);
+        if (n_seg) {
+            if ((rc = reserve_dev(c, c->d_bam_seg[s], (uint64_t)(n_seg + 1) * (sizeof(ChainSeg) + 8) + 64))) { err = c->err; return rc; }
+            ChainSeg *d_seg = (ChainSeg *)c->d_bam_seg[s].p, *d_one = d_seg + n_seg;
+            uint64_t *d_base = (uint64_t *)(d_one + 1);
+            k_bam_chain<<<(n_seg + 127) / 128, 128, 0, st>>>(D.p, have_d, SEG, first, n_seg, n_ref, nullptr, d_seg);
+            std::vector<ChainSeg> seg(n_seg);
+            std::vector<uint64_t> base(n_seg);
+            cudaMemcpyAsync(seg.data(), d_seg, (size_t)n_seg * sizeof(ChainSeg), cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "the BAM chain kernel failed"; return XM_ERR_CUDA; }
+            auto repair = [&](uint32_t k, uint64_t entry) {
+                const uint64_t lo = (uint64_t)k * SEG, hi = std::min(lo + SEG, have_d);
+                ChainSeg r;
+                k_bam_chain_one<<<1, 32, 0, st>>>(D.p, have_d, lo, hi, entry, n_ref, d_one);
+                cudaMemcpyAsync(&r, d_one, sizeof r, cudaMemcpyDeviceToHost, st);
+                if (cudaStreamSynchronize(st) != cudaSuccess) { r.entry = entry; r.exit = entry; r.count = 0; r.flag = CHAIN_CORRUPT; }
+                return r;
+            };
+            uint64_t end = 0, nr = 0;
+            uint32_t nrep = 0;
+            if (!chain_confirm(seg.data(), base.data(), n_seg, SEG, first, have_d, repair, end, nr, nrep)) { err = "corrupt BAM record"; return XM_ERR_IO; }
+            c->bam_stats.chain_repairs += nrep;
+            c->bam_stats.n_launches += 1 + nrep;
+            n_rec = nr; win_end = end;
+            if (n_rec) {
+                const uint64_t nb = (n_rec + 1023) / 1024;
+                if ((rc = reserve_dev(c, c->d_bam_rec[s], n_rec * 8)) || (rc = reserve_dev(c, c->d_bam_len[s], n_rec * 8 + 16)) ||
+                    (rc = reserve_dev(c, c->d_bam_sum[s], nb * 8 + 16))) { err = c->err; return rc; }
+                cudaMemcpyAsync(d_seg, seg.data(), (size_t)n_seg * sizeof(ChainSeg), cudaMemcpyHostToDevice, st);
+                cudaMemcpyAsync(d_base, base.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st);
+                k_bam_chain_emit<<<(n_seg + 127) / 128, 128, 0, st>>>(D.p, have_d, SEG, n_seg, d_seg, d_base, (uint64_t *)c->d_bam_rec[s].p);
+                unsigned long long *d_err = (unsigned long long *)(c->d_bam_sum[s].p + nb * 8);
+                const unsigned long long no_err = BAM_NO_ERROR;
+                cudaMemcpyAsync(d_err, &no_err, 8, cudaMemcpyHostToDevice, st);
+                BamDev B = dev_view(0, n_rec);
+                uint32_t *d_len = (uint32_t *)c->d_bam_len[s].p, *d_loff = d_len + n_rec + (n_rec & 1);
+                cudaEvent_t r0, r1;
+                cudaEventCreate(&r0); cudaEventCreate(&r1);
+                cudaEventRecord(r0, st);
+                k_bam_len<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(B, d_len, d_err);
+                k_bam_scan_blocks<<<(unsigned)nb, 1024, 0, st>>>(d_len, n_rec, d_loff, (unsigned long long *)c->d_bam_sum[s].p);
+                cudaEventRecord(r1, st);
+                sums.assign(nb + 1, 0);
+                cudaMemcpyAsync(sums.data(), c->d_bam_sum[s].p, (nb + 1) * 8, cudaMemcpyDeviceToHost, st);
+                const bool ok = cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+                float ms = 0.f;
+                if (ok) cudaEventElapsedTime(&ms, r0, r1);
+                cudaEventDestroy(r0); cudaEventDestroy(r1);
+                if (!ok) { err = "BAM length kernels failed"; return XM_ERR_CUDA; }
+                c->bam_stats.render_ms += ms;
+                c->bam_stats.n_launches += 3;
+                if (sums[nb] != BAM_NO_ERROR) {
+                    if ((sums[nb] & 0xff) == BAM_E_FLOAT) { err = "a BAM record has a float aux value (f or B:f): not rendered on the device"; return XM_ERR_UNSUPPORTED; }
+                    err = "corrupt BAM record"; return XM_ERR_IO;
+                }
+                c->bam_stats.records += n_rec;
+            }
+        }
+        if (blk == blocks.size() && win_end != have_d) { err = "truncated BAM record at the end of the file"; return XM_ERR_IO; }
+        c->bam_stats.inflate_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return XM_OK;
+    }
+    BamDev dev_view(uint64_t r0, uint64_t n) const
+    {
+        BamDev B;
+        B.data = c->d_bam[s].p; B.rec = (const uint64_t *)c->d_bam_rec[s].p + r0; B.n = n;
+        B.ref_off = (const uint32_t *)c->d_bam_ref[s].p; B.ref_names = d_names; B.n_ref = n_ref;
+        return B;
+    }
+    /* text bytes the rest of the window renders to (0: the window is spent) */
+    uint64_t window_text_left() const
+    {
+        uint64_t t = 0;
+        if (r_next == n_rec) return 0;
+        for (uint64_t g = r_next / 1024, nb = (n_rec + 1023) / 1024; g < nb; ++g) t += sums[g];
+        return t - cut_off;
+    }
+
+    int next(uint8_t *dev_dst, uint64_t max_bytes, uint64_t &n_out, bool &final, std::string &err) override
+    {
+        if (host_mode) return next_host(dev_dst, max_bytes, n_out, final, err);
+        n_out = 0; final = false;
+        if (max_bytes == 0) return XM_OK;
+        cudaStream_t st = c->be.st;
+        while (r_next == n_rec) {
+            if (blk == blocks.size()) { final = true; return XM_OK; }
+            const int rc = load_window(err);
+            if (rc) return rc;
+        }
+        /* whole groups of 1024 records while they fit, then the records of the next group that still do (its offsets
+         * are read back: 4 KiB).  cut_off: text bytes of r_next's group that earlier calls rendered. */
+        const uint64_t g0 = r_next >> 10, nbw = (n_rec + 1023) / 1024;
+        const uint32_t *d_len = (const uint32_t *)c->d_bam_len[s].p, *d_loff = d_len + n_rec + (n_rec & 1);
+        uint64_t g = g0, bytes = 0, r_end = r_next, cut_end = cut_off;
+        while (g < nbw) {
+            const uint64_t rem = sums[g] - (g == g0 ? cut_off : 0);
+            if (bytes + rem > max_bytes) break;
+            bytes += rem; ++g;
+            r_end = std::min(n_rec, g * 1024); cut_end = 0;
+        }
+        if (g < nbw && bytes < max_bytes) {
+            const uint64_t lo = g * 1024, cnt_g = std::min<uint64_t>(1024, n_rec - lo);
+            uint32_t loff[1024];
+            cudaMemcpyAsync(loff, d_loff + lo, cnt_g * 4, cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess) { err = "D2H copy failed"; return XM_ERR_CUDA; }
+            const uint64_t start = g == g0 ? cut_off : 0, room = max_bytes - bytes;
+            uint64_t j = r_end - lo;                                   /* records [lo + j0, lo + j) of this group are taken */
+            while (j + 1 < cnt_g && loff[j + 1] - start <= room) ++j;  /* loff[j + 1] - start: text of the records up to j */
+            if (lo + j > r_end) { bytes += loff[j] - start; r_end = lo + j; cut_end = loff[j]; }
+        }
+        if (r_end == r_next) {
+            if (max_bytes >= full_cap) { err = "a BAM record renders to more text than a staging step holds"; return XM_ERR_UNSUPPORTED; }
+            return XM_OK;                        /* offered less than a whole step: the walk buffer is full of carried records */
+        }
+        const uint64_t cnt = r_end - r_next, ng = ((r_end - 1) >> 10) - g0 + 1;
+        std::vector<unsigned long long> bases(ng);
+        unsigned long long run = 0ull - cut_off;                       /* wraps: the first group's base lies before dev_dst */
+        for (uint64_t k = 0; k < ng; ++k) { bases[k] = run; run += sums[g0 + k]; }
+        cudaMemcpyAsync(c->d_bam_sum[s].p, bases.data(), bases.size() * 8, cudaMemcpyHostToDevice, st);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        k_bam_render<<<(unsigned)((cnt * 32 + 255) / 256), 256, 0, st>>>(dev_view(0, n_rec), r_next, cnt, d_loff, (const unsigned long long *)c->d_bam_sum[s].p, dev_dst);
+        cudaEventRecord(e1, st);
+        const bool ok = cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+        float ms = 0.f;
+        if (ok) cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (!ok) { err = "BAM render kernel failed"; return XM_ERR_CUDA; }
+        c->bam_stats.render_ms += ms;
+        c->bam_stats.text_bytes += bytes;
+        c->bam_stats.n_launches += 1;
+        cut_off = cut_end;
+        r_next = r_end;
+        n_out = bytes;
+        final = r_next == n_rec && blk == blocks.size();
+        return XM_OK;
+    }
     /* pinned buffer of the inflated batch, grown without losing the bytes at its front */
     int reserve_host_keep(uint64_t need)
     {
@@ -1043,6 +1254,54 @@ struct BamProducer : DevSource {
     }
 };
 
+/* one BAM file as SAM text in device memory (slot s): the producer's windows rendered one behind the other */
+static int bam_to_device_text(xm_ctx *c, const void *bam, uint64_t len, int s, uint8_t **d_text, uint64_t *text_len)
+{
+    *d_text = nullptr; *text_len = 0;
+    BamProducer p;
+    p.c = c; p.s = s; p.bam = (const uint8_t *)bam; p.bam_len = len;
+    std::string err;
+    int rc = p.open(err);
+    if (rc) return fail(c, rc, err);
+    DevBuf &T = c->d_bam_text[s];
+    uint64_t off = 0;
+    if (p.host_mode) {
+        /* the host path renders what it is offered room for: offer the most a BAM byte can become */
+        if ((rc = reserve_dev(c, T, p.inflated_total * 6 + 4096))) return rc;
+        p.full_cap = T.cap;
+        for (;;) {
+            uint64_t n = 0;
+            bool final = false;
+            if ((rc = p.next(T.p + off, T.cap - off, n, final, err))) return fail(c, rc, err);
+            off += n;
+            if (final) break;
+        }
+    } else {
+        for (;;) {
+            while (p.r_next == p.n_rec && p.blk < p.blocks.size()) if ((rc = p.load_window(err))) return fail(c, rc, err);
+            const uint64_t want = p.window_text_left();
+            if (!want) break;
+            if (off + want > T.cap || !T.p) {                   /* grow, keeping what is rendered */
+                uint8_t *np_ = nullptr;
+                const uint64_t cap = std::max<uint64_t>(off + want, T.cap * 2);
+                if (cudaMalloc((void **)&np_, cap + 64) != cudaSuccess) { cudaGetLastError(); return fail(c, XM_ERR_NOMEM, "cudaMalloc: out of memory"); }
+                if (off) { cudaMemcpyAsync(np_, T.p, off, cudaMemcpyDeviceToDevice, c->be.st); cudaStreamSynchronize(c->be.st); }
+                if (T.p) cudaFree(T.p);
+                T.p = np_; T.cap = cap;
+            }
+            p.full_cap = want;
+            uint64_t n = 0;
+            bool final = false;
+            if ((rc = p.next(T.p + off, want, n, final, err))) return fail(c, rc, err);
+            off += n;
+        }
+        if (!T.p && (rc = reserve_dev(c, T, 64))) return rc;
+    }
+    *d_text = T.p;
+    *text_len = off;
+    return XM_OK;
+}
+
 int xm_classify_bam_host(xm_ctx *c, const void *prim_bam, uint64_t prim_len, const void *sec_bam, uint64_t sec_len,
                          const xm_opts *opts, xm_result *res)
 {
@@ -1056,12 +1315,11 @@ int xm_classify_bam_host(xm_ctx *c, const void *prim_bam, uint64_t prim_len, con
     const uint32_t launches0 = c->bam_stats.n_launches;
     for (int s = 0; s < 2; ++s) {
         prod[s].c = c; prod[s].s = s; prod[s].bam = (const uint8_t *)src[s]; prod[s].bam_len = len[s];
-        uint64_t total = 0;
         std::string err;
-        if (!bgzf_scan(prod[s].bam, len[s], prod[s].blocks, total, err)) return res->status = fail(c, XM_ERR_IO, "BAM input: " + err);
-        c->bam_stats.bam_bytes += len[s];
+        const int rc = prod[s].open(err);
+        if (rc) return res->status = fail(c, rc, err);
         in[s].prod = &prod[s];
-        in[s].len = total * 3 + 4096;                   /* an estimate of the text: sizes the staging steps of small files */
+        in[s].len = prod[s].inflated_total * 3 + 4096;  /* an estimate of the text: sizes the staging steps of small files */
     }
     const uint64_t step = std::max<uint64_t>(std::min<uint64_t>(chunk_bytes(), std::max(in[0].len, in[1].len) + 64), 64);     /* stream_walk's chunk */
     prod[0].full_cap = prod[1].full_cap = step;
@@ -1198,10 +1456,22 @@ int xm_classify_sharded_device(xm_ctx *c, void *d_prim, uint64_t prim_len, void 
     return rc;
 }
 
+/* one memcpy by several threads (a single core moves ~10 GB/s, less than the PCIe link takes) */
+static void memcpy_threads(uint8_t *dst, const uint8_t *src, size_t n, int threads)
+{
+    if (threads <= 1 || n < (8u << 20)) { memcpy(dst, src, n); return; }
+    const size_t part = ((n + (size_t)threads - 1) / (size_t)threads + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (size_t at = part; at < n; at += part) pool.emplace_back([=]() { memcpy(dst + at, src + at, std::min(part, n - at)); });
+    memcpy(dst, src, std::min(part, n));
+    for (auto &t : pool) t.join();
+}
+
 /* pageable host memory -> device through two pinned blocks, the memcpy of one overlapping the H2D of the other */
 static int upload_shard(xm_ctx *c, uint8_t *d_dst, const uint8_t *src, uint64_t n)
 {
     const uint64_t blk = 64ull << 20;
+    const int nt = std::max(1, std::min(8, host_threads() / 2));
     int rc;
     for (int k = 0; k < 2; ++k) if ((rc = reserve_host(c, c->h_stage[k], std::min<uint64_t>(blk, n ? n : 1)))) return rc;
     cudaEvent_t ev[2];
@@ -1211,7 +1481,7 @@ static int upload_shard(xm_ctx *c, uint8_t *d_dst, const uint8_t *src, uint64_t 
         const int b = k & 1;
         const uint64_t m = std::min<uint64_t>(std::min<uint64_t>(blk, c->h_stage[b].cap), n - done);
         if (k >= 2) cudaEventSynchronize(ev[b]);
-        memcpy(c->h_stage[b].p, src + done, (size_t)m);
+        memcpy_threads(c->h_stage[b].p, src + done, (size_t)m, nt);
         cudaMemcpyAsync(d_dst + done, c->h_stage[b].p, (size_t)m, cudaMemcpyHostToDevice, c->copy_st[b]);
         cudaEventRecord(ev[b], c->copy_st[b]);
         done += m;

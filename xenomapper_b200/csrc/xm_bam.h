@@ -339,14 +339,16 @@ __global__ void k_bam_scan_blocks(const uint32_t *len, uint64_t n, uint32_t *loc
     if (i < n) local_off[i] = wsum[warp] + x - v;
 }
 
-/* one warp per record */
-__global__ void k_bam_render(const BamDev B, const uint32_t *local_off, const unsigned long long *block_base, uint8_t *out)
+/* one warp per record: records [i0, i0 + cnt) of B; local_off[] and block_base[] are indexed by record and by group of
+ * 1024 records counted from i0's group (block_base[0] may be "negative": part of that group was rendered before) */
+__global__ void k_bam_render(const BamDev B, uint64_t i0, uint64_t cnt, const uint32_t *local_off, const unsigned long long *block_base, uint8_t *out)
 {
-    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (i >= B.n) return;
+    if (w >= cnt) return;
+    const uint64_t i = i0 + w;
     const uint8_t *r = B.data + B.rec[i];
-    uint8_t *dst = out + block_base[i >> 10] + local_off[i];
+    uint8_t *dst = out + (block_base[(i >> 10) - (i0 >> 10)] + local_off[i]);
     /* lane 0 writes everything but the three bulk fields and tells the others where those go */
     uint32_t l_qname = 0, l_seq = 0, seq_at = 0, qual_at = 0;
     bool qstar = false;
