@@ -334,7 +334,9 @@ extern "C" int xm_emu_classify_sharded(const void *prim, uint64_t plen, const vo
 extern "C" int xm_emu_inflate(const void *in, uint32_t in_len, void *out, uint32_t out_len)
 {
     std::vector<xm::InflateTables> t(1);
-    return xm::inflate_raw((const uint8_t *)in, in_len, (uint8_t *)out, out_len, t[0]);
+    uint32_t base[xm::INF_BASE_WORDS];
+    for (int k = 0; k < xm::INF_BASE_WORDS; ++k) base[k] = xm::inf_base_word(k);
+    return xm::inflate_raw((const uint8_t *)in, in_len, (uint8_t *)out, out_len, t[0], base);
 }
 
 extern "C" uint32_t xm_emu_crc32(const void *p, uint32_t n) { return xm::crc32_by_lanes((const uint8_t *)p, n); }

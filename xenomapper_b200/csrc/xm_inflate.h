@@ -12,8 +12,8 @@
  *     match together (byte i of the match by lane i % 32, periodic source for distances
  *     shorter than the match);
  *   - per warp in shared memory: a 10-bit look-up table for the literal/length code and an
- *     8-bit one for the distance code (symbol + code length per entry), and the sorted symbol
- *     lists of the canonical codes for the few codes longer than that;
+ *     8-bit one for the distance code (symbol + code length per entry); codes longer than
+ *     that are found by comparing the next 15 bits with one limit per code length;
  *   - CRC-32 of the inflated block: each lane folds a 1/32 slice byte by byte, the slices are
  *     joined with the "append n zero bytes" operator of the CRC's linear feedback register.
  *
@@ -35,13 +35,16 @@ enum { INF_OK = 0, INF_E_HEADER = 1, INF_E_CODES = 2, INF_E_SYMBOL = 3, INF_E_DI
 
 /* decode tables of one warp (shared memory on the device) */
 struct InflateTables {
-    uint16_t lit_lut[1 << INF_LIT_BITS];        /* symbol | code length << 9; 0: code longer than the table */
+    uint16_t lit_lut[1 << INF_LIT_BITS];        /* symbol | code length << 9; 0: the code is longer than the table's index */
     uint16_t dist_lut[1 << INF_DIST_BITS];
-    uint16_t lit_count[16], dist_count[16];     /* codes per length */
+    uint16_t lit_limit[16], dist_limit[16];     /* per code length l: (first code + codes of that length) << (15 - l); while building: the counts */
+    int16_t lit_delta[16], dist_delta[16];      /* index in sym[] of the first symbol of length l, minus the first code of length l */
     uint16_t lit_sym[288], dist_sym[32];        /* symbols in canonical order */
     uint8_t lens[320];                          /* code lengths as read */
     uint32_t fixed;                             /* the tables hold the fixed code */
 };
+/* base value << 8 | extra bits of the 29 length symbols ([0..28]) and the 30 distance symbols ([32..61]); one table per CTA */
+constexpr int INF_BASE_WORDS = 64;
 
 #if XM_DEVICE_PASS
 #define XM_INF_LANE ((int)(threadIdx.x & 31))
@@ -64,31 +67,63 @@ XM_HD uint32_t inf_bitrev(uint32_t v, int n)
 #endif
 }
 
-/* canonical code of `n` lengths -> count[], sym[] and the look-up table of `bits` index bits.
+/* lengths 3..258: eight symbols without extra bits, then four per extra-bit count (RFC 1951, 3.2.5); s = symbol - 257 */
+XM_HD uint32_t inf_len_base(int s)
+{
+    if (s < 8) return 3u + (uint32_t)s;
+    if (s == 28) return 258u;
+    const uint32_t x = (uint32_t)(s - 4) >> 2;
+    return 3u + ((4u + ((uint32_t)s & 3u)) << x);
+}
+XM_HD int inf_len_extra(int s) { return (s < 8 || s == 28) ? 0 : (s - 4) >> 2; }
+/* distances 1..32768: four symbols without extra bits, then two per extra-bit count */
+XM_HD uint32_t inf_dist_base(int s)
+{
+    if (s < 4) return 1u + (uint32_t)s;
+    const uint32_t x = (uint32_t)(s - 2) >> 1;
+    return 1u + ((2u + ((uint32_t)s & 1u)) << x);
+}
+XM_HD int inf_dist_extra(int s) { return s < 4 ? 0 : (s - 2) >> 1; }
+XM_HD uint32_t inf_base_word(int k)
+{
+    if (k < 29) return (inf_len_base(k) << 8) | (uint32_t)inf_len_extra(k);
+    if (k >= 32 && k < 62) return (inf_dist_base(k - 32) << 8) | (uint32_t)inf_dist_extra(k - 32);
+    return 0;
+}
+
+/* canonical code of `n` lengths -> limit[], delta[], sym[] and the look-up table of `bits` index bits.
  * Returns false for an over-subscribed set, or an incomplete one unless it is a lone one-bit code (zlib's rule). */
-XM_HD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sym, uint16_t *lut, int bits)
+XM_HD bool inf_build(const uint8_t *lens, int n, uint16_t *limit, int16_t *delta, uint16_t *sym, uint16_t *lut, int bits)
 {
     const int lane = XM_INF_LANE;
-    uint16_t offs[16];
-    if (lane == 0) for (int l = 0; l < 16; ++l) count[l] = 0;
+    uint16_t offs[16], count[16];
+    uint16_t *cnt = limit;                       /* the counts are gathered in limit[] */
+    if (lane == 0) for (int l = 0; l < 16; ++l) cnt[l] = 0;
     XM_INF_SYNC();
-    if (lane == 0) for (int s = 0; s < n; ++s) count[lens[s]]++;
+    if (lane == 0) for (int s = 0; s < n; ++s) cnt[lens[s]]++;
     XM_INF_SYNC();
     int left = 1, used = 0;
     for (int l = 1; l < 16; ++l) {
+        count[l] = cnt[l];
         left <<= 1;
         left -= (int)count[l];
         if (left < 0) return false;
         used += count[l];
     }
-    if (left > 0 && !(used == 1 && count[1] == 1) && used != 0) return false;
     if (used == 0) return false;
+    if (left > 0 && !(used == 1 && count[1] == 1)) return false;
+    XM_INF_SYNC();                               /* every lane has read the counts: limit[] may be overwritten */
     /* first code of each length (MSB-first canonical code) and first slot in sym[] */
     uint32_t next_code[16];
     {
         uint32_t code = 0;
         uint16_t o = 0;
-        for (int l = 1; l < 16; ++l) { next_code[l] = code; offs[l] = o; code = (code + count[l]) << 1; o = (uint16_t)(o + count[l]); }
+        for (int l = 1; l < 16; ++l) {
+            next_code[l] = code; offs[l] = o;
+            if (lane == 0) { limit[l] = (uint16_t)((code + count[l]) << (15 - l)); delta[l] = (int16_t)((int)o - (int)code); }
+            code = (code + count[l]) << 1;
+            o = (uint16_t)(o + count[l]);
+        }
     }
     for (int k = lane; k < (1 << bits); k += XM_INF_LANES) lut[k] = 0;
     XM_INF_SYNC();
@@ -142,8 +177,9 @@ XM_HD uint32_t inf_take(InfBits &B, int n)
     return v;
 }
 
-/* one symbol of a canonical code: the table for codes of at most `bits` bits, bit by bit beyond (at least 15 bits buffered) */
-XM_HD int inf_symbol(InfBits &B, const uint16_t *lut, int bits, const uint16_t *count, const uint16_t *sym)
+/* one symbol of a canonical code (at least 15 bits buffered): the table for codes of at most `bits` bits; a longer code is
+ * found by its length -- the next 15 bits, first bit on top, lie below limit[l] for the first time at the code's length */
+XM_HD int inf_symbol(InfBits &B, const uint16_t *lut, int bits, const uint16_t *limit, const int16_t *delta, const uint16_t *sym)
 {
     const uint32_t e = lut[(uint32_t)B.bb & ((1u << bits) - 1u)];
     if (e) {
@@ -152,46 +188,23 @@ XM_HD int inf_symbol(InfBits &B, const uint16_t *lut, int bits, const uint16_t *
         B.bc -= l;
         return (int)(e & 0x1ffu);
     }
-    int code = 0, first = 0, index = 0;
-    for (int l = 1; l < 16; ++l) {
-        code |= (int)((B.bb >> (l - 1)) & 1u);
-        const int c = (int)count[l];
-        if (code - c < first) {
+    const uint32_t v = inf_bitrev((uint32_t)B.bb & 0x7fffu, 15);
+    for (int l = bits + 1; l < 16; ++l) {
+        if (v < (uint32_t)limit[l]) {
             B.bb >>= l;
             B.bc -= l;
-            return (int)sym[index + (code - first)];
+            return (int)sym[(int)(v >> (15 - l)) + (int)delta[l]];
         }
-        index += c;
-        first += c;
-        first <<= 1;
-        code <<= 1;
     }
     return -1;
 }
 
-XM_HD uint32_t inf_len_base(int s)        /* s = symbol - 257, 0..28 */
-{
-    /* lengths 3..258: eight codes without extra bits, then four per extra-bit count */
-    if (s < 8) return 3u + (uint32_t)s;
-    if (s == 28) return 258u;
-    const uint32_t x = (uint32_t)(s - 4) >> 2;
-    return 3u + ((4u + ((uint32_t)s & 3u)) << x);
-}
-XM_HD int inf_len_extra(int s) { return (s < 8 || s == 28) ? 0 : (s - 4) >> 2; }
-XM_HD uint32_t inf_dist_base(int s)       /* 0..29 */
-{
-    if (s < 4) return 1u + (uint32_t)s;
-    const uint32_t x = (uint32_t)(s - 2) >> 1;
-    return 1u + ((2u + ((uint32_t)s & 1u)) << x);
-}
-XM_HD int inf_dist_extra(int s) { return s < 4 ? 0 : (s - 2) >> 1; }
-
 /*
  * Raw DEFLATE stream at `in` (in_len bytes, readable as aligned words up to 12 bytes past its end) -> exactly
  * out_len bytes at `out`.  Every lane of the warp calls it with the same arguments; returns INF_OK or an INF_E_* code
- * (the same in every lane).
+ * (the same in every lane).  base: inf_base_word(0..63).
  */
-XM_HD int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, InflateTables &T)
+XM_HD int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_len, InflateTables &T, const uint32_t *base)
 {
     const int lane = XM_INF_LANE;
     InfBits B;
@@ -222,11 +235,11 @@ XM_HD int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t
                     XM_INF_SYNC();
                     for (int s = lane; s < 288; s += XM_INF_LANES) T.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
                     XM_INF_SYNC();
-                    inf_build(T.lens, 288, T.lit_count, T.lit_sym, T.lit_lut, INF_LIT_BITS);
+                    inf_build(T.lens, 288, T.lit_limit, T.lit_delta, T.lit_sym, T.lit_lut, INF_LIT_BITS);
                     XM_INF_SYNC();
                     for (int s = lane; s < 32; s += XM_INF_LANES) T.lens[s] = 5;          /* 30 and 31 complete the code and are refused when met */
                     XM_INF_SYNC();
-                    inf_build(T.lens, 32, T.dist_count, T.dist_sym, T.dist_lut, INF_DIST_BITS);
+                    inf_build(T.lens, 32, T.dist_limit, T.dist_delta, T.dist_sym, T.dist_lut, INF_DIST_BITS);
                     if (lane == 0) T.fixed = 1;
                     XM_INF_SYNC();
                 }
@@ -246,13 +259,13 @@ XM_HD int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t
                 }
                 for (int s = lane; s < 19; s += XM_INF_LANES) T.lens[s] = (uint8_t)((cl[s / 8] >> (4 * (s % 8))) & 7u);
                 XM_INF_SYNC();
-                if (!inf_build(T.lens, 19, T.dist_count, T.dist_sym, T.dist_lut, 7)) return INF_E_CODES;
-                /* the nlen + ndist code lengths, run-length coded; kept in a register window and written by lane 0 */
+                if (!inf_build(T.lens, 19, T.dist_limit, T.dist_delta, T.dist_sym, T.dist_lut, 7)) return INF_E_CODES;
+                /* the nlen + ndist code lengths, run-length coded; lane 0 writes them */
                 int idx = 0;
                 uint32_t prev = 0;
                 while (idx < nlen + ndist) {
                     XM_INF_NEED(B, 15 + 7);
-                    const int s = inf_symbol(B, T.dist_lut, 7, T.dist_count, T.dist_sym);
+                    const int s = inf_symbol(B, T.dist_lut, 7, T.dist_limit, T.dist_delta, T.dist_sym);
                     if (s < 0) return INF_E_CODES;
                     uint32_t val = 0;
                     int rep = 1;
@@ -261,56 +274,80 @@ XM_HD int inflate_raw(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t
                     else if (s == 17) { rep = 3 + (int)inf_take(B, 3); prev = 0; }
                     else { rep = 11 + (int)inf_take(B, 7); prev = 0; }
                     if (idx + rep > nlen + ndist) return INF_E_CODES;
-                    /* the lengths go to the far end of lens[] first: the code-length code's own lengths sit in lens[0..18] and its
-                     * count[]/sym[] were built from them already, so overwriting is safe -- but all lanes must have read before */
+                    /* lens[0..18] held the code-length code's own lengths: its tables are built, every lane is past reading them */
                     if (lane == 0) for (int k = 0; k < rep; ++k) T.lens[idx + k] = (uint8_t)val;
                     idx += rep;
                 }
                 XM_INF_SYNC();
                 if (T.lens[256] == 0) return INF_E_CODES;                    /* no end-of-block code */
-                if (!inf_build(T.lens, nlen, T.lit_count, T.lit_sym, T.lit_lut, INF_LIT_BITS)) return INF_E_CODES;
-                XM_INF_SYNC();
-                /* the distance lengths follow the literal/length ones; a block of literals only may have no usable distance code */
-                bool any = false;
+                bool any = false;                                            /* a block of literals only may have no distance code */
                 for (int k = 0; k < ndist; ++k) any = any || T.lens[nlen + k] != 0;
+                XM_INF_SYNC();
+                if (!inf_build(T.lens, nlen, T.lit_limit, T.lit_delta, T.lit_sym, T.lit_lut, INF_LIT_BITS)) return INF_E_CODES;
+                XM_INF_SYNC();
                 if (any) {
-                    if (!inf_build(T.lens + nlen, ndist, T.dist_count, T.dist_sym, T.dist_lut, INF_DIST_BITS)) return INF_E_CODES;
+                    if (!inf_build(T.lens + nlen, ndist, T.dist_limit, T.dist_delta, T.dist_sym, T.dist_lut, INF_DIST_BITS)) return INF_E_CODES;
                 } else {
-                    if (lane == 0) for (int l = 0; l < 16; ++l) T.dist_count[l] = 0;
+                    if (lane == 0) for (int l = 0; l < 16; ++l) T.dist_limit[l] = 0;
                     for (int k = lane; k < (1 << INF_DIST_BITS); k += XM_INF_LANES) T.dist_lut[k] = 0;
                 }
                 XM_INF_SYNC();
             }
-            /* the symbols */
+            /* The symbols.  Literals wait in a register, four at a time, and leave with one store of lanes 0..3.  A match of at
+             * most 32 bytes that does not overlap itself is LOADED when it is met and STORED when the next match (or the end
+             * of the block) comes: the decode of the symbols in between hides the load's round trip to L2. */
+            uint32_t lit_acc = 0, lit_n = 0;
+            uint32_t pend_pos = 0, pend_len = 0, pend_byte = 0;
+#define XM_INF_FLUSH()                                                                                              \
+    do {                                                                                                            \
+        if ((uint32_t)lane < lit_n) out[pos - lit_n + (uint32_t)lane] = (uint8_t)(lit_acc >> (8u * (uint32_t)lane)); \
+        lit_acc = 0; lit_n = 0;                                                                                     \
+    } while (0)
+#define XM_INF_COMMIT()                                                                                             \
+    do {                                                                                                            \
+        if ((uint32_t)lane < pend_len) out[pend_pos + (uint32_t)lane] = (uint8_t)pend_byte;                         \
+        pend_len = 0;                                                                                               \
+    } while (0)
             for (;;) {
                 XM_INF_NEED(B, 20);
-                const int s = inf_symbol(B, T.lit_lut, INF_LIT_BITS, T.lit_count, T.lit_sym);
+                const int s = inf_symbol(B, T.lit_lut, INF_LIT_BITS, T.lit_limit, T.lit_delta, T.lit_sym);
                 if (s < 0) return INF_E_SYMBOL;
                 if (s < 256) {
                     if (pos >= out_len) return INF_E_OVERRUN;
-                    if (lane == 0) out[pos] = (uint8_t)s;
-                    ++pos;
+                    lit_acc |= (uint32_t)s << (8u * lit_n);
+                    ++lit_n; ++pos;
+                    if (lit_n == (XM_INF_LANES >= 4 ? 4u : 1u)) XM_INF_FLUSH();
                     continue;
                 }
-                if (s == 256) break;
+                XM_INF_FLUSH();
+                if (s == 256) { XM_INF_COMMIT(); break; }
                 if (s > 285) return INF_E_SYMBOL;
-                const uint32_t len = inf_len_base(s - 257) + inf_take(B, inf_len_extra(s - 257));
+                const uint32_t lw = base[s - 257];
+                const uint32_t len = (lw >> 8) + inf_take(B, (int)(lw & 15u));
                 XM_INF_NEED(B, 28);
-                const int d = inf_symbol(B, T.dist_lut, INF_DIST_BITS, T.dist_count, T.dist_sym);
+                const int d = inf_symbol(B, T.dist_lut, INF_DIST_BITS, T.dist_limit, T.dist_delta, T.dist_sym);
                 if (d < 0 || d > 29) return INF_E_DISTANCE;
-                const uint32_t dist = inf_dist_base(d) + inf_take(B, inf_dist_extra(d));
+                const uint32_t dw = base[32 + d];
+                const uint32_t dist = (dw >> 8) + inf_take(B, (int)(dw & 15u));
                 if (dist > pos) return INF_E_DISTANCE;
                 if (pos + len > out_len) return INF_E_OVERRUN;
+                XM_INF_COMMIT();
                 XM_INF_SYNC();                                            /* the bytes the match reads are written */
                 const uint8_t *from = out + pos - dist;
                 if (dist >= len) {
-                    for (uint32_t k = (uint32_t)lane; k < len; k += XM_INF_LANES) out[pos + k] = from[k];
+                    if (len <= (uint32_t)XM_INF_LANES && XM_INF_LANES > 1) {
+                        if ((uint32_t)lane < len) pend_byte = from[lane];
+                        pend_pos = pos; pend_len = len;
+                    } else
+                        for (uint32_t k = (uint32_t)lane; k < len; k += XM_INF_LANES) out[pos + k] = from[k];
                 } else {
                     /* the match overlaps what it writes: the source repeats with period dist */
                     for (uint32_t k = (uint32_t)lane; k < len; k += XM_INF_LANES) out[pos + k] = from[k % dist];
                 }
                 pos += len;
             }
+#undef XM_INF_FLUSH
+#undef XM_INF_COMMIT
         } else
             return INF_E_HEADER;
         if (bfinal) break;
@@ -400,15 +437,17 @@ k_bgzf_inflate(const uint8_t *comp, const BgzfDev *blocks, uint32_t n, uint8_t *
     __shared__ InflateTables s_tab[INF_WARPS];
     __shared__ uint32_t s_crc[256];
     __shared__ uint32_t s_op[INF_WARPS][32], s_slice[INF_WARPS][32];
+    __shared__ uint32_t s_base[INF_BASE_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x) s_crc[k] = crc_table_entry(k);
+    if (threadIdx.x < INF_BASE_WORDS) s_base[threadIdx.x] = inf_base_word((int)threadIdx.x);
     __syncthreads();
     const uint32_t b = blockIdx.x * INF_WARPS + (uint32_t)warp;
     if (b >= n) return;
     const BgzfDev blk = blocks[b];
     if (!blk.out_len && blk.in_len <= 2) return;             /* the empty block at the end of the file */
     uint8_t *dst = out + blk.out_off;
-    int rc = inflate_raw(comp + blk.in_off, blk.in_len, dst, blk.out_len, s_tab[warp]);
+    int rc = inflate_raw(comp + blk.in_off, blk.in_len, dst, blk.out_len, s_tab[warp], s_base);
     if (rc == INF_OK && check_crc && blk.out_len) {
         __syncwarp();
         uint32_t lo, hi, L;
