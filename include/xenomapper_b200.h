@@ -187,6 +187,17 @@ int xm_classify_streams(xm_ctx *ctx, int fd_prim, int fd_sec, const int out_fds[
 /* len bytes as BGZF members appended to fd (deflated by the host thread pool); eof != 0: the 28-byte end-of-file
  * member behind them.  No context needed. */
 int xm_bgzf_write(int fd, const void *data, uint64_t len, int eof);
+/* The bins of an XM_OUT_BGZF walk are deflated ON THE DEVICE before they are copied back (csrc/xm_deflate.h: one warp
+ * per member, one prefix code per bin fitted to a sample of its bytes; XM_BGZF_DEFLATE=host in the environment keeps
+ * zlib on the host threads).  The same compressor for a host buffer: len bytes in, BGZF members out (no end-of-file
+ * member); *out stays valid until the next call on the context. */
+int xm_bgzf_deflate_host(xm_ctx *ctx, const void *data, uint64_t len, const void **out, uint64_t *out_len);
+typedef struct xm_bgzf_stats {
+    uint64_t in_bytes, out_bytes, members;   /* of the device compressor, since the last reset */
+    float kernel_ms;                         /* device time of its kernels */
+    uint32_t n_launches;
+} xm_bgzf_stats;
+int xm_bgzf_get_stats(xm_ctx *ctx, xm_bgzf_stats *out, int reset);
 
 /* ---- headers -------------------------------------------------------------- */
 

@@ -25,7 +25,8 @@ EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_cla
            "xm_bam_header_text", "xm_bam_render_host", "xm_bam_get_stats", "xm_get_walk_kernels",
            "xm_comm_unique_id", "xm_comm_init_rank", "xm_comm_destroy", "xm_comm_barrier", "xm_comm_allreduce_f64",
            "xm_classify_sharded_device", "xm_classify_sharded_host", "xm_copy_ceiling",
-           "xm_process_headers_fds", "xm_process_headers_mem", "xm_classify_fds_ex", "xm_bgzf_write", "xm_classify_streams")
+           "xm_process_headers_fds", "xm_process_headers_mem", "xm_classify_fds_ex", "xm_bgzf_write", "xm_classify_streams",
+           "xm_bgzf_deflate_host", "xm_bgzf_get_stats")
 OUT_BGZF = 1
 
 
@@ -64,6 +65,10 @@ class BamStats(C.Structure):
     _fields_ = [("inflate_s", C.c_double), ("render_ms", C.c_float), ("n_launches", C.c_uint32), ("bam_bytes", C.c_uint64),
                 ("inflated_bytes", C.c_uint64), ("text_bytes", C.c_uint64), ("records", C.c_uint64),
                 ("upload_s", C.c_double), ("inflate_ms", C.c_float), ("chain_repairs", C.c_uint32)]
+
+
+class BgzfStats(C.Structure):
+    _fields_ = [("in_bytes", C.c_uint64), ("out_bytes", C.c_uint64), ("members", C.c_uint64), ("kernel_ms", C.c_float), ("n_launches", C.c_uint32)]
 
 
 class XenomapperLibraryError(RuntimeError):
@@ -349,6 +354,20 @@ class Context:
             raise UnsupportedInput(self.error())
         del keep
         return C.string_at(p.value, ln.value) if ln.value else b""
+
+    def bgzf_deflate_host(self, data):
+        """data as BGZF members (no end-of-file member), deflated on the device"""
+        a, n, keep = _host_ptr(data)
+        p, ln = C.c_void_p(), C.c_uint64()
+        rc = self.lib.xm_bgzf_deflate_host(self.h, a, n, C.byref(p), C.byref(ln))
+        self._check(rc, "xm_bgzf_deflate_host")
+        del keep
+        return C.string_at(p.value, ln.value) if ln.value else b""
+
+    def bgzf_stats(self, reset=True):
+        st = BgzfStats()
+        self.lib.xm_bgzf_get_stats(self.h, C.byref(st), int(reset))
+        return st
 
     def walk_kernels(self):
         """names of the kernels the last resident walk ran"""

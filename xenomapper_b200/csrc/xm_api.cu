@@ -31,6 +31,7 @@
 #include "xm_bam.h"
 #include "xm_inflate.h"
 #include "xm_bamchain.h"
+#include "xm_deflate.h"
 #include "xm_shard.h"
 #include "xm_headers.h"
 #include "xm_bgzf.h"
@@ -196,6 +197,10 @@ struct xm_ctx {
     HostBuf h_bam[2];
     DevBuf d_bam[2], d_bam_rec[2], d_bam_ref[2], d_bam_len[2], d_bam_sum[2], d_bam_text[2];
     DevBuf d_bam_comp[2], d_bam_tab[2], d_bam_seg[2];      /* compressed window, its block table, the chain's segments */
+    /* BGZF output deflated on the device (xm_deflate.h): member slots, sizes + offsets + plan, packed members per output set and bin */
+    DevBuf d_zslot, d_zmeta, d_zout[2][6];
+    std::vector<uint8_t> z_host;
+    xm_bgzf_stats bgzf_stats{};
     std::vector<uint8_t> bam_text_host;
     xm_bam_stats bam_stats{};
     /* the walk across GPUs (xm_shard.h): communicator, row scratch, shard staging of the host entry point */
@@ -284,7 +289,9 @@ void xm_destroy(xm_ctx *c)
     for (auto &s : c->d_out) for (auto &b : s) if (b.p) cudaFree(b.p);
     for (auto &b : c->h_stage) if (b.p) cudaFreeHost(b.p);
     for (auto &b : c->h_bam) if (b.p) cudaFreeHost(b.p);
-    for (auto *arr : {c->d_bam, c->d_bam_rec, c->d_bam_ref, c->d_bam_len, c->d_bam_sum, c->d_bam_text, c->d_bam_comp, c->d_bam_tab, c->d_bam_seg}) for (int k = 0; k < 2; ++k) if (arr[k].p) cudaFree(arr[k].p);
+    if (c->d_zslot.p) cudaFree(c->d_zslot.p);
+    if (c->d_zmeta.p) cudaFree(c->d_zmeta.p);
+    for (auto *arr : {c->d_bam, c->d_bam_rec, c->d_bam_ref, c->d_bam_len, c->d_bam_sum, c->d_bam_text, c->d_bam_comp, c->d_bam_tab, c->d_bam_seg, c->d_zout[0], c->d_zout[0] + 2, c->d_zout[0] + 4, c->d_zout[1], c->d_zout[1] + 2, c->d_zout[1] + 4}) for (int k = 0; k < 2; ++k) if (arr[k].p) cudaFree(arr[k].p);
     for (auto &v : c->bins) for (auto &b : v) cudaFreeHost(b.p);
     for (auto &b : c->pool) cudaFreeHost(b.p);
     if (c->dl) cudaStreamDestroy(c->dl);
@@ -471,6 +478,60 @@ static int bin_append_d2h(xm_ctx *c, int b, const uint8_t *d_src, uint64_t n)
 }
 
 static int host_threads();
+static int upload_shard(xm_ctx *c, uint8_t *d_dst, const uint8_t *src, uint64_t n);
+
+static bool bgzf_on_host()
+{
+    const char *e = getenv("XM_BGZF_DEFLATE");
+    return e && !strcmp(e, "host");
+}
+
+/* n bytes at d_src (device, 4-byte aligned, readable 8 bytes past the end) as BGZF members in `Z` (device): xm_deflate.h.
+ * plan: the bin's code, made from a sample of these bytes when *have_plan is false.  The stream is synchronised on return. */
+static int device_bgzf(xm_ctx *c, const uint8_t *d_src, uint64_t n, DevBuf &Z, uint64_t *z_len, DeflatePlan *plan, bool *have_plan)
+{
+    *z_len = 0;
+    if (!n) return XM_OK;
+    cudaStream_t st = c->be.st;
+    const uint64_t members = (n + DEF_IN_MAX - 1) / DEF_IN_MAX;
+    int rc;
+    const uint64_t meta = members * 4 + 8 + (members + 1) * 8 + sizeof(DeflatePlan);
+    if ((rc = reserve_dev(c, c->d_zslot, members * (uint64_t)DEF_SLOT + 64)) || (rc = reserve_dev(c, c->d_zmeta, meta + 64))) return rc;
+    unsigned long long *d_offs = (unsigned long long *)c->d_zmeta.p;
+    DeflatePlan *d_plan = (DeflatePlan *)(d_offs + members + 1);
+    uint32_t *d_sizes = (uint32_t *)(d_plan + 1);
+    if (!*have_plan) {
+        std::vector<uint8_t> sample((size_t)std::min<uint64_t>(n, 256u << 10));
+        XM_CUDA(c, cudaMemcpyAsync(sample.data(), d_src, sample.size(), cudaMemcpyDeviceToHost, st), "D2H copy");
+        XM_CUDA(c, cudaStreamSynchronize(st), "D2H copy");
+        deflate_plan(sample.data(), sample.size(), *plan);
+        *have_plan = true;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaMemcpyAsync(d_plan, plan, sizeof *plan, cudaMemcpyHostToDevice, st);
+    cudaEventRecord(e0, st);
+    k_bgzf_deflate<<<(unsigned)((members + DEF_WARPS - 1) / DEF_WARPS), DEF_WARPS * 32, 0, st>>>(d_src, n, (uint32_t)members, d_plan, c->d_zslot.p, d_sizes);
+    k_bgzf_offsets<<<1, 1024, 0, st>>>(d_sizes, (uint32_t)members, d_offs);
+    unsigned long long total = 0;
+    cudaMemcpyAsync(&total, d_offs + members, 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(c, e, "BGZF deflate kernel"); }
+    if ((rc = reserve_dev(c, Z, total + 64))) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    k_bgzf_pack<<<(unsigned)((members * 32 + 255) / 256), 256, 0, st>>>(c->d_zslot.p, d_sizes, d_offs, (uint32_t)members, Z.p);
+    cudaEventRecord(e1, st);
+    e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) return cuda_fail(c, e, "BGZF pack kernel");
+    c->bgzf_stats.in_bytes += n; c->bgzf_stats.out_bytes += total; c->bgzf_stats.members += members; c->bgzf_stats.kernel_ms += ms;
+    c->bgzf_stats.n_launches += 3;
+    *z_len = total;
+    return XM_OK;
+}
 
 /* The bins of a descriptor walk are written by a thread of their own: a step's blocks are queued behind the event
  * that marks the end of their D2H copies, written with write(2) in bin order, and handed back to the pool. */
@@ -648,7 +709,10 @@ static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opt
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, c->be.st);
-    BinWriter *writer = out_fds ? new BinWriter(c, out_fds, (out_flags & XM_OUT_BGZF) != 0) : nullptr;
+    const bool z_device = out_fds && (out_flags & XM_OUT_BGZF) && !bgzf_on_host();
+    std::vector<DeflatePlan> z_plan(6);
+    bool z_have[6] = {false, false, false, false, false, false};
+    BinWriter *writer = out_fds ? new BinWriter(c, out_fds, (out_flags & XM_OUT_BGZF) != 0 && !z_device) : nullptr;
     int emit_rc = XM_OK;
     cudaEvent_t set_done[2];
     bool set_used[2] = {false, false};
@@ -663,6 +727,13 @@ static int stream_walk(xm_ctx *c, HostIn in[2], const int *out_fds, const xm_opt
             return;
         }
         if (writer) writer->reclaim();
+        if (z_device) {
+            /* the bin leaves the device as BGZF members: deflated where it lies, then copied */
+            uint64_t zn = 0;
+            emit_rc = device_bgzf(c, d_src, n, c->d_zout[set][b], &zn, &z_plan[b], &z_have[b]);
+            if (!emit_rc) emit_rc = bin_append_d2h(c, b, c->d_zout[set][b].p, zn);
+            return;
+        }
         emit_rc = bin_append_d2h(c, b, d_src, n);
     };
     int wait_rc = XM_OK;
@@ -734,6 +805,36 @@ int xm_classify_fds(xm_ctx *c, int fd_prim, int64_t off_prim, int fd_sec, int64_
                     const xm_opts *opts, xm_result *res)
 {
     return xm_classify_fds_ex(c, fd_prim, off_prim, fd_sec, off_sec, out_fds, opts, 0, res);
+}
+
+int xm_bgzf_deflate_host(xm_ctx *c, const void *data, uint64_t len, const void **out, uint64_t *out_len)
+{
+    if (!c || (!data && len) || !out || !out_len) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    *out = nullptr; *out_len = 0;
+    int rc;
+    if ((rc = reserve_dev(c, c->d_bam_text[0], len + 64))) return rc;           /* any idle device buffer will do for the input */
+    if ((rc = upload_shard(c, c->d_bam_text[0].p, (const uint8_t *)data, len))) return rc;
+    DeflatePlan plan;
+    bool have = false;
+    uint64_t zn = 0;
+    if ((rc = device_bgzf(c, c->d_bam_text[0].p, len, c->d_zout[0][0], &zn, &plan, &have))) return rc;
+    c->z_host.resize(zn);
+    if (zn) {
+        XM_CUDA(c, cudaMemcpyAsync(c->z_host.data(), c->d_zout[0][0].p, zn, cudaMemcpyDeviceToHost, c->be.st), "D2H copy");
+        XM_CUDA(c, cudaStreamSynchronize(c->be.st), "D2H copy");
+    }
+    *out = c->z_host.data();
+    *out_len = zn;
+    return XM_OK;
+}
+
+int xm_bgzf_get_stats(xm_ctx *c, xm_bgzf_stats *out, int reset)
+{
+    if (!c || !out) return XM_ERR_ARG;
+    *out = c->bgzf_stats;
+    if (reset) c->bgzf_stats = xm_bgzf_stats{};
+    return XM_OK;
 }
 
 int xm_bgzf_write(int fd, const void *data, uint64_t len, int eof)
