@@ -495,23 +495,35 @@ static int device_bgzf(xm_ctx *c, const uint8_t *d_src, uint64_t n, DevBuf &Z, u
     cudaStream_t st = c->be.st;
     const uint64_t members = (n + DEF_IN_MAX - 1) / DEF_IN_MAX;
     int rc;
-    const uint64_t meta = members * 4 + 8 + (members + 1) * 8 + sizeof(DeflatePlan);
+    const uint64_t meta = members * 4 + 8 + (members + 1) * 8 + sizeof(DeflatePlan) + 316 * 4 + 16;
     if ((rc = reserve_dev(c, c->d_zslot, members * (uint64_t)DEF_SLOT + 64)) || (rc = reserve_dev(c, c->d_zmeta, meta + 64))) return rc;
     unsigned long long *d_offs = (unsigned long long *)c->d_zmeta.p;
     DeflatePlan *d_plan = (DeflatePlan *)(d_offs + members + 1);
     uint32_t *d_sizes = (uint32_t *)(d_plan + 1);
     if (!*have_plan) {
+        /* the bin's code: a first guess from a sample of its bytes; the first members are deflated with it and the
+         * symbols of the tokens that come out make the code that is used */
         std::vector<uint8_t> sample((size_t)std::min<uint64_t>(n, 256u << 10));
         XM_CUDA(c, cudaMemcpyAsync(sample.data(), d_src, sample.size(), cudaMemcpyDeviceToHost, st), "D2H copy");
         XM_CUDA(c, cudaStreamSynchronize(st), "D2H copy");
         deflate_plan(sample.data(), sample.size(), *plan);
+        const uint32_t probe = (uint32_t)std::min<uint64_t>(members, 512);
+        uint32_t *d_hist = (uint32_t *)(d_sizes + members + 1);
+        uint32_t hist[316];
+        cudaMemcpyAsync(d_plan, plan, sizeof *plan, cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(d_hist, 0, sizeof hist, st);
+        k_bgzf_deflate<<<(probe + DEF_WARPS - 1) / DEF_WARPS, DEF_WARPS * 32, 0, st>>>(d_src, std::min<uint64_t>(n, (uint64_t)probe * DEF_IN_MAX), probe, d_plan, c->d_zslot.p, d_sizes, d_hist);
+        XM_CUDA(c, cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, st), "D2H copy");
+        XM_CUDA(c, cudaStreamSynchronize(st), "BGZF deflate kernel");
+        deflate_plan_hist(hist, *plan);
+        c->bgzf_stats.n_launches += 1;
         *have_plan = true;
     }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaMemcpyAsync(d_plan, plan, sizeof *plan, cudaMemcpyHostToDevice, st);
     cudaEventRecord(e0, st);
-    k_bgzf_deflate<<<(unsigned)((members + DEF_WARPS - 1) / DEF_WARPS), DEF_WARPS * 32, 0, st>>>(d_src, n, (uint32_t)members, d_plan, c->d_zslot.p, d_sizes);
+    k_bgzf_deflate<<<(unsigned)((members + DEF_WARPS - 1) / DEF_WARPS), DEF_WARPS * 32, 0, st>>>(d_src, n, (uint32_t)members, d_plan, c->d_zslot.p, d_sizes, nullptr);
     k_bgzf_offsets<<<1, 1024, 0, st>>>(d_sizes, (uint32_t)members, d_offs);
     unsigned long long total = 0;
     cudaMemcpyAsync(&total, d_offs + members, 8, cudaMemcpyDeviceToHost, st);

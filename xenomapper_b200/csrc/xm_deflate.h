@@ -111,7 +111,11 @@ inline void canonical_codes(const uint8_t *len, int n, uint32_t *out)
     for (int s = 0; s < n; ++s) out[s] = len[s] ? (bitrev_host(next[len[s]]++, len[s]) | ((uint32_t)len[s] << 16)) : 0u;
 }
 
-/* sample: bytes of the bin (any part of it); n may be 0 (a flat code) */
+/* the plan of given symbol counts (zero counts are raised to one: every symbol stays encodable) */
+inline void deflate_plan_counts(const uint64_t *lf, const uint64_t *df, DeflatePlan &P);
+
+/* first guess from a sample of the bin's bytes (n may be 0: a flat code): literal counts from the sample, made-up counts
+ * for the length and distance symbols */
 inline void deflate_plan(const uint8_t *sample, uint64_t n, DeflatePlan &P)
 {
     uint64_t lf[286], df[30];
@@ -122,6 +126,18 @@ inline void deflate_plan(const uint8_t *sample, uint64_t n, DeflatePlan &P)
     /* matches: about one token in six on SAM text, short ones most often */
     for (int s = 257; s < 286; ++s) lf[s] = std::max<uint64_t>(1, total / 6 / (uint64_t)(4 + (s - 257) * (s - 257) / 4) / 4);
     for (int s = 0; s < 30; ++s) df[s] = 1 + (uint64_t)(s >= 8 ? 8 : 1) * (uint64_t)(s >= 16 ? 2 : 1);       /* distances: the far ones are the common ones */
+    deflate_plan_counts(lf, df, P);
+}
+/* second guess: the tokens k_bgzf_deflate made of the bin's first members with the first plan (hist: 286 + 30 counts) */
+inline void deflate_plan_hist(const uint32_t *hist, DeflatePlan &P)
+{
+    uint64_t lf[286], df[30];
+    for (int s = 0; s < 286; ++s) lf[s] = 4ull * hist[s] + 1;
+    for (int s = 0; s < 30; ++s) df[s] = 4ull * hist[286 + s] + 1;
+    deflate_plan_counts(lf, df, P);
+}
+inline void deflate_plan_counts(const uint64_t *lf, const uint64_t *df, DeflatePlan &P)
+{
     uint8_t ll[286], dl[30];
     huffman_lengths(lf, 286, 15, ll);
     huffman_lengths(df, 30, 15, dl);
@@ -154,6 +170,7 @@ struct DeflateSmem {
     uint32_t lit[286], dist[30];
     uint32_t crc[256];
     uint32_t op[DEF_WARPS][32], slice[DEF_WARPS][32];
+    uint32_t hist[316];              /* tokens by symbol, when the launch collects them */
 };
 
 __device__ __forceinline__ uint32_t def_load4(const uint32_t *W, uint32_t off)
@@ -165,16 +182,17 @@ __device__ __forceinline__ uint32_t def_load4(const uint32_t *W, uint32_t off)
 /* src: 4-byte aligned, readable 8 bytes past its end.  member m covers [m * DEF_IN_MAX, ...); its gzip member is built in
  * slot + m * DEF_SLOT and its size goes to sizes[m]. */
 __global__ void __launch_bounds__(DEF_WARPS * 32, XM_DEF_OCC)
-k_bgzf_deflate(const uint8_t *src, uint64_t n_total, uint32_t n_members, const DeflatePlan *plan, uint8_t *slot, uint32_t *sizes)
+k_bgzf_deflate(const uint8_t *src, uint64_t n_total, uint32_t n_members, const DeflatePlan *plan, uint8_t *slot, uint32_t *sizes, uint32_t *hist)
 {
     __shared__ DeflateSmem S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t k = threadIdx.x; k < 286; k += blockDim.x) S.lit[k] = plan->lit[k];
     if (threadIdx.x < 30) S.dist[threadIdx.x] = plan->dist[threadIdx.x];
     for (uint32_t k = threadIdx.x; k < 256; k += blockDim.x) S.crc[k] = crc_table_entry(k);
+    for (uint32_t k = threadIdx.x; k < 316; k += blockDim.x) S.hist[k] = 0;
     __syncthreads();
     const uint32_t m = blockIdx.x * DEF_WARPS + (uint32_t)warp;
-    if (m >= n_members) return;
+    if (m >= n_members) { if (hist) __syncthreads(); return; }
     const uint64_t lo64 = (uint64_t)m * DEF_IN_MAX;
     const uint32_t n = (uint32_t)((n_total - lo64) < DEF_IN_MAX ? (n_total - lo64) : DEF_IN_MAX);
     const uint8_t *in = src + lo64;
@@ -219,6 +237,38 @@ k_bgzf_deflate(const uint8_t *src, uint64_t n_total, uint32_t n_members, const D
                 mlen = l; mdist = p - c;
             }
         }
+        /* what the match would cost, and what its bytes cost as literals: the literal bits of this step's bytes are summed
+         * by a warp scan, a match that runs past the step is charged at the average of its part inside.  DNA letters get
+         * two- or three-bit codes from the bin's plan: a four-letter match 30 000 bytes back (26 bits) must not replace them */
+        uint32_t b1 = 0, n1 = 0, b2 = 0, n2 = 0, h_lsym = 0, h_dsym = 0;
+        const uint32_t le0 = valid ? S.lit[can ? (v & 0xffu) : (uint32_t)in[p]] : 0u;
+        if (mlen >= (uint32_t)DEF_MIN_MATCH) {
+            const uint32_t l = mlen - 3;
+            uint32_t lsym, lex = 0, lexv = 0;
+            if (mlen == 258) lsym = 28;
+            else if (l < 8) lsym = l;
+            else { lex = (uint32_t)(29 - __clz((int)l)); lsym = 4 * lex + 4 + ((l >> lex) & 3u); lexv = l & ((1u << lex) - 1u); }
+            const uint32_t le = S.lit[257 + lsym], lb = le >> 16;
+            b1 = (le & 0xffffu) | (lexv << lb); n1 = lb + lex; h_lsym = lsym;
+            const uint32_t d = mdist - 1;
+            uint32_t dsym, dex = 0, dexv = 0;
+            if (d < 4) dsym = d;
+            else { dex = (uint32_t)(30 - __clz((int)d)); dsym = 2 * dex + 2 + ((d >> dex) & 1u); dexv = d & ((1u << dex) - 1u); }
+            const uint32_t de = S.dist[dsym], db = de >> 16;
+            b2 = (de & 0xffffu) | (dexv << db); n2 = db + dex; h_dsym = dsym;
+        }
+        {
+            uint32_t lc = le0 >> 16;                               /* inclusive scan of the literal bits */
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, lc, o); if (lane >= o) lc += y; }
+            const uint32_t inside = mlen < 32u - (uint32_t)lane ? mlen : 32u - (uint32_t)lane;       /* bytes of the match inside the step */
+            const uint32_t upto = __shfl_sync(0xffffffffu, lc, (lane + (int)(inside ? inside : 1u) - 1) & 31);
+            if (mlen >= (uint32_t)DEF_MIN_MATCH) {
+                const uint32_t lit_in = upto - (lc - (le0 >> 16));
+                const uint32_t lit_est = lit_in * mlen / inside;
+                if (n1 + n2 + 2u >= lit_est) mlen = 0;
+            }
+        }
         /* greedy selection in position order */
         const uint32_t M = __ballot_sync(0xffffffffu, mlen >= (uint32_t)DEF_MIN_MATCH);
         bool covered = p < cu, selected = false;
@@ -237,24 +287,14 @@ k_bgzf_deflate(const uint8_t *src, uint64_t n_total, uint32_t n_members, const D
         const uint32_t step_end = base + 32 < n ? base + 32 : n;
         cu = cur > step_end ? cur : step_end;
         /* the tokens' bits */
-        uint32_t b1 = 0, n1 = 0, b2 = 0, n2 = 0;
-        if (selected) {
-            const uint32_t l = mlen - 3;
-            uint32_t lsym, lex = 0, lexv = 0;
-            if (mlen == 258) lsym = 28;
-            else if (l < 8) lsym = l;
-            else { lex = (uint32_t)(29 - __clz((int)l)); lsym = 4 * lex + 4 + ((l >> lex) & 3u); lexv = l & ((1u << lex) - 1u); }
-            const uint32_t le = S.lit[257 + lsym], lb = le >> 16;
-            b1 = (le & 0xffffu) | (lexv << lb); n1 = lb + lex;
-            const uint32_t d = mdist - 1;
-            uint32_t dsym, dex = 0, dexv = 0;
-            if (d < 4) dsym = d;
-            else { dex = (uint32_t)(30 - __clz((int)d)); dsym = 2 * dex + 2 + ((d >> dex) & 1u); dexv = d & ((1u << dex) - 1u); }
-            const uint32_t de = S.dist[dsym], db = de >> 16;
-            b2 = (de & 0xffffu) | (dexv << db); n2 = db + dex;
-        } else if (valid && !covered) {
-            const uint32_t e = S.lit[can ? (v & 0xffu) : (uint32_t)in[p]];
-            b1 = e & 0xffffu; n1 = e >> 16;
+        if (!selected) {
+            b2 = 0; n2 = 0;
+            if (valid && !covered) { b1 = le0 & 0xffffu; n1 = le0 >> 16; }
+            else { b1 = 0; n1 = 0; }
+        }
+        if (hist) {
+            if (selected) { atomicAdd(&S.hist[257 + h_lsym], 1u); atomicAdd(&S.hist[286 + h_dsym], 1u); }
+            else if (valid && !covered) atomicAdd(&S.hist[can ? (v & 0xffu) : (uint32_t)in[p]], 1u);
         }
         const uint32_t nb = n1 + n2;
         uint32_t inc = nb;
@@ -321,6 +361,10 @@ k_bgzf_deflate(const uint8_t *src, uint64_t n_total, uint32_t n_members, const D
         uint8_t *t = out + total - 8;
         for (int k = 0; k < 4; ++k) { t[k] = (uint8_t)(crc >> (8 * k)); t[4 + k] = (uint8_t)(n >> (8 * k)); }
         sizes[m] = total;
+    }
+    if (hist) {
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < 316; k += blockDim.x) if (S.hist[k]) atomicAdd(&hist[k], S.hist[k]);
     }
 }
 
