@@ -9,7 +9,9 @@
  * members of at most 64 KiB of input, each with the "BC" extra field that holds
  * the member's size minus one, ended by the 28-byte empty member.  Any gzip
  * reader inflates the concatenation to exactly the SAM text; htslib can index
- * it.  Members are deflated side by side by a pool of host threads.
+ * it.  This file is the host writer: headers, xm_bgzf_write, and the bins when XM_BGZF_DEFLATE=host (members deflated
+ * side by side by a pool of host threads).  The bins of an XM_OUT_BGZF walk are normally deflated on the device:
+ * xm_deflate.h.
  */
 #pragma once
 #include <stdint.h>
