@@ -16,5 +16,6 @@ ncu --set full --clock-control none --import-source on -k regex:k_ -s 6 -c 2 -o 
 XM_ROWS=1 ncu --set full --clock-control none --import-source on -k regex:k_ -s 12 -c 5 -o gpurun_out/${T}_prof_rows -f $CMD > gpurun_out/ncu_full_rows.log 2>&1
 python scripts/bench_bam.py --make 4000000 && python scripts/bench_bam.py > gpurun_out/${T}_bench_bam_4m.json 2> gpurun_out/bench_bam.err; cat gpurun_out/${T}_bench_bam_4m.json
 XM_BAM_INFLATE=host python scripts/bench_bam.py > gpurun_out/${T}_bench_bam_4m_host_inflate.json 2>/dev/null
+timeout 300 python scripts/bench_bgzf.py 2000000 > gpurun_out/${T}_bench_bgzf_device.json 2>/dev/null; cut -c1-300 gpurun_out/${T}_bench_bgzf_device.json
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/${T}_gpu.txt
 ls -la gpurun_out | tail -12

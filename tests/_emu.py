@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "xm_emu.cpp")
 SO = os.path.join(HERE, "emu", "libxm_emu.so")
 DEPS = [SRC] + [os.path.join(ROOT, "xenomapper_b200", "csrc", f) for f in
-                ("xm_common.h", "xm_parse.h", "xm_tile.h", "xm_walk.h", "xm_stream.h", "xm_shard.h", "xm_inflate.h", "xm_bamchain.h")] + [os.path.join(ROOT, "include", "xenomapper_b200.h")]
+                ("xm_common.h", "xm_parse.h", "xm_tile.h", "xm_walk.h", "xm_stream.h", "xm_shard.h", "xm_inflate.h", "xm_bamchain.h", "xm_deflate.h")] + [os.path.join(ROOT, "include", "xenomapper_b200.h")]
 
 
 class Opts(C.Structure):
@@ -75,6 +75,9 @@ def lib():
         _lib.xm_emu_bam_chain.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.c_uint64,
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         _lib.xm_emu_bam_chain.restype = C.c_int64
+        _lib.xm_emu_deflate_literals.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                                 C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
+        _lib.xm_emu_deflate_literals.restype = C.c_uint64
     return _lib
 
 
@@ -169,3 +172,15 @@ def bam_chain(inflated, first, n_ref, seg_bytes=16384):
     if n < 0:
         return None
     return list(rec[:n]), int(end.value), int(rep.value)
+
+
+def deflate_literals(sample, data, hist=None):
+    """csrc/xm_deflate.h's plan (from a byte sample, or from 316 token counts) used to code `data` as one block of literals:
+    (raw DEFLATE bytes, literal/length code lengths, distance code lengths)"""
+    sample, data = bytes(sample), bytes(data)
+    cap = 2 * len(data) + 4096
+    out = C.create_string_buffer(cap)
+    ll, dl = (C.c_uint8 * 286)(), (C.c_uint8 * 30)()
+    h = (C.c_uint32 * 316)(*hist) if hist is not None else None
+    n = lib().xm_emu_deflate_literals(sample, len(sample), h, data, len(data), out, cap, ll, dl)
+    return out.raw[:n], list(ll), list(dl)

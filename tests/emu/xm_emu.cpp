@@ -368,3 +368,28 @@ extern "C" int64_t xm_emu_bam_chain(const void *data, uint64_t have, uint64_t se
     }
     return (int64_t)n_rec;
 }
+
+/* ---- the host half of the device BGZF compressor (csrc/xm_deflate.h): the plan -------------------------------------- */
+#include "../../xenomapper_b200/csrc/xm_deflate.h"
+
+/* `data` as ONE raw DEFLATE block of literals coded with the plan made from `sample` (hist: 316 token counts, or NULL for the
+ * first guess): header bits as the kernel copies them, then the literal codes and the end-of-block code.  Returns the byte count. */
+extern "C" uint64_t xm_emu_deflate_literals(const void *sample, uint64_t ns, const uint32_t *hist, const void *data, uint64_t n, void *out, uint64_t cap,
+                                            uint8_t *lit_len, uint8_t *dist_len)
+{
+    using namespace xm;
+    DeflatePlan P;
+    if (hist) deflate_plan_hist(hist, P); else deflate_plan((const uint8_t *)sample, ns, P);
+    for (int s = 0; s < 286; ++s) lit_len[s] = (uint8_t)(P.lit[s] >> 16);
+    for (int s = 0; s < 30; ++s) dist_len[s] = (uint8_t)(P.dist[s] >> 16);
+    std::vector<uint8_t> bits;                       /* one byte per bit: simple and obviously right */
+    for (uint32_t b = 16; b < P.hdr_bits; ++b) bits.push_back((P.hdr_words[b >> 5] >> (b & 31)) & 1u);
+    auto put = [&](uint32_t e) { for (uint32_t k = 0; k < (e >> 16); ++k) bits.push_back((e >> k) & 1u); };
+    for (uint64_t k = 0; k < n; ++k) put(P.lit[((const uint8_t *)data)[k]]);
+    put(P.lit[256]);
+    const uint64_t nbytes = (bits.size() + 7) / 8;
+    if (nbytes > cap) return 0;
+    memset(out, 0, nbytes);
+    for (size_t b = 0; b < bits.size(); ++b) if (bits[b]) ((uint8_t *)out)[b >> 3] |= (uint8_t)(1u << (b & 7));
+    return nbytes;
+}

@@ -155,3 +155,37 @@ def test_parallel_chain_reports_a_corrupt_length():
     bad = bytearray(raw)
     bad[want[200]:want[200] + 4] = struct.pack("<I", 7)
     assert _emu.bam_chain(bytes(bad), first, n_ref, 4096) is None
+
+
+# ---- the plan of the device BGZF compressor (csrc/xm_deflate.h, host half) ------------------------------------------------
+def _kraft(lengths):
+    from fractions import Fraction
+    return sum(Fraction(1, 2 ** l) for l in lengths if l)
+
+
+@pytest.mark.parametrize("name,data", SAMPLES[1:], ids=[s[0] for s in SAMPLES[1:]])
+def test_deflate_plan_is_a_valid_dynamic_block(name, data):
+    """the header bits the kernel copies in front of every member and the codes it looks up: zlib reads a block coded with them"""
+    stream, ll, dl = _emu.deflate_literals(data[:4096], data)
+    assert all(1 <= l <= 15 for l in ll) and all(1 <= l <= 15 for l in dl)          # every symbol stays encodable
+    assert _kraft(ll) == 1 and _kraft(dl) == 1                                       # complete codes: no inflater objects
+    assert zlib.decompress(stream, -15) == data
+    rc, out = _emu.inflate(stream, len(data))                                        # and the device inflater
+    assert rc == 0 and out == data
+
+
+def test_deflate_plan_from_token_counts():
+    rnd = random.Random(2)
+    data = SAMPLES[8][1]
+    for hist in ([0] * 316, [rnd.randrange(0, 5) ** 6 for _ in range(316)], [10 ** 9] * 316, [1 << k % 31 for k in range(316)]):
+        stream, ll, dl = _emu.deflate_literals(b"", data, hist=hist)
+        assert max(ll) <= 15 and max(dl) <= 15 and min(ll) >= 1 and min(dl) >= 1
+        assert _kraft(ll) == 1 and _kraft(dl) == 1
+        assert zlib.decompress(stream, -15) == data
+
+
+def test_deflate_plan_fits_the_sample():
+    data = SAMPLES[7][1]                                   # DNA: four letters
+    stream, ll, dl = _emu.deflate_literals(data[:8192], data)
+    assert max(ll[c] for c in b"ACGT") <= 3
+    assert len(stream) < 0.3 * len(data)
