@@ -78,7 +78,7 @@ def test_device_deflate_is_read_by_any_inflater(ctx, name, data, max_ratio):
     z = ctx.bgzf_deflate_host(data)
     assert gzip.decompress(z + EOF_MEMBER) == data
     ms = members(z)
-    assert len(ms) == (len(data) + 0xff00 - 1) // 0xff00
+    assert (len(data) + 0xff00 - 1) // 0xff00 <= len(ms) <= (len(data) + 0x4000 - 1) // 0x4000      # small inputs are cut finer
     at = 0
     for m in ms:
         isize = struct.unpack_from("<I", m, len(m) - 4)[0]

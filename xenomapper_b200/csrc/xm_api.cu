@@ -493,10 +493,13 @@ static int device_bgzf(xm_ctx *c, const uint8_t *d_src, uint64_t n, DevBuf &Z, u
     *z_len = 0;
     if (!n) return XM_OK;
     cudaStream_t st = c->be.st;
-    const uint64_t members = (n + DEF_IN_MAX - 1) / DEF_IN_MAX;
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, c->device);
+    const uint32_t in_per = deflate_member_bytes(n, (uint32_t)sm_count), slot_bytes = deflate_slot_bytes(in_per);
+    const uint64_t members = (n + in_per - 1) / in_per;
     int rc;
     const uint64_t meta = members * 4 + 8 + (members + 1) * 8 + sizeof(DeflatePlan) + 316 * 4 + 16;
-    if ((rc = reserve_dev(c, c->d_zslot, members * (uint64_t)DEF_SLOT + 64)) || (rc = reserve_dev(c, c->d_zmeta, meta + 64))) return rc;
+    if ((rc = reserve_dev(c, c->d_zslot, members * (uint64_t)slot_bytes + 64)) || (rc = reserve_dev(c, c->d_zmeta, meta + 64))) return rc;
     unsigned long long *d_offs = (unsigned long long *)c->d_zmeta.p;
     DeflatePlan *d_plan = (DeflatePlan *)(d_offs + members + 1);
     uint32_t *d_sizes = (uint32_t *)(d_plan + 1);
@@ -512,7 +515,7 @@ static int device_bgzf(xm_ctx *c, const uint8_t *d_src, uint64_t n, DevBuf &Z, u
         uint32_t hist[316];
         cudaMemcpyAsync(d_plan, plan, sizeof *plan, cudaMemcpyHostToDevice, st);
         cudaMemsetAsync(d_hist, 0, sizeof hist, st);
-        k_bgzf_deflate<<<(probe + DEF_WARPS - 1) / DEF_WARPS, DEF_WARPS * 32, 0, st>>>(d_src, std::min<uint64_t>(n, (uint64_t)probe * DEF_IN_MAX), probe, d_plan, c->d_zslot.p, d_sizes, d_hist);
+        k_bgzf_deflate<<<(probe + DEF_WARPS - 1) / DEF_WARPS, DEF_WARPS * 32, 0, st>>>(d_src, std::min<uint64_t>(n, (uint64_t)probe * in_per), probe, in_per, slot_bytes, d_plan, c->d_zslot.p, d_sizes, d_hist);
         XM_CUDA(c, cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, st), "D2H copy");
         XM_CUDA(c, cudaStreamSynchronize(st), "BGZF deflate kernel");
         deflate_plan_hist(hist, *plan);
@@ -523,7 +526,7 @@ static int device_bgzf(xm_ctx *c, const uint8_t *d_src, uint64_t n, DevBuf &Z, u
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaMemcpyAsync(d_plan, plan, sizeof *plan, cudaMemcpyHostToDevice, st);
     cudaEventRecord(e0, st);
-    k_bgzf_deflate<<<(unsigned)((members + DEF_WARPS - 1) / DEF_WARPS), DEF_WARPS * 32, 0, st>>>(d_src, n, (uint32_t)members, d_plan, c->d_zslot.p, d_sizes, nullptr);
+    k_bgzf_deflate<<<(unsigned)((members + DEF_WARPS - 1) / DEF_WARPS), DEF_WARPS * 32, 0, st>>>(d_src, n, (uint32_t)members, in_per, slot_bytes, d_plan, c->d_zslot.p, d_sizes, nullptr);
     k_bgzf_offsets<<<1, 1024, 0, st>>>(d_sizes, (uint32_t)members, d_offs);
     unsigned long long total = 0;
     cudaMemcpyAsync(&total, d_offs + members, 8, cudaMemcpyDeviceToHost, st);
@@ -531,7 +534,7 @@ static int device_bgzf(xm_ctx *c, const uint8_t *d_src, uint64_t n, DevBuf &Z, u
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(c, e, "BGZF deflate kernel"); }
     if ((rc = reserve_dev(c, Z, total + 64))) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
-    k_bgzf_pack<<<(unsigned)((members * 32 + 255) / 256), 256, 0, st>>>(c->d_zslot.p, d_sizes, d_offs, (uint32_t)members, Z.p);
+    k_bgzf_pack<<<(unsigned)((members * 32 + 255) / 256), 256, 0, st>>>(c->d_zslot.p, slot_bytes, d_sizes, d_offs, (uint32_t)members, Z.p);
     cudaEventRecord(e1, st);
     e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();

@@ -35,8 +35,9 @@
 
 namespace xm {
 
-constexpr uint32_t DEF_IN_MAX = 0xff00;            /* input bytes per member, as htslib */
-constexpr uint32_t DEF_SLOT = 0x10000 + 256;       /* bytes of scratch per member */
+constexpr uint32_t DEF_IN_MAX = 0xff00;            /* most input bytes per member, as htslib */
+constexpr uint32_t DEF_IN_MIN = 0x4000;            /* fewest: small bins are cut finer so that every SM has members to work on */
+constexpr uint32_t DEF_SLOT = 0x10000 + 256;       /* bytes of scratch per member of DEF_IN_MAX bytes */
 constexpr uint32_t DEF_MEMBER_MAX = 0x10000;       /* BSIZE is 16 bits */
 constexpr int DEF_HASH_BITS = 12;
 constexpr int DEF_MIN_MATCH = 4, DEF_MAX_MATCH = 258;
@@ -179,10 +180,22 @@ __device__ __forceinline__ uint32_t def_load4(const uint32_t *W, uint32_t off)
     return __funnelshift_r(w0, w1, (off & 3u) * 8u);
 }
 
-/* src: 4-byte aligned, readable 8 bytes past its end.  member m covers [m * DEF_IN_MAX, ...); its gzip member is built in
- * slot + m * DEF_SLOT and its size goes to sizes[m]. */
+/* input bytes per member for a bin of n bytes: DEF_IN_MAX when that still gives every SM several members (a member is one
+ * warp's work and takes milliseconds whatever else runs), finer otherwise; a multiple of 256 */
+inline uint32_t deflate_member_bytes(uint64_t n, uint32_t sm_count)
+{
+    const uint64_t want = (uint64_t)sm_count * 40;                /* two waves of 20 warps per SM */
+    uint64_t per = (n + want - 1) / want;
+    per = (per + 255) & ~255ull;
+    return (uint32_t)std::min<uint64_t>(DEF_IN_MAX, std::max<uint64_t>(DEF_IN_MIN, per));
+}
+inline uint32_t deflate_slot_bytes(uint32_t in_per) { return in_per + 256 + 256; }
+
+/* src: 4-byte aligned, readable 8 bytes past its end.  member m covers [m * in_per, ...); its gzip member is built in
+ * slot + m * slot_bytes and its size goes to sizes[m]. */
 __global__ void __launch_bounds__(DEF_WARPS * 32, XM_DEF_OCC)
-k_bgzf_deflate(const uint8_t *src, uint64_t n_total, uint32_t n_members, const DeflatePlan *plan, uint8_t *slot, uint32_t *sizes, uint32_t *hist)
+k_bgzf_deflate(const uint8_t *src, uint64_t n_total, uint32_t n_members, uint32_t in_per, uint32_t slot_bytes, const DeflatePlan *plan, uint8_t *slot,
+               uint32_t *sizes, uint32_t *hist)
 {
     __shared__ DeflateSmem S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -193,11 +206,11 @@ k_bgzf_deflate(const uint8_t *src, uint64_t n_total, uint32_t n_members, const D
     __syncthreads();
     const uint32_t m = blockIdx.x * DEF_WARPS + (uint32_t)warp;
     if (m >= n_members) { if (hist) __syncthreads(); return; }
-    const uint64_t lo64 = (uint64_t)m * DEF_IN_MAX;
-    const uint32_t n = (uint32_t)((n_total - lo64) < DEF_IN_MAX ? (n_total - lo64) : DEF_IN_MAX);
+    const uint64_t lo64 = (uint64_t)m * in_per;
+    const uint32_t n = (uint32_t)((n_total - lo64) < in_per ? (n_total - lo64) : in_per);
     const uint8_t *in = src + lo64;
-    const uint32_t *W = (const uint32_t *)in;                      /* DEF_IN_MAX is a multiple of 4 */
-    uint8_t *out = slot + (uint64_t)m * DEF_SLOT;
+    const uint32_t *W = (const uint32_t *)in;                      /* in_per is a multiple of 4 */
+    uint8_t *out = slot + (uint64_t)m * slot_bytes;
     uint32_t *OW = (uint32_t *)out;
     uint16_t *htab = S.htab[warp];
     uint32_t *stage = S.stage[warp];
@@ -212,7 +225,8 @@ k_bgzf_deflate(const uint8_t *src, uint64_t n_total, uint32_t n_members, const D
     __syncwarp();
     if (lane == 0) stage[0] = plan->hdr_words[hdr_bits >> 5];
     __syncwarp();
-    const uint32_t word_limit = (DEF_MEMBER_MAX - 8 - 160) / 4;     /* room for a step (32 tokens of at most 48 bits), EOB, the trailer */
+    const uint32_t room = slot_bytes < DEF_MEMBER_MAX ? slot_bytes : DEF_MEMBER_MAX;
+    const uint32_t word_limit = (room - 8 - 160) / 4;               /* room for a step (32 tokens), EOB, the trailer */
     bool overflow = false;
     uint32_t cu = 0;                                                /* first position without a token */
 
@@ -384,12 +398,12 @@ __global__ void k_bgzf_offsets(const uint32_t *sizes, uint32_t n, unsigned long 
 }
 
 /* member m from its slot to dst + offs[m]: one warp per member */
-__global__ void k_bgzf_pack(const uint8_t *slot, const uint32_t *sizes, const unsigned long long *offs, uint32_t n_members, uint8_t *dst)
+__global__ void k_bgzf_pack(const uint8_t *slot, uint32_t slot_bytes, const uint32_t *sizes, const unsigned long long *offs, uint32_t n_members, uint8_t *dst)
 {
     const uint32_t m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (m >= n_members) return;
-    const uint8_t *s = slot + (uint64_t)m * DEF_SLOT;
+    const uint8_t *s = slot + (uint64_t)m * slot_bytes;
     uint8_t *d = dst + offs[m];
     const uint32_t n = sizes[m];
     /* destination-aligned 16-byte stores; the source words come by byte (L2-resident, written a moment ago) */

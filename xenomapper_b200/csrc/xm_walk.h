@@ -463,6 +463,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
             if (be.read(&G, sc.g, sizeof G)) { errmsg = "result read failed"; return res->status = XM_ERR_CUDA; }
         }
         res->ms_scan = be.elapsed(3, 1); res->ms_classify = be.elapsed(1, 2); res->ms_total += be.elapsed(0, 2);
+        res->ms_kernel[0] = res->ms_scan; res->ms_kernel[1] = res->ms_classify;       /* the scan / classify pair */
 
 #ifdef XM_PHASE_TIMING
         {
