@@ -174,8 +174,11 @@ __global__ void __launch_bounds__(EM_WARPS * 32) k_size(const EmitArgs a)
 {
     __shared__ unsigned long long s_tot[EM_WARPS][8];
     __shared__ __align__(16) uint8_t s_qn[EM_WARPS * 32][QN_SLOT];
+    __shared__ uint32_t s_cnt[36];              /* the CTA's part of the histogram: one global atomic per category and CTA */
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t w0 = ((uint64_t)blockIdx.x * EM_WARPS + (uint64_t)warp) * EM_PER_WARP;
+    if (threadIdx.x < 36) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     bool bad = false;
     RowCarry carry{UA, 0, 0, 0, 0, false};
     unsigned long long tot = 0;                 /* lane b < 6: this warp's bytes for bin b */
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(EM_WARPS * 32) k_size(const EmitArgs a)
         const RowDec d = rows_decide<true>(a, i, valid, kb == 0, carry, bad, s_qn[threadIdx.x]);
         {
             const unsigned peers = __match_any_sync(0xffffffffu, d.key);
-            if (d.key < 36u && lane == __ffs((int)peers) - 1) atomicAdd(&a.g->counts[d.key], (unsigned long long)__popc(peers));
+            if (d.key < 36u && lane == __ffs((int)peers) - 1) atomicAdd(&s_cnt[d.key], (uint32_t)__popc(peers));
         }
         const uint32_t bytes = d.plen + d.slen;
 #pragma unroll
@@ -207,6 +210,10 @@ __global__ void __launch_bounds__(EM_WARPS * 32) k_size(const EmitArgs a)
 #pragma unroll
         for (int w = 0; w < EM_WARPS; ++w) t += s_tot[w][threadIdx.x];
         a.tile_tot[(size_t)blockIdx.x * C2_SLOTS + threadIdx.x] = t;
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 68) {
+        const uint32_t v = s_cnt[threadIdx.x - 32];
+        if (v) atomicAdd(&a.g->counts[threadIdx.x - 32], (unsigned long long)v);
     }
 }
 
