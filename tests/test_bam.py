@@ -274,3 +274,45 @@ def test_bam_walk_with_small_windows_equals_the_big_one(ctx, monkeypatch):
     rc3, res3, outs3 = ctx.classify_bam_host(bam_p, bam_s, opts)
     assert rc3 == 0, ctx.error()
     assert outs3 == outs and list(res3.counts) == list(res.counts)
+
+
+@pytest.mark.gpu
+def test_device_inflate_edge_shapes(ctx, monkeypatch):
+    """no records at all; empty BGZF members between the data; no end-of-file member; a record cut off by the end of the file"""
+    from xenomapper_b200 import _lib, synth
+    empty = _bamwriter.sam_to_bam(FULL_HEADER, b"")
+    assert ctx.bam_render_host(empty) == b""
+    p, _ = synth.generate(3000, seed=5, style=0)
+    text = bytes(p)
+    bam = _bamwriter.sam_to_bam(FULL_HEADER, text, block=5000)
+    eof = bam[-28:]
+    assert eof == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    # split the members, put empty ones in between
+    ms, at = [], 0
+    while at < len(bam):
+        bs = int.from_bytes(bam[at + 16:at + 18], "little") + 1
+        ms.append(bam[at:at + bs]); at += bs
+    holes = b"".join(m + (eof if k % 7 == 3 else b"") for k, m in enumerate(ms[:-1]))
+    for window in ("20000", str(1 << 30)):
+        monkeypatch.setenv("XM_BAM_WINDOW", window)
+        assert ctx.bam_render_host(holes + eof) == text
+        assert ctx.bam_render_host(holes) == text                       # samtools warns about the missing EOF marker and goes on
+        with pytest.raises(_lib.XenomapperLibraryError, match="truncated"):
+            ctx.bam_render_host(b"".join(ms[:-3]) + eof)                # the last record is cut by the missing members
+
+
+@pytest.mark.gpu
+def test_bam_walk_survives_an_error_and_goes_on(ctx):
+    """a failed call leaves the context usable and the next BAM walk correct"""
+    from xenomapper_b200 import _lib, synth
+    p, s = synth.generate(4000, seed=6, style=0)
+    hdr2 = FULL_HEADER.replace("SN:chr", "SN:").replace("SN:M\t", "SN:MT\t")
+    bam_p, bam_s = _bamwriter.sam_to_bam(FULL_HEADER, bytes(p)), _bamwriter.sam_to_bam(hdr2, bytes(s))
+    opts = _lib.Context.opts(_lib.MODE_SE, _lib.SCORE_AS_XS, True, float("-inf"))
+    bad = bytearray(bam_s)
+    bad[len(bad) // 2] ^= 0x40
+    with pytest.raises(_lib.XenomapperLibraryError):
+        ctx.classify_bam_host(bam_p, bytes(bad), opts)
+    rc, res, outs = ctx.classify_bam_host(bam_p, bam_s, opts)
+    rc2, res2, outs2 = ctx.classify_host(p, s, opts)
+    assert rc == 0 and outs == outs2 and list(res.counts) == list(res2.counts)
