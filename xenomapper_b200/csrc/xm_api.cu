@@ -111,6 +111,15 @@ struct DevBuf {
     uint8_t *p = nullptr;
     uint64_t cap = 0;
 };
+/* two timing events that go away with the scope, whichever way it is left */
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EventPair() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    EventPair(const EventPair &) = delete;
+    EventPair &operator=(const EventPair &) = delete;
+    float ms() const { float v = 0.f; cudaEventElapsedTime(&v, a, b); return v; }
+};
 struct HostBuf {
     uint8_t *p = nullptr;
     uint64_t cap = 0, len = 0;
@@ -522,27 +531,23 @@ static int device_bgzf(xm_ctx *c, const uint8_t *d_src, uint64_t n, DevBuf &Z, u
         c->bgzf_stats.n_launches += 1;
         *have_plan = true;
     }
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    EventPair ev;
     cudaMemcpyAsync(d_plan, plan, sizeof *plan, cudaMemcpyHostToDevice, st);
-    cudaEventRecord(e0, st);
+    cudaEventRecord(ev.a, st);
     k_bgzf_deflate<<<(unsigned)((members + DEF_WARPS - 1) / DEF_WARPS), DEF_WARPS * 32, 0, st>>>(d_src, n, (uint32_t)members, in_per, slot_bytes, d_plan, c->d_zslot.p, d_sizes, nullptr);
     k_bgzf_offsets<<<1, 1024, 0, st>>>(d_sizes, (uint32_t)members, d_offs);
     unsigned long long total = 0;
     cudaMemcpyAsync(&total, d_offs + members, 8, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(c, e, "BGZF deflate kernel"); }
-    if ((rc = reserve_dev(c, Z, total + 64))) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    if (e != cudaSuccess) return cuda_fail(c, e, "BGZF deflate kernel");
+    if ((rc = reserve_dev(c, Z, total + 64))) return rc;
     k_bgzf_pack<<<(unsigned)((members * 32 + 255) / 256), 256, 0, st>>>(c->d_zslot.p, slot_bytes, d_sizes, d_offs, (uint32_t)members, Z.p);
-    cudaEventRecord(e1, st);
+    cudaEventRecord(ev.b, st);
     e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
-    float ms = 0.f;
-    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (e != cudaSuccess) return cuda_fail(c, e, "BGZF pack kernel");
-    c->bgzf_stats.in_bytes += n; c->bgzf_stats.out_bytes += total; c->bgzf_stats.members += members; c->bgzf_stats.kernel_ms += ms;
+    c->bgzf_stats.in_bytes += n; c->bgzf_stats.out_bytes += total; c->bgzf_stats.members += members; c->bgzf_stats.kernel_ms += ev.ms();
     c->bgzf_stats.n_launches += 3;
     *z_len = total;
     return XM_OK;
@@ -1166,8 +1171,7 @@ struct BamProducer : DevSource {
             if (left) { cudaMemcpyAsync(D.p, tmp, left, cudaMemcpyDeviceToDevice, st); cudaStreamSynchronize(st); cudaFree(tmp); }
         }
         const size_t nblk = last - blk;
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        EventPair ev;
         unsigned long long *d_status = nullptr;
         if (nblk) {
             const uint64_t c0 = blocks[blk].in_off, c1 = blocks[last - 1].in_off + blocks[last - 1].in_len;
@@ -1189,20 +1193,17 @@ struct BamProducer : DevSource {
             d_status = (unsigned long long *)(c->d_bam_tab[s].p + nblk * sizeof(BgzfDev));
             const unsigned long long none = ~0ull;
             cudaMemcpyAsync(d_status, &none, 8, cudaMemcpyHostToDevice, st);
-            cudaEventRecord(e0, st);
+            cudaEventRecord(ev.a, st);
             k_bgzf_inflate<<<(unsigned)((nblk + INF_WARPS - 1) / INF_WARPS), INF_WARPS * 32, 0, st>>>(c->d_bam_comp[s].p, (const BgzfDev *)c->d_bam_tab[s].p,
                                                                                                    (uint32_t)nblk, D.p, d_status, 1);
-            cudaEventRecord(e1, st);
+            cudaEventRecord(ev.b, st);
             unsigned long long status = 0;
             cudaMemcpyAsync(&status, d_status, 8, cudaMemcpyDeviceToHost, st);
             if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "the BGZF inflate kernel failed"; return XM_ERR_CUDA; }
             if (status != ~0ull) { err = "BAM input: BGZF block does not inflate (corrupt data or CRC mismatch)"; return XM_ERR_IO; }
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, e0, e1);
-            c->bam_stats.inflate_ms += ms;
+            c->bam_stats.inflate_ms += ev.ms();
             c->bam_stats.n_launches += 1;
         }
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
         have_d = left + add;
         blk = last;
         c->bam_stats.inflated_bytes += add;
@@ -1254,20 +1255,15 @@ struct BamProducer : DevSource {
                 cudaMemcpyAsync(d_err, &no_err, 8, cudaMemcpyHostToDevice, st);
                 BamDev B = dev_view(0, n_rec);
                 uint32_t *d_len = (uint32_t *)c->d_bam_len[s].p, *d_loff = d_len + n_rec + (n_rec & 1);
-                cudaEvent_t r0, r1;
-                cudaEventCreate(&r0); cudaEventCreate(&r1);
-                cudaEventRecord(r0, st);
+                EventPair rv;
+                cudaEventRecord(rv.a, st);
                 k_bam_len<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(B, d_len, d_err);
                 k_bam_scan_blocks<<<(unsigned)nb, 1024, 0, st>>>(d_len, n_rec, d_loff, (unsigned long long *)c->d_bam_sum[s].p);
-                cudaEventRecord(r1, st);
+                cudaEventRecord(rv.b, st);
                 sums.assign(nb + 1, 0);
                 cudaMemcpyAsync(sums.data(), c->d_bam_sum[s].p, (nb + 1) * 8, cudaMemcpyDeviceToHost, st);
-                const bool ok = cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
-                float ms = 0.f;
-                if (ok) cudaEventElapsedTime(&ms, r0, r1);
-                cudaEventDestroy(r0); cudaEventDestroy(r1);
-                if (!ok) { err = "BAM length kernels failed"; return XM_ERR_CUDA; }
-                c->bam_stats.render_ms += ms;
+                if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "BAM length kernels failed"; return XM_ERR_CUDA; }
+                c->bam_stats.render_ms += rv.ms();
                 c->bam_stats.n_launches += 3;
                 if (sums[nb] != BAM_NO_ERROR) {
                     if ((sums[nb] & 0xff) == BAM_E_FLOAT) { err = "a BAM record has a float aux value (f or B:f): not rendered on the device"; return XM_ERR_UNSUPPORTED; }
@@ -1337,17 +1333,12 @@ struct BamProducer : DevSource {
         unsigned long long run = 0ull - cut_off;                       /* wraps: the first group's base lies before dev_dst */
         for (uint64_t k = 0; k < ng; ++k) { bases[k] = run; run += sums[g0 + k]; }
         cudaMemcpyAsync(c->d_bam_sum[s].p, bases.data(), bases.size() * 8, cudaMemcpyHostToDevice, st);
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        cudaEventRecord(e0, st);
+        EventPair ev;
+        cudaEventRecord(ev.a, st);
         k_bam_render<<<(unsigned)((cnt * 32 + 255) / 256), 256, 0, st>>>(dev_view(0, n_rec), r_next, cnt, d_loff, (const unsigned long long *)c->d_bam_sum[s].p, dev_dst);
-        cudaEventRecord(e1, st);
-        const bool ok = cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
-        float ms = 0.f;
-        if (ok) cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        if (!ok) { err = "BAM render kernel failed"; return XM_ERR_CUDA; }
-        c->bam_stats.render_ms += ms;
+        cudaEventRecord(ev.b, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "BAM render kernel failed"; return XM_ERR_CUDA; }
+        c->bam_stats.render_ms += ev.ms();
         c->bam_stats.text_bytes += bytes;
         c->bam_stats.n_launches += 1;
         cut_off = cut_end;
