@@ -273,6 +273,11 @@ int xm_classify_sharded_host(xm_ctx *ctx, const void *prim, uint64_t prim_len, c
  * Float aux values (types f, B:f) are refused with XM_ERR_UNSUPPORTED. */
 int xm_classify_bam_host(xm_ctx *ctx, const void *prim_bam, uint64_t prim_len,
                          const void *sec_bam, uint64_t sec_len, const xm_opts *opts, xm_result *res);
+/* The same with the bins appended to six descriptors as the walk goes (-1: bin disabled), plain or as BGZF members
+ * (XM_OUT_BGZF) -- BAM in, BGZF out, inflate and deflate both on the device.  The BAM files may be mapped files:
+ * they are read once, front to back. */
+int xm_classify_bam_fds(xm_ctx *ctx, const void *prim_bam, uint64_t prim_len, const void *sec_bam, uint64_t sec_len,
+                        const int out_fds[6], const xm_opts *opts, uint32_t out_flags, xm_result *res);
 /* The header text stored in a BAM file (l_text bytes; what `samtools view -H`
  * of xm.py:49 printed before samtools 1.10 began to append its own @PG line).
  * *needed receives its length; it is copied to dst when cap suffices.

@@ -198,3 +198,35 @@ def test_cli_reads_pipes(tmp_path, name, flags, chunk):
     e = case["expect"]
     assert [G.sha(o.read_bytes()) for o in outs] == e["full_sha256"]
     assert G.sha(r.stderr) == e["summary_sha256"]
+
+
+@pytest.mark.parametrize("bgzf", [False, True], ids=["sam_out", "bgzf_out"])
+@pytest.mark.parametrize("chunk", [None, "3000"])
+def test_cli_bam_inputs_to_files(tmp_path, bgzf, chunk):
+    """--primary_bam / --secondary_bam (xm.py:703-713) with real output files: the BAM files are mapped, inflated and
+    rendered on the GPU and the bins go to the descriptors (xm_classify_bam_fds) -- with --bgzf deflated on the GPU too.
+    The six files are the reference CLI's on the SAM twins, headers included."""
+    import gzip
+    import os
+    import subprocess
+    import sys
+    name = "fixture_pe_mode1_src0_skip0_min-inf"
+    if name not in G.BY_NAME:
+        pytest.skip("no such golden")
+    case = G.BY_NAME[name]
+    p, s = tmp_path / "h.bam", tmp_path / "m.bam"
+    p.write_bytes(G.fixture_bytes("pe", "primary", "bam")); s.write_bytes(G.fixture_bytes("pe", "secondary", "bam"))
+    outs = [tmp_path / (b + (".sam.gz" if bgzf else ".sam")) for b in G.BINS]
+    cmd = [sys.executable, "-m", "xenomapper_b200.xenomapper", "--primary_bam", str(p), "--secondary_bam", str(s), "--paired"] + (["--bgzf"] if bgzf else [])
+    for b, o in zip(G.BINS, outs):
+        cmd += ["--" + b, str(o)]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **({"XM_CHUNK_BYTES": chunk, "XM_BAM_WINDOW": "70000"} if chunk else {}))
+    r = subprocess.run(cmd, cwd=root, capture_output=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr.decode()
+    e = case["expect"]
+    raw = [o.read_bytes() for o in outs]
+    if bgzf:
+        raw = [gzip.decompress(x) for x in raw]
+    assert [G.sha(x) for x in raw] == e["full_sha256"]
+    assert G.sha(r.stderr) == e["summary_sha256"]

@@ -26,7 +26,7 @@ EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_cla
            "xm_comm_unique_id", "xm_comm_init_rank", "xm_comm_destroy", "xm_comm_barrier", "xm_comm_allreduce_f64",
            "xm_classify_sharded_device", "xm_classify_sharded_host", "xm_copy_ceiling",
            "xm_process_headers_fds", "xm_process_headers_mem", "xm_classify_fds_ex", "xm_bgzf_write", "xm_classify_streams",
-           "xm_bgzf_deflate_host", "xm_bgzf_get_stats")
+           "xm_bgzf_deflate_host", "xm_bgzf_get_stats", "xm_classify_bam_fds")
 OUT_BGZF = 1
 
 
@@ -343,6 +343,17 @@ class Context:
                 outs.append(C.string_at(p.value, n.value) if n.value else b"")
         del pk, sk
         return rc, res, outs
+
+    def classify_bam_fds(self, prim_bam, sec_bam, out_fds, opts, out_flags=0):
+        """BAM files (bytes-like, or numpy arrays over mapped files) in, the six bins appended to descriptors"""
+        pa, pn, pk = _host_ptr(prim_bam)
+        sa, sn, sk = _host_ptr(sec_bam)
+        res = Result()
+        fds = (C.c_int * 6)(*out_fds)
+        rc = self.lib.xm_classify_bam_fds(self.h, pa, pn, sa, sn, fds, C.byref(opts), out_flags, C.byref(res))
+        self._check(rc, "xm_classify_bam_fds")
+        del pk, sk
+        return rc, res
 
     def bam_render_host(self, bam):
         """all records of a BAM file as SAM text (what `samtools view` prints), rendered on the device"""

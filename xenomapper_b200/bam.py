@@ -1,12 +1,26 @@
 """BAM input for the walks: the replacement of the reference's `samtools view` pipes (xm.py:48-93).
 
-Nothing is decoded in Python: the BGZF blocks are inflated by the library on host threads, the alignment
-records are rendered as SAM text by CUDA kernels (csrc/xm_bam.h).
+Nothing is decoded in Python: the BGZF blocks are inflated, the record chain is followed and the alignment records are
+rendered as SAM text by CUDA kernels (csrc/xm_inflate.h, xm_bamchain.h, xm_bam.h).
 """
+import mmap
+import os
+import stat
+
 from . import _lib
 
 
 def _all_bytes(bamfile):
+    """the file's bytes: a read-only mapping for a regular file (the library reads it once, front to back; nothing is
+    copied into Python), else what read() returns"""
+    try:
+        fd = bamfile.fileno()
+        st = os.fstat(fd)
+        if stat.S_ISREG(st.st_mode) and st.st_size > 0 and "b" in getattr(bamfile, "mode", "b"):
+            import numpy as np
+            return np.frombuffer(mmap.mmap(fd, 0, access=mmap.ACCESS_READ), dtype=np.uint8)
+    except (AttributeError, OSError, ValueError):
+        pass
     bamfile.seek(0)
     data = bamfile.read()
     if isinstance(data, str):

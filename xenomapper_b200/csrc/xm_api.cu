@@ -1409,10 +1409,9 @@ static int bam_to_device_text(xm_ctx *c, const void *bam, uint64_t len, int s, u
     return XM_OK;
 }
 
-int xm_classify_bam_host(xm_ctx *c, const void *prim_bam, uint64_t prim_len, const void *sec_bam, uint64_t sec_len,
-                         const xm_opts *opts, xm_result *res)
+static int classify_bam(xm_ctx *c, const void *prim_bam, uint64_t prim_len, const void *sec_bam, uint64_t sec_len,
+                        const int *out_fds, const xm_opts *opts, uint32_t out_flags, xm_result *res)
 {
-    if (!c || !opts || !res || !prim_bam || !sec_bam) return XM_ERR_ARG;
     cudaSetDevice(c->device);
     memset(res, 0, sizeof *res);
     BamProducer prod[2];
@@ -1430,9 +1429,23 @@ int xm_classify_bam_host(xm_ctx *c, const void *prim_bam, uint64_t prim_len, con
     }
     const uint64_t step = std::max<uint64_t>(std::min<uint64_t>(chunk_bytes(), std::max(in[0].len, in[1].len) + 64), 64);     /* stream_walk's chunk */
     prod[0].full_cap = prod[1].full_cap = step;
-    const int rc = stream_walk(c, in, nullptr, opts, res);
+    const int rc = stream_walk(c, in, out_fds, opts, res, out_flags);
     res->n_launches += c->bam_stats.n_launches - launches0;
     return rc;
+}
+
+int xm_classify_bam_host(xm_ctx *c, const void *prim_bam, uint64_t prim_len, const void *sec_bam, uint64_t sec_len,
+                         const xm_opts *opts, xm_result *res)
+{
+    if (!c || !opts || !res || !prim_bam || !sec_bam) return XM_ERR_ARG;
+    return classify_bam(c, prim_bam, prim_len, sec_bam, sec_len, nullptr, opts, 0, res);
+}
+
+int xm_classify_bam_fds(xm_ctx *c, const void *prim_bam, uint64_t prim_len, const void *sec_bam, uint64_t sec_len,
+                        const int out_fds[6], const xm_opts *opts, uint32_t out_flags, xm_result *res)
+{
+    if (!c || !opts || !res || !prim_bam || !sec_bam || !out_fds) return XM_ERR_ARG;
+    return classify_bam(c, prim_bam, prim_len, sec_bam, sec_len, out_fds, opts, out_flags, res);
 }
 
 int xm_get_walk_kernels(xm_ctx *c, uint32_t *mask)

@@ -344,7 +344,17 @@ def _walk(mode, readpairs, outputs, min_score, tag_func):
             _raise_for(rc, ctx, res)
         return _counter(res, mode != _lib.MODE_SE)
     if bam_inputs:
-        rc, res, outs = ctx.classify_bam_host(bam_inputs[0], bam_inputs[1], opts)      # inflate on the host, decode + walk on the GPU
+        out_fds = _output_descriptors(outputs)
+        if out_fds:
+            # BAM in, descriptors out: inflate, record chain, rendering, the walk (and the deflate of --bgzf) on the GPU
+            rc, res = ctx.classify_bam_fds(bam_inputs[0], bam_inputs[1], out_fds, opts,
+                                           _lib.OUT_BGZF if getattr(readpairs, "bgzf", False) else 0)
+            if rc != _lib.XM_OK:
+                _raise_for(rc, ctx, res)
+            return _counter(res, mode != _lib.MODE_SE)
+        if getattr(readpairs, "bgzf", False):
+            raise NotImplementedError("BGZF output needs outputs with descriptors")
+        rc, res, outs = ctx.classify_bam_host(bam_inputs[0], bam_inputs[1], opts)
     else:
         rc, res, outs = ctx.classify_host(prim, sec, opts)
     # everything before a failing record is written, like the reference's streaming prints
@@ -379,6 +389,14 @@ def _descriptors(readpairs, outputs):
         if getattr(f, "newlines", None) not in (None, "\n"):
             return None                      # universal newlines already translated something: let the text layer decide
         ins.append((fd, pos))
+    out_fds = _output_descriptors(outputs)
+    if out_fds is None:
+        return None
+    return ins[0], ins[1], out_fds
+
+
+def _output_descriptors(outputs):
+    """the six outputs' descriptors (-1: disabled), flushed; None when one of them has none"""
     out_fds = []
     for out in outputs:
         if not out:
@@ -389,7 +407,7 @@ def _descriptors(readpairs, outputs):
             out_fds.append(out.fileno())
         except (AttributeError, OSError, ValueError):
             return None
-    return ins[0], ins[1], out_fds
+    return out_fds
 
 
 def main_single_end(readpairs, primary_specific=sys.stdout, secondary_specific=None, primary_multi=None,
@@ -529,18 +547,23 @@ def _main_bgzf(args, tag_func, outs, skip):
     """--bgzf: headers and bins leave as BGZF members (xm_bgzf_write, xm_classify_fds_ex with XM_OUT_BGZF).
     gunzip of every output equals what the command writes without the flag."""
     import io
-    if not args.primary_sam:
-        raise NotImplementedError("--bgzf takes SAM inputs")
+    bam = not args.primary_sam
     files = {k: f for k, f in outs.items() if f}
     for k, f in files.items():
         if _regular_fd(f) is None and not hasattr(f, "fileno"):
             raise ValueError("--bgzf writes through descriptors: {0} has none".format(k))
     texts = {k: io.StringIO() for k in files}
-    process_headers(args.primary_sam, args.secondary_sam, **{k: texts.get(k) for k in outs})
+    if bam:
+        process_headers(args.primary_bam, args.secondary_bam, bam=True, **{k: texts.get(k) for k in outs})
+    else:
+        process_headers(args.primary_sam, args.secondary_sam, **{k: texts.get(k) for k in outs})
     for k, f in files.items():
         f.flush()
         _lib.bgzf_write(f.fileno(), texts[k].getvalue().encode())
-    pairs = getReadPairs(args.primary_sam, args.secondary_sam, skip_repeated_reads=skip)
+    if bam:
+        pairs = getBamReadPairs(args.primary_bam, args.secondary_bam, skip_repeated_reads=skip)
+    else:
+        pairs = getReadPairs(args.primary_sam, args.secondary_sam, skip_repeated_reads=skip)
     pairs.bgzf = True
     walk = main_single_end if not args.paired else (conservative_main_paired_end if args.conservative else main_paired_end)
     try:
