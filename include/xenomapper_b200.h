@@ -278,6 +278,22 @@ int xm_classify_bam_host(xm_ctx *ctx, const void *prim_bam, uint64_t prim_len,
  * they are read once, front to back. */
 int xm_classify_bam_fds(xm_ctx *ctx, const void *prim_bam, uint64_t prim_len, const void *sec_bam, uint64_t sec_len,
                         const int out_fds[6], const xm_opts *opts, uint32_t out_flags, xm_result *res);
+
+/* BAM input for the walk across GPUs (xm_classify_sharded_device).  Every rank maps the whole file; rank r of `world`
+ * takes the BGZF blocks that start in its 1/world of the file's bytes and the records that start inside them, inflates
+ * them (and as much of what follows as its last record reaches into) and finds its records with the parallel chain:
+ *   xm_bam_shard_open   *guess = the offset in the INFLATED stream at which it believes its first record starts (rank 0
+ *                       knows), *exit_off = the first record start behind its part -- the next rank's true entry.
+ *                       UINT64_MAX in both: the part holds no record start of its own (header only): it passes on the
+ *                       entry it is given.
+ *   xm_bam_shard_chain  the caller has compared the ranks' numbers (one small all-gather): a rank whose guess was not the
+ *                       exit of the rank before it follows its part again from the true entry; *exit_off as above.
+ *   xm_bam_shard_text   the part's records as SAM text in device memory, front_room writable bytes before and back_room
+ *                       after it: *d_text goes to xm_classify_sharded_device as this rank's byte shard of that stream.
+ * stream: 0 primary, 1 secondary.  The buffers stay with the context until the next xm_bam_shard_open on the stream. */
+int xm_bam_shard_open(xm_ctx *ctx, int stream, const void *bam, uint64_t len, int rank, int world, uint64_t *guess, uint64_t *exit_off);
+int xm_bam_shard_chain(xm_ctx *ctx, int stream, uint64_t entry, uint64_t *exit_off);
+int xm_bam_shard_text(xm_ctx *ctx, int stream, uint64_t front_room, uint64_t back_room, void **d_text, uint64_t *text_len);
 /* The header text stored in a BAM file (l_text bytes; what `samtools view -H`
  * of xm.py:49 printed before samtools 1.10 began to append its own @PG line).
  * *needed receives its length; it is copied to dst when cap suffices.

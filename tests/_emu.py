@@ -73,7 +73,7 @@ def lib():
         _lib.xm_emu_crc32.argtypes = [C.c_void_p, C.c_uint32]
         _lib.xm_emu_crc32.restype = C.c_uint32
         _lib.xm_emu_bam_chain.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.c_uint64,
-                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(C.c_uint64)]
         _lib.xm_emu_bam_chain.restype = C.c_int64
         _lib.xm_emu_deflate_literals.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                                  C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
@@ -161,17 +161,21 @@ def crc32(data):
     return int(lib().xm_emu_crc32(buf, len(data)))
 
 
-def bam_chain(inflated, first, n_ref, seg_bytes=16384):
-    """record offsets of an inflated BAM stream by the segment-parallel chain: (offsets, end, repaired segments); None: corrupt"""
+def bam_chain(inflated, first, n_ref, seg_bytes=16384, stop=0, want_guess=False):
+    """record offsets of an inflated BAM stream by the segment-parallel chain: (offsets, end, repaired segments); None: corrupt.
+    first=None: no record start is known (a part of a file): the chain starts at the first guess.  stop: only records that
+    start before that byte."""
     data = bytes(inflated)
     buf = C.create_string_buffer(data, len(data) + 64)
     cap = len(data) // 36 + 16
     rec = (C.c_uint64 * cap)()
-    end, rep = C.c_uint64(), C.c_uint32()
-    n = lib().xm_emu_bam_chain(buf, len(data), seg_bytes, first, n_ref, rec, cap, C.byref(end), C.byref(rep))
+    end, rep, guess = C.c_uint64(), C.c_uint32(), C.c_uint64()
+    n = lib().xm_emu_bam_chain(buf, len(data), seg_bytes, (1 << 64) - 1 if first is None else first, n_ref, rec, cap, C.byref(end), C.byref(rep),
+                               stop, C.byref(guess))
     if n < 0:
         return None
-    return list(rec[:n]), int(end.value), int(rep.value)
+    out = (list(rec[:n]), int(end.value), int(rep.value))
+    return out + (int(guess.value),) if want_guess else out
 
 
 def deflate_literals(sample, data, hist=None):

@@ -343,7 +343,7 @@ extern "C" uint32_t xm_emu_crc32(const void *p, uint32_t n) { return xm::crc32_b
 
 /* the parallel chain, one emulated thread per segment; returns the number of records (-1: corrupt, -2: rec[] too small) */
 extern "C" int64_t xm_emu_bam_chain(const void *data, uint64_t have, uint64_t seg_bytes, uint64_t first, uint32_t n_ref, uint64_t *rec,
-                                    uint64_t cap, uint64_t *end, uint32_t *repaired)
+                                    uint64_t cap, uint64_t *end, uint32_t *repaired, uint64_t stop, uint64_t *guess)
 {
     using namespace xm;
     const uint8_t *d = (const uint8_t *)data;
@@ -352,18 +352,24 @@ extern "C" int64_t xm_emu_bam_chain(const void *data, uint64_t have, uint64_t se
     std::vector<uint64_t> base(n_seg + 1);
     for (uint32_t k = 0; k < n_seg; ++k) {
         const uint64_t lo = (uint64_t)k * seg_bytes, hi = std::min(lo + seg_bytes, have);
-        if (lo + seg_bytes <= first) { seg[k] = ChainSeg{CHAIN_NONE, CHAIN_NONE, 0, 0}; continue; }
-        seg[k] = chain_segment(d, have, lo, hi, k == first / seg_bytes ? first : CHAIN_NONE, n_ref);
+        if (first != CHAIN_NONE && lo + seg_bytes <= first) { seg[k] = ChainSeg{CHAIN_NONE, CHAIN_NONE, 0, 0}; continue; }
+        seg[k] = chain_segment(d, have, lo, hi, (first != CHAIN_NONE && k == first / seg_bytes) ? first : CHAIN_NONE, n_ref);
     }
     uint64_t n_rec = 0;
-    auto repair = [&](uint32_t k, uint64_t entry) {
-        const uint64_t lo = (uint64_t)k * seg_bytes, hi = std::min(lo + seg_bytes, have);
-        return chain_segment(d, have, lo, hi, entry, n_ref);
+    auto repair = [&](uint32_t k, uint64_t entry, uint64_t hi) {
+        return chain_segment(d, have, (uint64_t)k * seg_bytes, hi, entry, n_ref);
     };
-    if (!chain_confirm(seg.data(), base.data(), n_seg, seg_bytes, first, have, repair, *end, n_rec, *repaired)) return -1;
+    if (stop == 0 || stop > have) stop = have;
+    if (first == CHAIN_NONE) {
+        /* a part of a file: the chain starts at the first guess */
+        for (uint32_t k = 0; k < n_seg && first == CHAIN_NONE; ++k) first = seg[k].entry;
+        if (first == CHAIN_NONE) { *end = have; *repaired = 0; return 0; }
+    }
+    *guess = first;
+    if (!chain_confirm(seg.data(), base.data(), n_seg, seg_bytes, first, have, stop, repair, *end, n_rec, *repaired)) return -1;
     if (n_rec > cap) return -2;
     for (uint32_t k = 0; k < n_seg; ++k) {
-        const uint64_t lo = (uint64_t)k * seg_bytes, hi = std::min(lo + seg_bytes, have);
+        const uint64_t lo = (uint64_t)k * seg_bytes, hi = std::min(std::min(lo + seg_bytes, have), stop);
         if (seg[k].count) chain_emit(d, have, hi, seg[k].entry, seg[k].count, rec + base[k]);
     }
     return (int64_t)n_rec;

@@ -316,3 +316,58 @@ def test_bam_walk_survives_an_error_and_goes_on(ctx):
     rc, res, outs = ctx.classify_bam_host(bam_p, bam_s, opts)
     rc2, res2, outs2 = ctx.classify_host(p, s, opts)
     assert rc == 0 and outs == outs2 and list(res.counts) == list(res2.counts)
+
+
+# ---- BAM input of the walk across GPUs: a rank's part of a file (xm_bam_shard_*) -------------------------------------------
+def _parts_text(ctx, bam, world, stream=0):
+    """every rank's part of `bam` rendered one after the other on this GPU, the chains joined the way sharded.py does"""
+    none = ctx.NONE64
+    cur, texts, repaired = None, [], 0
+    for r in range(world):
+        guess, exit_off = ctx.bam_shard_open(stream, bam, r, world)
+        if cur is not None and guess != cur:
+            exit_off = ctx.bam_shard_chain(stream, cur)
+            repaired += guess != none
+            guess = cur
+        if guess != none:
+            cur = exit_off
+        d, n = ctx.bam_shard_text(stream, 4096, 4096)
+        texts.append(ctx.d2h(d, n))
+    return texts, repaired
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 3, 8, 37])
+@pytest.mark.parametrize("block", [0xff00, 3000])
+def test_bam_parts_concatenate_to_the_whole_text(ctx, world, block):
+    """records straddle the parts' block ranges, one record is longer than a whole part, many parts hold no record start"""
+    text = _long_text(3000)
+    bam = _bamwriter.sam_to_bam(FULL_HEADER, text, block=block, level=1)
+    parts, repaired = _parts_text(ctx, bam, world)
+    assert b"".join(parts) == text
+    assert all(p == b"" or p.endswith(b"\n") for p in parts)
+    if world <= 8 and block == 0xff00:
+        assert sum(1 for p in parts if p) >= min(world, 3)
+
+
+@pytest.mark.gpu
+def test_bam_parts_with_a_header_longer_than_a_part(ctx):
+    header = "@HD\tVN:1.0\n" + "".join("@SQ\tSN:contig_%06d\tLN:%d\n" % (k, 1000 + k) for k in range(9000))
+    text = b"".join(b"r%d\t0\tcontig_%06d\t%d\t30\t4M\t*\t0\t0\tACGT\tIIII\tAS:i:-%d\n" % (k, k % 9000, k + 1, k % 7 + 1) for k in range(3000))
+    bam = _bamwriter.sam_to_bam(header, text)
+    for world in (2, 5, 16):
+        parts, _ = _parts_text(ctx, bam, world)
+        assert b"".join(parts) == text
+
+
+@pytest.mark.gpu
+def test_sharded_bam_walk_on_one_rank_equals_the_sam_walk(ctx):
+    from xenomapper_b200 import _lib, sharded, synth
+    p, s = synth.generate(20000, seed=44, style=1)
+    hdr2 = FULL_HEADER.replace("SN:chr", "SN:").replace("SN:M\t", "SN:MT\t")
+    bam_p, bam_s = _bamwriter.sam_to_bam(FULL_HEADER, bytes(p)), _bamwriter.sam_to_bam(hdr2, bytes(s))
+    sharded.init_comm(ctx, 0, 1)
+    res = sharded.sharded_bam_walk(ctx, 0, 1, None, bam_p, bam_s, mode=_lib.MODE_PE_LIBERAL, score_src=_lib.SCORE_CIGAR_NM, min_score=-40.0)
+    assert res["status"] == 0, res["message"]
+    rc, r2, outs2 = ctx.classify_host(p, s, _lib.Context.opts(_lib.MODE_PE_LIBERAL, _lib.SCORE_CIGAR_NM, False, -40.0))
+    assert res["outputs"] == outs2 and res["counts"] == list(r2.counts)

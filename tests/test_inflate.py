@@ -189,3 +189,27 @@ def test_deflate_plan_fits_the_sample():
     stream, ll, dl = _emu.deflate_literals(data[:8192], data)
     assert max(ll[c] for c in b"ACGT") <= 3
     assert len(stream) < 0.3 * len(data)
+
+
+@pytest.mark.parametrize("seg", [512, 4096])
+def test_parallel_chain_of_a_part_of_the_stream(seg):
+    """a rank's part of a file shared between GPUs: no record start is known, the records that start before `stop` are its own"""
+    raw, first, n_ref = _inflated_bam(1500, long_every=211)
+    want, _ = _serial_chain(raw, first)
+    rnd = random.Random(seg)
+    for _ in range(12):
+        lo = rnd.randrange(first, len(raw) - 20000)
+        hi = lo + rnd.randrange(1000, 150000)
+        part = raw[lo:min(len(raw), hi + 120000)]                        # the part and what follows it (the last record's tail)
+        stop = min(hi, len(raw)) - lo
+        rec, end, _, guess = _emu.bam_chain(part, None, n_ref, seg, stop=stop, want_guess=True)
+        own = [w - lo for w in want if lo <= w < lo + stop]
+        if not own:                                                      # the part lies inside one long record
+            continue
+        if guess == own[0]:                                              # the guess is the true first record: everything follows
+            assert rec == own
+            nxt = [w - lo for w in want if w >= lo + stop]
+            assert end == (nxt[0] if nxt and nxt[0] <= len(part) else end)
+        # given the true entry (what the rank before reports), the part is exact whatever the guess was
+        rec2, end2, _ = _emu.bam_chain(part, own[0], n_ref, seg, stop=stop)
+        assert rec2 == own

@@ -268,3 +268,40 @@ def test_sharded_cli_over_nccl_on_two_gpus(tmp_path):
         body = data[data.index(b"\n@CO") + 1:]
         body = body[body.index(b"\n") + 1:]
         assert body == ref["outputs"][b], n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [[], ["--paired", "--cigar_scores", "--min_score", "-40"]], ids=["se", "pe_cigar"])
+def test_sharded_cli_on_bam_inputs_equals_single_process_cli(tmp_path, flags):
+    """--primary_bam / --secondary_bam under the launcher (two ranks, one device each): every rank maps both files, inflates
+    and renders its part on its GPU (xm_bam_shard_*), the text shards go through the walk across GPUs.  The six files,
+    headers included, equal those of the single-process command on the same BAM files."""
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    from tests import _bamwriter
+    from tests.test_bam import FULL_HEADER
+    style = synth.STYLE_PE_BOWTIE2 if flags else synth.STYLE_SE_BOWTIE2
+    p, s = synth.generate(60000, seed=29, style=style)
+    if not flags:
+        p, s = with_repeats(p), with_repeats(s, every=5)
+    hdr2 = FULL_HEADER.replace("SN:chr", "SN:").replace("SN:M\t", "SN:MT\t")
+    open(tmp_path / "p.bam", "wb").write(_bamwriter.sam_to_bam(FULL_HEADER, bytes(p)))
+    open(tmp_path / "s.bam", "wb").write(_bamwriter.sam_to_bam(hdr2, bytes(s)))
+    names = ["primary_specific", "secondary_specific", "primary_multi", "secondary_multi", "unassigned", "unresolved"]
+
+    def run(tag, launcher):
+        outs = []
+        for n in names:
+            outs += ["--" + n, str(tmp_path / ("%s_%s.sam" % (tag, n)))]
+        cmd = launcher + ["-m", "xenomapper_b200.xenomapper", "--primary_bam", str(tmp_path / "p.bam"),
+                          "--secondary_bam", str(tmp_path / "s.bam")] + outs + flags
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, timeout=600)
+        assert r.returncode == 0, r.stderr.decode()[-3000:]
+        return [open(tmp_path / ("%s_%s.sam" % (tag, n)), "rb").read() for n in names], r.stderr.decode()
+
+    one, summary1 = run("one", [sys.executable])
+    two, summary2 = run("two", [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                                "--master-addr", "127.0.0.1", "--master-port", str(free_port())])
+    assert two == one
+    assert summary1[summary1.index("Read Count"):].strip() in summary2
+    assert sum(len(x) for x in one) > len(bytes(p)) // 2

@@ -26,7 +26,8 @@ EXPORTS = ("xm_abi_version", "xm_create", "xm_destroy", "xm_last_error", "xm_cla
            "xm_comm_unique_id", "xm_comm_init_rank", "xm_comm_destroy", "xm_comm_barrier", "xm_comm_allreduce_f64",
            "xm_classify_sharded_device", "xm_classify_sharded_host", "xm_copy_ceiling",
            "xm_process_headers_fds", "xm_process_headers_mem", "xm_classify_fds_ex", "xm_bgzf_write", "xm_classify_streams",
-           "xm_bgzf_deflate_host", "xm_bgzf_get_stats", "xm_classify_bam_fds")
+           "xm_bgzf_deflate_host", "xm_bgzf_get_stats", "xm_classify_bam_fds",
+           "xm_bam_shard_open", "xm_bam_shard_chain", "xm_bam_shard_text")
 OUT_BGZF = 1
 
 
@@ -354,6 +355,38 @@ class Context:
         self._check(rc, "xm_classify_bam_fds")
         del pk, sk
         return rc, res
+
+    NONE64 = (1 << 64) - 1
+
+    def bam_shard_open(self, stream, bam, rank, world):
+        """this rank's part of a BAM file: (guess, exit) offsets in the inflated stream (NONE64: no record start of its own);
+        the buffer must stay alive until bam_shard_text has been called"""
+        a, n, keep = _host_ptr(bam)
+        g, e = C.c_uint64(), C.c_uint64()
+        rc = self.lib.xm_bam_shard_open(self.h, stream, a, C.c_uint64(n), rank, world, C.byref(g), C.byref(e))
+        self._check(rc, "xm_bam_shard_open")
+        if rc:
+            raise XenomapperLibraryError("xm_bam_shard_open failed (%d): %s" % (rc, self.error()))
+        self._shard_keep = getattr(self, "_shard_keep", {})
+        self._shard_keep[stream] = keep
+        return int(g.value), int(e.value)
+
+    def bam_shard_chain(self, stream, entry):
+        e = C.c_uint64()
+        rc = self.lib.xm_bam_shard_chain(self.h, stream, C.c_uint64(entry), C.byref(e))
+        self._check(rc, "xm_bam_shard_chain")
+        if rc:
+            raise XenomapperLibraryError("xm_bam_shard_chain failed (%d): %s" % (rc, self.error()))
+        return int(e.value)
+
+    def bam_shard_text(self, stream, front_room, back_room):
+        """(device pointer of the part's SAM text, its length)"""
+        p, n = C.c_void_p(), C.c_uint64()
+        rc = self.lib.xm_bam_shard_text(self.h, stream, C.c_uint64(front_room), C.c_uint64(back_room), C.byref(p), C.byref(n))
+        self._check(rc, "xm_bam_shard_text")
+        if rc:
+            raise XenomapperLibraryError("xm_bam_shard_text failed (%d): %s" % (rc, self.error()))
+        return p.value, int(n.value)
 
     def bam_render_host(self, bam):
         """all records of a BAM file as SAM text (what `samtools view` prints), rendered on the device"""

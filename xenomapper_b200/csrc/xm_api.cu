@@ -208,6 +208,7 @@ struct xm_ctx {
     DevBuf d_bam_comp[2], d_bam_tab[2], d_bam_seg[2];      /* compressed window, its block table, the chain's segments */
     /* BGZF output deflated on the device (xm_deflate.h): member slots, sizes + offsets + plan, packed members per output set and bin */
     DevBuf d_zslot, d_zmeta, d_zout[2][6];
+    void *bam_shard[2] = {nullptr, nullptr};      /* BamProducer of a rank's part of a BAM file (xm_bam_shard_*) */
     std::vector<uint8_t> z_host;
     xm_bgzf_stats bgzf_stats{};
     std::vector<uint8_t> bam_text_host;
@@ -217,6 +218,7 @@ struct xm_ctx {
     ShardScratch shard;
     DevBuf d_shard[2];
 };
+extern "C" { static void bam_shard_free(xm_ctx *c); }
 
 static int fail(xm_ctx *c, int code, const std::string &msg)
 {
@@ -297,6 +299,7 @@ void xm_destroy(xm_ctx *c)
     for (auto &s : c->h_ring) for (auto &b : s) if (b.p) cudaFreeHost(b.p);
     for (auto &s : c->d_out) for (auto &b : s) if (b.p) cudaFree(b.p);
     for (auto &b : c->h_stage) if (b.p) cudaFreeHost(b.p);
+    bam_shard_free(c);
     for (auto &b : c->h_bam) if (b.p) cudaFreeHost(b.p);
     if (c->d_zslot.p) cudaFree(c->d_zslot.p);
     if (c->d_zmeta.p) cudaFree(c->d_zmeta.p);
@@ -1113,6 +1116,9 @@ struct BamProducer : DevSource {
     uint64_t have_d = 0, win_end = 0;   /* inflated bytes in d_bam[s]; end of the last whole record among them */
     uint64_t n_rec = 0, r_next = 0;     /* records of the window; the next one to render */
     uint64_t cut_off = 0;               /* text bytes of r_next's group of 1024 that are rendered already */
+    std::vector<ChainSeg> seg0;         /* the segments' guesses of the current window */
+    bool seg_valid = false;
+    uint64_t skip_abs = 0;              /* offset of the first record in the inflated stream */
     std::vector<unsigned long long> sums;      /* text bytes of each group of 1024 records of the window */
 
     /* block table, header (leading blocks inflated on the host: a few KiB), reference names to the device */
@@ -1131,6 +1137,7 @@ struct BamProducer : DevSource {
             if (bam_index(buf.data(), bytes, ix, true, e)) {
                 have_header = true;
                 skip = ix.first_record;
+                skip_abs = ix.first_record;
                 n_ref = (uint32_t)ix.ref_off.size() - 1;
                 const uint64_t ref_bytes = ix.ref_off.size() * 4 + ix.ref_names.size() + 16;
                 int rc;
@@ -1147,6 +1154,119 @@ struct BamProducer : DevSource {
 
     /* the next window: what is left of the last one moves to the front, the next blocks are inflated behind it, the chain is
      * followed and the text length of every record is found */
+    /* blocks [lo, hi) inflated behind the `left` bytes at the front of d_bam[s] (which holds them all) */
+    int inflate_blocks(size_t lo, size_t hi, uint64_t left, std::string &err)
+    {
+        cudaStream_t st = c->be.st;
+        const size_t nblk = hi - lo;
+        if (!nblk) return XM_OK;
+        int rc;
+        const uint64_t c0 = blocks[lo].in_off, c1 = blocks[hi - 1].in_off + blocks[hi - 1].in_len;
+        if ((rc = reserve_dev(c, c->d_bam_comp[s], c1 - c0 + 64)) || (rc = reserve_dev(c, c->d_bam_tab[s], nblk * sizeof(BgzfDev) + 16))) { err = c->err; return rc; }
+        const auto tu = std::chrono::steady_clock::now();
+        if ((rc = upload_shard(c, c->d_bam_comp[s].p, bam + c0, c1 - c0))) { err = c->err; return rc; }
+        c->bam_stats.upload_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - tu).count();
+        std::vector<BgzfDev> tab(nblk);
+        for (size_t k = 0; k < nblk; ++k) {
+            const BgzfBlock &b = blocks[lo + k];
+            tab[k].in_off = b.in_off - c0 + b.hdr_len;
+            tab[k].in_len = b.in_len - b.hdr_len - 8;
+            tab[k].out_off = left + (b.out_off - blocks[lo].out_off);
+            tab[k].out_len = b.out_len;
+            tab[k].crc = rd_u32(bam + b.in_off + b.in_len - 8);
+            tab[k].pad = 0;
+        }
+        EventPair ev;
+        cudaMemcpyAsync(c->d_bam_tab[s].p, tab.data(), nblk * sizeof(BgzfDev), cudaMemcpyHostToDevice, st);
+        unsigned long long *d_status = (unsigned long long *)(c->d_bam_tab[s].p + nblk * sizeof(BgzfDev));
+        const unsigned long long none = ~0ull;
+        cudaMemcpyAsync(d_status, &none, 8, cudaMemcpyHostToDevice, st);
+        cudaEventRecord(ev.a, st);
+        k_bgzf_inflate<<<(unsigned)((nblk + INF_WARPS - 1) / INF_WARPS), INF_WARPS * 32, 0, st>>>(c->d_bam_comp[s].p, (const BgzfDev *)c->d_bam_tab[s].p,
+                                                                                               (uint32_t)nblk, c->d_bam[s].p, d_status, 1);
+        cudaEventRecord(ev.b, st);
+        unsigned long long status = 0;
+        cudaMemcpyAsync(&status, d_status, 8, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "the BGZF inflate kernel failed"; return XM_ERR_CUDA; }
+        if (status != ~0ull) { err = "BAM input: BGZF block does not inflate (corrupt data or CRC mismatch)"; return XM_ERR_IO; }
+        c->bam_stats.inflate_ms += ev.ms();
+        c->bam_stats.n_launches += 1;
+        return XM_OK;
+    }
+
+    /* The record chain over d_bam[s][0, have_d) (xm_bamchain.h) and the text length of every record.  first: offset of a
+     * known record start, or CHAIN_NONE (a rank's part of a file: the chain starts at the first guess, reported in *guess).
+     * stop: only records that start before it are taken.  Sets n_rec, win_end (where the chain ended), sums. */
+    int chain_records(uint64_t first, uint64_t stop, uint64_t *guess, std::string &err)
+    {
+        cudaStream_t st = c->be.st;
+        DevBuf &D = c->d_bam[s];
+        int rc;
+        n_rec = 0; r_next = 0; win_end = 0; cut_off = 0;
+        if (guess) *guess = CHAIN_NONE;
+        const uint64_t SEG = bam_seg_bytes();
+        const uint32_t n_seg = (uint32_t)((have_d + SEG - 1) / SEG);
+        if (!n_seg) return XM_OK;
+        if ((rc = reserve_dev(c, c->d_bam_seg[s], (uint64_t)(n_seg + 1) * (sizeof(ChainSeg) + 8) + 64))) { err = c->err; return rc; }
+        ChainSeg *d_seg = (ChainSeg *)c->d_bam_seg[s].p, *d_one = d_seg + n_seg;
+        uint64_t *d_base = (uint64_t *)(d_one + 1);
+        if (!seg_valid) {
+            k_bam_chain<<<(n_seg + 127) / 128, 128, 0, st>>>(D.p, have_d, SEG, first, n_seg, n_ref, nullptr, d_seg);
+            seg0.resize(n_seg);
+            cudaMemcpyAsync(seg0.data(), d_seg, (size_t)n_seg * sizeof(ChainSeg), cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "the BAM chain kernel failed"; return XM_ERR_CUDA; }
+            c->bam_stats.n_launches += 1;
+        }
+        std::vector<ChainSeg> seg(seg0);                  /* the confirmation changes them; the guesses are kept for another try */
+        std::vector<uint64_t> base(n_seg);
+        if (first == CHAIN_NONE) {
+            for (uint32_t k = 0; k < n_seg && first == CHAIN_NONE; ++k) first = seg[k].entry;
+            if (first == CHAIN_NONE) { win_end = have_d; return XM_OK; }        /* no record starts in these bytes */
+        }
+        if (guess) *guess = first;
+        auto repair = [&](uint32_t k, uint64_t entry, uint64_t hi) {
+            ChainSeg r;
+            k_bam_chain_one<<<1, 32, 0, st>>>(D.p, have_d, (uint64_t)k * SEG, hi, entry, n_ref, d_one);
+            cudaMemcpyAsync(&r, d_one, sizeof r, cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess) { r.entry = entry; r.exit = entry; r.count = 0; r.flag = CHAIN_CORRUPT; }
+            return r;
+        };
+        uint64_t end = 0, nr = 0;
+        uint32_t nrep = 0;
+        if (!chain_confirm(seg.data(), base.data(), n_seg, SEG, first, have_d, std::min(stop, have_d), repair, end, nr, nrep)) { err = "corrupt BAM record"; return XM_ERR_IO; }
+        c->bam_stats.chain_repairs += nrep;
+        c->bam_stats.n_launches += nrep;
+        n_rec = nr; win_end = end;
+        if (!n_rec) return XM_OK;
+        const uint64_t nb = (n_rec + 1023) / 1024;
+        if ((rc = reserve_dev(c, c->d_bam_rec[s], n_rec * 8)) || (rc = reserve_dev(c, c->d_bam_len[s], n_rec * 8 + 16)) ||
+            (rc = reserve_dev(c, c->d_bam_sum[s], nb * 8 + 16))) { err = c->err; return rc; }
+        cudaMemcpyAsync(d_seg, seg.data(), (size_t)n_seg * sizeof(ChainSeg), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_base, base.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st);
+        k_bam_chain_emit<<<(n_seg + 127) / 128, 128, 0, st>>>(D.p, have_d, SEG, n_seg, d_seg, d_base, (uint64_t *)c->d_bam_rec[s].p);
+        unsigned long long *d_err = (unsigned long long *)(c->d_bam_sum[s].p + nb * 8);
+        const unsigned long long no_err = BAM_NO_ERROR;
+        cudaMemcpyAsync(d_err, &no_err, 8, cudaMemcpyHostToDevice, st);
+        BamDev B = dev_view(0, n_rec);
+        uint32_t *d_len = (uint32_t *)c->d_bam_len[s].p, *d_loff = d_len + n_rec + (n_rec & 1);
+        EventPair rv;
+        cudaEventRecord(rv.a, st);
+        k_bam_len<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(B, d_len, d_err);
+        k_bam_scan_blocks<<<(unsigned)nb, 1024, 0, st>>>(d_len, n_rec, d_loff, (unsigned long long *)c->d_bam_sum[s].p);
+        cudaEventRecord(rv.b, st);
+        sums.assign(nb + 1, 0);
+        cudaMemcpyAsync(sums.data(), c->d_bam_sum[s].p, (nb + 1) * 8, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "BAM length kernels failed"; return XM_ERR_CUDA; }
+        c->bam_stats.render_ms += rv.ms();
+        c->bam_stats.n_launches += 4;
+        if (sums[nb] != BAM_NO_ERROR) {
+            if ((sums[nb] & 0xff) == BAM_E_FLOAT) { err = "a BAM record has a float aux value (f or B:f): not rendered on the device"; return XM_ERR_UNSUPPORTED; }
+            err = "corrupt BAM record"; return XM_ERR_IO;
+        }
+        c->bam_stats.records += n_rec;
+        return XM_OK;
+    }
+
     int load_window(std::string &err)
     {
         cudaStream_t st = c->be.st;
@@ -1170,44 +1290,12 @@ struct BamProducer : DevSource {
             if ((rc = reserve_dev(c, D, std::max<uint64_t>(left + add + 64, std::min<uint64_t>(W, inflated_total) + 64)))) { if (tmp) cudaFree(tmp); err = c->err; return rc; }
             if (left) { cudaMemcpyAsync(D.p, tmp, left, cudaMemcpyDeviceToDevice, st); cudaStreamSynchronize(st); cudaFree(tmp); }
         }
-        const size_t nblk = last - blk;
-        EventPair ev;
-        unsigned long long *d_status = nullptr;
-        if (nblk) {
-            const uint64_t c0 = blocks[blk].in_off, c1 = blocks[last - 1].in_off + blocks[last - 1].in_len;
-            if ((rc = reserve_dev(c, c->d_bam_comp[s], c1 - c0 + 64)) || (rc = reserve_dev(c, c->d_bam_tab[s], nblk * sizeof(BgzfDev) + 16))) { err = c->err; return rc; }
-            const auto tu = std::chrono::steady_clock::now();
-            if ((rc = upload_shard(c, c->d_bam_comp[s].p, bam + c0, c1 - c0))) { err = c->err; return rc; }
-            c->bam_stats.upload_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - tu).count();
-            std::vector<BgzfDev> tab(nblk);
-            for (size_t k = 0; k < nblk; ++k) {
-                const BgzfBlock &b = blocks[blk + k];
-                tab[k].in_off = b.in_off - c0 + b.hdr_len;
-                tab[k].in_len = b.in_len - b.hdr_len - 8;
-                tab[k].out_off = left + (b.out_off - blocks[blk].out_off);
-                tab[k].out_len = b.out_len;
-                tab[k].crc = rd_u32(bam + b.in_off + b.in_len - 8);
-                tab[k].pad = 0;
-            }
-            cudaMemcpyAsync(c->d_bam_tab[s].p, tab.data(), nblk * sizeof(BgzfDev), cudaMemcpyHostToDevice, st);
-            d_status = (unsigned long long *)(c->d_bam_tab[s].p + nblk * sizeof(BgzfDev));
-            const unsigned long long none = ~0ull;
-            cudaMemcpyAsync(d_status, &none, 8, cudaMemcpyHostToDevice, st);
-            cudaEventRecord(ev.a, st);
-            k_bgzf_inflate<<<(unsigned)((nblk + INF_WARPS - 1) / INF_WARPS), INF_WARPS * 32, 0, st>>>(c->d_bam_comp[s].p, (const BgzfDev *)c->d_bam_tab[s].p,
-                                                                                                   (uint32_t)nblk, D.p, d_status, 1);
-            cudaEventRecord(ev.b, st);
-            unsigned long long status = 0;
-            cudaMemcpyAsync(&status, d_status, 8, cudaMemcpyDeviceToHost, st);
-            if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "the BGZF inflate kernel failed"; return XM_ERR_CUDA; }
-            if (status != ~0ull) { err = "BAM input: BGZF block does not inflate (corrupt data or CRC mismatch)"; return XM_ERR_IO; }
-            c->bam_stats.inflate_ms += ev.ms();
-            c->bam_stats.n_launches += 1;
-        }
+        if ((rc = inflate_blocks(blk, last, left, err))) return rc;
         have_d = left + add;
         blk = last;
         c->bam_stats.inflated_bytes += add;
         n_rec = 0; r_next = 0; win_end = 0; cut_off = 0;
+        seg_valid = false;
         uint64_t first = 0;
         if (skip) {
             if (skip >= have_d) {            /* nothing but header so far */
@@ -1217,65 +1305,85 @@ struct BamProducer : DevSource {
             }
             first = skip; skip = 0;
         }
-        /* the record chain (xm_bamchain.h) */
-        const uint64_t SEG = bam_seg_bytes();
-        const uint32_t n_seg = (uint32_t)((have_d + SEG - 1) / SEG);
-        if (n_seg) {
-            if ((rc = reserve_dev(c, c->d_bam_seg[s], (uint64_t)(n_seg + 1) * (sizeof(ChainSeg) + 8) + 64))) { err = c->err; return rc; }
-            ChainSeg *d_seg = (ChainSeg *)c->d_bam_seg[s].p, *d_one = d_seg + n_seg;
-            uint64_t *d_base = (uint64_t *)(d_one + 1);
-            k_bam_chain<<<(n_seg + 127) / 128, 128, 0, st>>>(D.p, have_d, SEG, first, n_seg, n_ref, nullptr, d_seg);
-            std::vector<ChainSeg> seg(n_seg);
-            std::vector<uint64_t> base(n_seg);
-            cudaMemcpyAsync(seg.data(), d_seg, (size_t)n_seg * sizeof(ChainSeg), cudaMemcpyDeviceToHost, st);
-            if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "the BAM chain kernel failed"; return XM_ERR_CUDA; }
-            auto repair = [&](uint32_t k, uint64_t entry) {
-                const uint64_t lo = (uint64_t)k * SEG, hi = std::min(lo + SEG, have_d);
-                ChainSeg r;
-                k_bam_chain_one<<<1, 32, 0, st>>>(D.p, have_d, lo, hi, entry, n_ref, d_one);
-                cudaMemcpyAsync(&r, d_one, sizeof r, cudaMemcpyDeviceToHost, st);
-                if (cudaStreamSynchronize(st) != cudaSuccess) { r.entry = entry; r.exit = entry; r.count = 0; r.flag = CHAIN_CORRUPT; }
-                return r;
-            };
-            uint64_t end = 0, nr = 0;
-            uint32_t nrep = 0;
-            if (!chain_confirm(seg.data(), base.data(), n_seg, SEG, first, have_d, repair, end, nr, nrep)) { err = "corrupt BAM record"; return XM_ERR_IO; }
-            c->bam_stats.chain_repairs += nrep;
-            c->bam_stats.n_launches += 1 + nrep;
-            n_rec = nr; win_end = end;
-            if (n_rec) {
-                const uint64_t nb = (n_rec + 1023) / 1024;
-                if ((rc = reserve_dev(c, c->d_bam_rec[s], n_rec * 8)) || (rc = reserve_dev(c, c->d_bam_len[s], n_rec * 8 + 16)) ||
-                    (rc = reserve_dev(c, c->d_bam_sum[s], nb * 8 + 16))) { err = c->err; return rc; }
-                cudaMemcpyAsync(d_seg, seg.data(), (size_t)n_seg * sizeof(ChainSeg), cudaMemcpyHostToDevice, st);
-                cudaMemcpyAsync(d_base, base.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st);
-                k_bam_chain_emit<<<(n_seg + 127) / 128, 128, 0, st>>>(D.p, have_d, SEG, n_seg, d_seg, d_base, (uint64_t *)c->d_bam_rec[s].p);
-                unsigned long long *d_err = (unsigned long long *)(c->d_bam_sum[s].p + nb * 8);
-                const unsigned long long no_err = BAM_NO_ERROR;
-                cudaMemcpyAsync(d_err, &no_err, 8, cudaMemcpyHostToDevice, st);
-                BamDev B = dev_view(0, n_rec);
-                uint32_t *d_len = (uint32_t *)c->d_bam_len[s].p, *d_loff = d_len + n_rec + (n_rec & 1);
-                EventPair rv;
-                cudaEventRecord(rv.a, st);
-                k_bam_len<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(B, d_len, d_err);
-                k_bam_scan_blocks<<<(unsigned)nb, 1024, 0, st>>>(d_len, n_rec, d_loff, (unsigned long long *)c->d_bam_sum[s].p);
-                cudaEventRecord(rv.b, st);
-                sums.assign(nb + 1, 0);
-                cudaMemcpyAsync(sums.data(), c->d_bam_sum[s].p, (nb + 1) * 8, cudaMemcpyDeviceToHost, st);
-                if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { err = "BAM length kernels failed"; return XM_ERR_CUDA; }
-                c->bam_stats.render_ms += rv.ms();
-                c->bam_stats.n_launches += 3;
-                if (sums[nb] != BAM_NO_ERROR) {
-                    if ((sums[nb] & 0xff) == BAM_E_FLOAT) { err = "a BAM record has a float aux value (f or B:f): not rendered on the device"; return XM_ERR_UNSUPPORTED; }
-                    err = "corrupt BAM record"; return XM_ERR_IO;
-                }
-                c->bam_stats.records += n_rec;
-            }
-        }
+        if ((rc = chain_records(first, have_d, nullptr, err))) return rc;
         if (blk == blocks.size() && win_end != have_d) { err = "truncated BAM record at the end of the file"; return XM_ERR_IO; }
         c->bam_stats.inflate_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         return XM_OK;
     }
+
+    /* ---- a rank's part of the file, for the walk across GPUs ------------------------------------------------------------
+     * Rank r of W takes the BGZF blocks that START in bytes [len r / W, len (r + 1) / W) of the file and, of the records,
+     * those that start in these blocks' inflated bytes [so0, so1).  It inflates its blocks and as many of the next ones as
+     * its last record reaches into (every rank maps the whole file: nothing is exchanged but two numbers per rank).  */
+    size_t sb0 = 0, sb1 = 0, sbx = 0;
+    uint64_t so0 = 0, so1 = 0;
+    int shard_open(int rank, int world, uint64_t &guess_abs, uint64_t &exit_abs, std::string &err)
+    {
+        auto first_block_at = [&](uint64_t byte) {
+            size_t lo = 0, hi = blocks.size();
+            while (lo < hi) { const size_t mid = (lo + hi) / 2; if (blocks[mid].in_off < byte) lo = mid + 1; else hi = mid; }
+            return lo;
+        };
+        sb0 = rank == 0 ? 0 : first_block_at(bam_len / (uint64_t)world * (uint64_t)rank);
+        sb1 = rank + 1 == world ? blocks.size() : first_block_at(bam_len / (uint64_t)world * (uint64_t)(rank + 1));
+        so0 = sb0 < blocks.size() ? blocks[sb0].out_off : inflated_total;
+        so1 = sb1 < blocks.size() ? blocks[sb1].out_off : inflated_total;
+        sbx = sb1;
+        return shard_chain(CHAIN_NONE, guess_abs, exit_abs, err);
+    }
+    /* (Re)do the chain of the rank's part.  entry_abs: the true start of its first record (the exit the rank before
+     * reports), or CHAIN_NONE for the first attempt: rank 0 knows its start, the others guess.  exit_abs: the first record
+     * start at or behind so1 -- the next rank's true entry. */
+    int shard_chain(uint64_t entry_abs, uint64_t &guess_abs, uint64_t &exit_abs, std::string &err)
+    {
+        const uint64_t data0 = std::max(so0, skip_abs);                       /* records start behind the header */
+        guess_abs = exit_abs = CHAIN_NONE;
+        if (so1 <= data0 || sb0 >= sb1) { n_rec = 0; have_d = 0; return XM_OK; }          /* header only, or no blocks: passes the entry on */
+        int rc;
+        for (size_t extra = 2;; extra *= 4) {
+            const size_t want = std::min(blocks.size(), sb1 + extra);
+            if (want != sbx || !have_d) {
+                uint64_t add = 0;
+                for (size_t k = sb0; k < want; ++k) add += blocks[k].out_len;
+                if ((rc = reserve_dev(c, c->d_bam[s], add + 64))) { err = c->err; return rc; }
+                if ((rc = inflate_blocks(sb0, want, 0, err))) return rc;
+                c->bam_stats.inflated_bytes += add;
+                have_d = add; sbx = want; seg_valid = false;
+            }
+            uint64_t first = entry_abs != CHAIN_NONE ? entry_abs - so0 : (so0 < skip_abs ? skip_abs - so0 : CHAIN_NONE);
+            if (first != CHAIN_NONE && first >= so1 - so0) { n_rec = 0; guess_abs = entry_abs; exit_abs = entry_abs; return XM_OK; }     /* one record covers the whole part */
+            uint64_t guess = CHAIN_NONE;
+            if ((rc = chain_records(first, so1 - so0, &guess, err))) return rc;
+            seg_valid = true;
+            guess_abs = guess == CHAIN_NONE ? CHAIN_NONE : so0 + guess;
+            if (guess == CHAIN_NONE) { exit_abs = CHAIN_NONE; return XM_OK; }     /* nothing that looks like a record: passes the entry on */
+            if (win_end >= so1 - so0 || (sbx == blocks.size() && win_end == have_d)) { exit_abs = so0 + win_end; return XM_OK; }
+            if (sbx == blocks.size()) { err = "truncated BAM record at the end of the file"; return XM_ERR_IO; }
+            /* the last record of the part runs past the blocks inflated so far: take more */
+        }
+    }
+    /* the part's records as SAM text at T.p + front_room (room behind it as well) */
+    int shard_text(uint64_t front_room, uint64_t back_room, DevBuf &T, uint64_t &text_len, std::string &err)
+    {
+        text_len = n_rec ? window_text_left() : 0;
+        int rc;
+        if ((rc = reserve_dev(c, T, front_room + text_len + back_room + 64))) { err = c->err; return rc; }
+        uint64_t off = 0;
+        while (r_next < n_rec) {
+            uint64_t n = 0;
+            bool fin = false;
+            full_cap = text_len - off;
+            const size_t keep_blk = blk;
+            blk = blocks.size();                               /* next() must not load windows */
+            rc = next(T.p + front_room + off, text_len - off, n, fin, err);
+            blk = keep_blk;
+            if (rc) return rc;
+            if (!n) { err = "BAM shard rendering made no progress"; return XM_ERR_IO; }
+            off += n;
+        }
+        return XM_OK;
+    }
+
     BamDev dev_view(uint64_t r0, uint64_t n) const
     {
         BamDev B;
@@ -1446,6 +1554,53 @@ int xm_classify_bam_fds(xm_ctx *c, const void *prim_bam, uint64_t prim_len, cons
 {
     if (!c || !opts || !res || !prim_bam || !sec_bam || !out_fds) return XM_ERR_ARG;
     return classify_bam(c, prim_bam, prim_len, sec_bam, sec_len, out_fds, opts, out_flags, res);
+}
+
+/* ---- a rank's part of a BAM file as SAM text on the device (the walk across GPUs on BAM input) ------------------------- */
+static void bam_shard_free(xm_ctx *c)
+{
+    for (auto &p : c->bam_shard) { delete (BamProducer *)p; p = nullptr; }
+}
+
+int xm_bam_shard_open(xm_ctx *c, int stream, const void *bam, uint64_t len, int rank, int world, uint64_t *guess, uint64_t *exit_off)
+{
+    if (!c || stream < 0 || stream > 1 || !bam || rank < 0 || world < 1 || rank >= world || !guess || !exit_off) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    delete (BamProducer *)c->bam_shard[stream];
+    BamProducer *p = new BamProducer;
+    c->bam_shard[stream] = p;
+    p->c = c; p->s = stream; p->bam = (const uint8_t *)bam; p->bam_len = len;
+    std::string err;
+    int rc = p->open(err);
+    if (rc) return fail(c, rc, err);
+    if (p->host_mode) return fail(c, XM_ERR_UNSUPPORTED, "the sharded BAM walk inflates on the device (unset XM_BAM_INFLATE)");
+    if ((rc = p->shard_open(rank, world, *guess, *exit_off, err))) return fail(c, rc, err);
+    return XM_OK;
+}
+
+int xm_bam_shard_chain(xm_ctx *c, int stream, uint64_t entry, uint64_t *exit_off)
+{
+    if (!c || stream < 0 || stream > 1 || !c->bam_shard[stream] || !exit_off) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    BamProducer *p = (BamProducer *)c->bam_shard[stream];
+    std::string err;
+    uint64_t guess = 0;
+    const int rc = p->shard_chain(entry, guess, *exit_off, err);
+    if (rc) return fail(c, rc, err);
+    return XM_OK;
+}
+
+int xm_bam_shard_text(xm_ctx *c, int stream, uint64_t front_room, uint64_t back_room, void **d_text, uint64_t *text_len)
+{
+    if (!c || stream < 0 || stream > 1 || !c->bam_shard[stream] || !d_text || !text_len) return XM_ERR_ARG;
+    cudaSetDevice(c->device);
+    BamProducer *p = (BamProducer *)c->bam_shard[stream];
+    std::string err;
+    front_room = (front_room + 15) & ~15ull;
+    const int rc = p->shard_text(front_room, back_room, c->d_bam_text[stream], *text_len, err);
+    if (rc) return fail(c, rc, err);
+    *d_text = c->d_bam_text[stream].p + front_room;
+    return XM_OK;
 }
 
 int xm_get_walk_kernels(xm_ctx *c, uint32_t *mask)

@@ -103,12 +103,14 @@ XM_HD void chain_emit(const uint8_t *d, uint64_t have, uint64_t hi, uint64_t ent
 __global__ void k_bam_chain(const uint8_t *d, uint64_t have, uint64_t seg_bytes, uint64_t first, uint32_t n_seg, uint32_t n_ref,
                             const uint64_t *entry_in, ChainSeg *seg)
 {
+    /* first == CHAIN_NONE: no record start is known (a rank's part of a file): every segment guesses */
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_seg) return;
     const uint64_t lo = (uint64_t)k * seg_bytes, hi = lo + seg_bytes < have ? lo + seg_bytes : have;
     uint64_t entry = entry_in ? entry_in[k] : CHAIN_NONE;
-    if (k == first / seg_bytes && !entry_in) entry = first;          /* the first record is known */
-    if (!entry_in && lo + seg_bytes <= first) { ChainSeg s; s.entry = CHAIN_NONE; s.exit = CHAIN_NONE; s.count = 0; s.flag = 0; seg[k] = s; return; }
+    const bool known = first != CHAIN_NONE;
+    if (known && k == first / seg_bytes && !entry_in) entry = first;          /* the first record is known */
+    if (known && !entry_in && lo + seg_bytes <= first) { ChainSeg s; s.entry = CHAIN_NONE; s.exit = CHAIN_NONE; s.count = 0; s.flag = 0; seg[k] = s; return; }
     seg[k] = chain_segment(d, have, lo, hi, entry, n_ref);
 }
 /* follow ONE segment from a given entry (the host's repair of an unconfirmed guess) */
@@ -129,24 +131,28 @@ __global__ void k_bam_chain_emit(const uint8_t *d, uint64_t have, uint64_t seg_b
 #endif
 
 /*
- * The host's part: confirm the guesses in order.  seg[] comes from the device; `repair(k, entry)` must follow segment k
- * from `entry` and return the result (one small launch; rare).  Leaves seg[k].count = 0 for segments no record starts
- * in, fills base[] (exclusive prefix of the counts) and returns the chain's end (the first byte that is not part of a
- * whole record); n_rec receives the number of records.  false: corrupt chain.
+ * The host's part: confirm the guesses in order.  seg[] comes from the device; `repair(k, entry, hi)` must follow segment k
+ * from `entry` up to byte hi and return the result (one small launch; rare).  Leaves seg[k].count = 0 for segments no
+ * record starts in, fills base[] (exclusive prefix of the counts) and returns the chain's end (the first byte that is not
+ * part of a whole record); n_rec receives the number of records.  false: corrupt chain.
+ * stop < have: only records that START before byte `stop` are counted (a rank's part of a file shared between GPUs);
+ * `end` is then the first record start at or behind stop when the data reaches that far, and less than stop when it
+ * does not (the caller fetches more).
  */
 template <class Repair>
-inline bool chain_confirm(ChainSeg *seg, uint64_t *base, uint32_t n_seg, uint64_t seg_bytes, uint64_t first, uint64_t have, Repair &&repair,
-                          uint64_t &end, uint64_t &n_rec, uint32_t &n_repaired)
+inline bool chain_confirm(ChainSeg *seg, uint64_t *base, uint32_t n_seg, uint64_t seg_bytes, uint64_t first, uint64_t have, uint64_t stop,
+                          Repair &&repair, uint64_t &end, uint64_t &n_rec, uint32_t &n_repaired)
 {
     uint64_t cur = first;
     n_rec = 0;
     n_repaired = 0;
     bool open = true;                       /* the chain still goes on (no incomplete record met) */
     for (uint32_t k = 0; k < n_seg; ++k) {
-        const uint64_t lo = (uint64_t)k * seg_bytes, hi = lo + seg_bytes < have ? lo + seg_bytes : have;
+        const uint64_t lo = (uint64_t)k * seg_bytes, whole = lo + seg_bytes < have ? lo + seg_bytes : have;
+        const uint64_t hi = whole < stop ? whole : stop;
         base[k] = n_rec;
-        if (!open || cur >= hi || cur < lo) { seg[k].count = 0; continue; }         /* no record starts here */
-        if (seg[k].entry != cur) { seg[k] = repair(k, cur); ++n_repaired; }
+        if (!open || lo >= stop || cur >= hi || cur < lo) { seg[k].count = 0; continue; }         /* no record of ours starts here */
+        if (seg[k].entry != cur || hi != whole) { seg[k] = repair(k, cur, hi); ++n_repaired; }
         if (seg[k].flag == CHAIN_CORRUPT) return false;
         n_rec += seg[k].count;
         cur = seg[k].exit;

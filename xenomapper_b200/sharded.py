@@ -15,6 +15,7 @@ and every collective live inside libxenomapper_b200.so (csrc/xm_shard.h): this m
     in rank order equal the single-GPU output byte for byte.
 """
 import os
+import struct
 import tempfile
 import time
 
@@ -130,3 +131,69 @@ def write_outputs(result, fds, header_len):
         done = 0
         while done < len(data):
             done += os.pwrite(fds[b], data[done:done + (1 << 30)], at + done)
+
+
+# ---------------------------------------------------------------------------
+# BAM input: every rank maps both files and takes the BGZF blocks that start in its 1/world of each file's bytes
+
+def _settle_entries(ctx, rank, world, rv, stream, guess, exit_off, tag):
+    """The ranks' record chains joined: rank r's part begins where the chain of the ranks before it leaves off.  Every rank
+    publishes (entry it followed, exit it reached) -- (NONE, NONE) when it saw no record start of its own -- and all read the
+    same table: going through the ranks in order, a rank whose entry is not the exit handed to it follows its part again from
+    there (xm_bam_shard_chain: a part the chain jumps over answers with the entry itself) and the table is made anew.
+    Guesses are nearly always right: one round, or two when a part saw nothing."""
+    none = ctx.NONE64
+    entry = guess
+    for rnd in range(world + 2):
+        rv.publish("%s_%d_%d_%d" % (tag, stream, rnd, rank), struct.pack("<QQ", entry, exit_off))
+        rows = [struct.unpack("<QQ", rv.fetch("%s_%d_%d_%d" % (tag, stream, rnd, r))) for r in range(world)]
+        cur, mine, ok = None, None, True
+        for r, (e_used, ex) in enumerate(rows):
+            if r == rank:
+                mine = cur
+            if cur is None:
+                if e_used != none:
+                    cur = ex                 # the first rank that holds records knows where they start
+                continue
+            if e_used != cur:
+                ok = False                   # that rank looks again; what it reports now cannot be trusted
+            cur = ex if e_used != none else cur
+        if ok:
+            return
+        if mine is not None and entry != mine:
+            exit_off = ctx.bam_shard_chain(stream, mine)
+            entry = mine
+    raise RuntimeError("the ranks' BAM record chains did not settle")
+
+
+def sharded_bam_walk(ctx, rank, world, rv, prim_bam, sec_bam, mode=_lib.MODE_SE, score_src=_lib.SCORE_AS_XS, skip=False,
+                     min_score=float("-inf"), enabled_bins=0x3F, room=1 << 20, tag="bamchain"):
+    """prim_bam / sec_bam: the WHOLE files (bytes-like; numpy arrays over mapped files).  This rank's part of each is
+    inflated and rendered as SAM text on its GPU, the text shards go through the walk across GPUs.  Returns the dict of
+    sharded_walk()."""
+    if rv is None and world > 1:
+        rv = Rendezvous(rank, world)
+    shards = []
+    for stream, bam in enumerate((prim_bam, sec_bam)):
+        guess, exit_off = ctx.bam_shard_open(stream, bam, rank, world)
+        if world > 1:
+            _settle_entries(ctx, rank, world, rv, stream, guess, exit_off, tag)
+        shards.append(ctx.bam_shard_text(stream, room, room))
+    (dp, np_), (ds, ns_) = shards
+    opts = ctx.opts(mode, score_src, skip, float(min_score), enabled_bins)
+    slack = 2 * room + 4096
+    caps = [np_ + slack, ns_ + slack, np_ + slack, ns_ + slack, np_ + slack, np_ + ns_ + slack]      # PS SS PM SM UA UR
+    caps = [c if (enabled_bins >> b) & 1 else 16 for b, c in enumerate(caps)]
+    d_out = [ctx.dev_alloc(c) for c in caps]
+    try:
+        rc, res, st = ctx.classify_sharded_device(dp, np_, ds, ns_, room, room, opts, d_out, caps)
+        outs = [ctx.d2h(d_out[b], int(res.out_len[b])) if rc == _lib.XM_OK else b"" for b in range(6)]
+    finally:
+        for d in d_out:
+            ctx.dev_free(d)
+    return dict(status=rc, message=ctx.error() if rc else "", err_record=int(res.err_record), counts=list(res.counts),
+                n_records=int(res.n_records), outputs=outs, out_offset=list(st.out_offset), out_total=list(st.out_total),
+                records=(int(st.rec_lo), int(st.rec_hi)), rank=rank, world=world,
+                stats=dict(align_ms=st.align_ms, index_ms=st.index_ms, sliver_ms=st.sliver_ms, walk_ms=st.walk_ms,
+                           comm_ms=st.comm_ms, total_ms=st.total_ms, sliver_bytes=int(st.sliver_bytes),
+                           sent_bytes=int(st.sent_bytes), collectives=int(st.n_collectives)))

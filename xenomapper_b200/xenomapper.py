@@ -499,8 +499,6 @@ def main(argv=None):
                 unassigned=args.unassigned, unresolved=args.unresolved)
     skip = not args.paired                       # xm.py:691
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        if not args.primary_sam:
-            raise NotImplementedError("the sharded walk (one process per GPU) takes SAM inputs")
         return _main_sharded(args, tag_func, outs, skip)
     if args.primary_sam and (_regular_fd(args.primary_sam) is None or _regular_fd(args.secondary_sam) is None):
         return _main_streams(args, tag_func, outs, skip)
@@ -590,9 +588,13 @@ def _main_sharded(args, tag_func, outs, skip):
     ctx = _lib.Context(local)
     rv = sharded.init_comm(ctx, rank, world)
     ctx.comm_barrier()                              # every rank has opened (and truncated) the outputs
+    bam = not args.primary_sam
     hdr_len = [0] * 6
     if rank == 0:
-        process_headers(args.primary_sam, args.secondary_sam, **outs)
+        if bam:
+            process_headers(args.primary_bam, args.secondary_bam, bam=True, **outs)
+        else:
+            process_headers(args.primary_sam, args.secondary_sam, **outs)
         for b, f in enumerate(files):
             if f:
                 f.flush()
@@ -600,16 +602,22 @@ def _main_sharded(args, tag_func, outs, skip):
         rv.publish("header_len", json.dumps(hdr_len).encode())
     else:
         hdr_len = json.loads(rv.fetch("header_len").decode())
-    # byte offset of each input's first record: the library's header pass on the raw bytes, on every rank
-    with open(args.primary_sam.name, "rb") as fp, open(args.secondary_sam.name, "rb") as fs:
-        hrc, _, rec_off, _, _ = _lib.process_headers(fp.fileno(), fs.fileno(), __version__)
-    if hrc != _lib.XM_OK:
-        raise IndexError('string index out of range')
     mode = _lib.MODE_SE if not args.paired else (_lib.MODE_PE_CONSERVATIVE if args.conservative else _lib.MODE_PE_LIBERAL)
     enabled = sum(1 << b for b, f in enumerate(files) if f)
-    with open(args.primary_sam.name, "rb") as fp, open(args.secondary_sam.name, "rb") as fs:
-        res = sharded.sharded_walk(ctx, rank, world, fp.fileno(), rec_off[0], fs.fileno(), rec_off[1], mode=mode, score_src=_SCORE_SRC[tag_func], skip=skip,
-                                   min_score=args.min_score, enabled_bins=enabled)
+    if bam:
+        # every rank maps both files; its part of each is inflated and rendered on its GPU (xm_bam_shard_*)
+        from . import bam as bam_mod
+        res = sharded.sharded_bam_walk(ctx, rank, world, rv, bam_mod._all_bytes(args.primary_bam), bam_mod._all_bytes(args.secondary_bam),
+                                       mode=mode, score_src=_SCORE_SRC[tag_func], skip=skip, min_score=args.min_score, enabled_bins=enabled)
+    else:
+        # byte offset of each input's first record: the library's header pass on the raw bytes, on every rank
+        with open(args.primary_sam.name, "rb") as fp, open(args.secondary_sam.name, "rb") as fs:
+            hrc, _, rec_off, _, _ = _lib.process_headers(fp.fileno(), fs.fileno(), __version__)
+        if hrc != _lib.XM_OK:
+            raise IndexError('string index out of range')
+        with open(args.primary_sam.name, "rb") as fp, open(args.secondary_sam.name, "rb") as fs:
+            res = sharded.sharded_walk(ctx, rank, world, fp.fileno(), rec_off[0], fs.fileno(), rec_off[1], mode=mode, score_src=_SCORE_SRC[tag_func], skip=skip,
+                                       min_score=args.min_score, enabled_bins=enabled)
     sharded.write_outputs(res, [f.fileno() if f else -1 for f in files], hdr_len)
     ctx.comm_barrier()
     if rank == 0:
