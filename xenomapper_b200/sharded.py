@@ -167,7 +167,7 @@ def _settle_entries(ctx, rank, world, rv, stream, guess, exit_off, tag):
 
 
 def sharded_bam_walk(ctx, rank, world, rv, prim_bam, sec_bam, mode=_lib.MODE_SE, score_src=_lib.SCORE_AS_XS, skip=False,
-                     min_score=float("-inf"), enabled_bins=0x3F, room=1 << 20, tag="bamchain"):
+                     min_score=float("-inf"), enabled_bins=0x3F, room=1 << 20, tag="bamchain", want_outputs=True):
     """prim_bam / sec_bam: the WHOLE files (bytes-like; numpy arrays over mapped files).  This rank's part of each is
     inflated and rendered as SAM text on its GPU, the text shards go through the walk across GPUs.  Returns the dict of
     sharded_walk()."""
@@ -187,7 +187,7 @@ def sharded_bam_walk(ctx, rank, world, rv, prim_bam, sec_bam, mode=_lib.MODE_SE,
     d_out = [ctx.dev_alloc(c) for c in caps]
     try:
         rc, res, st = ctx.classify_sharded_device(dp, np_, ds, ns_, room, room, opts, d_out, caps)
-        outs = [ctx.d2h(d_out[b], int(res.out_len[b])) if rc == _lib.XM_OK else b"" for b in range(6)]
+        outs = [ctx.d2h(d_out[b], int(res.out_len[b])) if rc == _lib.XM_OK and want_outputs else b"" for b in range(6)]
     finally:
         for d in d_out:
             ctx.dev_free(d)
