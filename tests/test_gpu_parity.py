@@ -257,3 +257,37 @@ print(json.dumps(out))
     for name, v in res.items():
         assert v["clean_ok"], (name, v)
         assert v["rc"] == 1 and v["ref_err"] == 1 and v["prefix_ok"], (name, v)
+
+
+@pytest.mark.parametrize("rows", [0, 4], ids=["fused", "rows"])
+@pytest.mark.parametrize("mode,skip", [(0, True), (1, False)])
+def test_cuda_short_read_lines_stay_on_the_span_kernels(mode, skip, rows):
+    """lines under ~190 bytes overflow the 64 lines a 12 KiB span holds and used to send the whole call to the exact
+    kernels.  Streams of short lines take spans of half the size -- chosen from a sample on a context's first walk, and switched
+    to when a span overflows on a later one."""
+    from oracle import oracle
+    from tests.test_emu_tiles import _fixed_width_pair
+    from xenomapper_b200 import _lib
+    fast = ["k_scan2", "k_size+k_prefix+k_emit"] if rows else ["k_scan2", "k_classify2"]
+    opts = _lib.Context.opts(mode, 0, skip)
+
+    def walk(c, width, n=6000):
+        p, s = _fixed_width_pair(n, width)
+        ref = oracle.classify(p, s, mode=mode, skip_repeated=skip)
+        rc, res, outs = c.classify_host(p, s, opts)
+        assert rc == 0, c.error()
+        assert list(res.counts) == ref["counts"] and outs == ref["outputs"]
+        return c.walk_kernels()
+
+    c = _lib.Context(0)
+    c.set_debug(rows)
+    for width in (128, 104, 160, 190, 700):                 # short lines from the start: the sample picks the small spans; long lines fit them too
+        assert walk(c, width) == fast, width
+    assert walk(c, 80) != fast                              # more than 64 lines per small span: the exact kernels
+    c.close()
+    c = _lib.Context(0)
+    c.set_debug(rows)
+    assert walk(c, 440) == fast                             # the usual geometry
+    assert walk(c, 128) == fast                             # a span overflows: the call goes on with the small spans
+    assert walk(c, 440) == fast
+    c.close()

@@ -103,7 +103,8 @@ struct DeviceBackend {
     int prefix(const EmitArgs &a) { return chk(launch_prefix(a, st)); }
     int emit(const EmitArgs &a) { return chk(launch_emit(a, st)); }
     int add64(void *p, uint64_t n, unsigned long long d) { return chk(launch_add_u64((unsigned long long *)p, d, n, st)) || chk(cudaStreamSynchronize(st)); }
-    uint64_t scan2_tiles(uint64_t len) { const uint64_t t = scan2_tile_bytes(); return (len + t - 1) / t; }
+    /* tiles the span kernels cut `len` bytes into at most, whatever geometry the launchers pick (look-back arrays are sized for it) */
+    uint64_t scan2_tiles(uint64_t len) { const uint64_t t = span_tile_bytes_min(); return (len + t - 1) / t; }
     int classify(const ClassifyArgs &a, bool small) { return chk(launch_classify(a, small, st)); }
 };
 

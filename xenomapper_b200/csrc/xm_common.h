@@ -103,6 +103,8 @@ struct ScanArgs {
     int32_t want_same;                /* mark rows whose QNAME repeats the previous line's (META_SAME): paired walks over rows */
     int32_t count_only;               /* record counts and row offsets only: the score tokens are not parsed */
     uint64_t start_bias;              /* added to every row's byte offset (sharded walks: offsets count from the shard allocation's first byte) */
+    int32_t short_lines;              /* lines of less than ~300 bytes on average: the span kernels take spans of half the size (64 lines per span still fit) */
+    int32_t pad_;
 };
 
 /* The row walk (xm_emit.cuh): both streams have been scanned into compact rows; record i of the walk is row i of
@@ -141,6 +143,7 @@ struct ClassifyArgs {
     uint8_t *out[6];
     uint64_t out_cap[6];
     uint32_t debug;
+    int32_t short_lines;              /* as in ScanArgs */
 };
 
 constexpr uint32_t DBG_FORCE_GENERIC = 1, DBG_SMALL_TILES = 2, DBG_ROWS = 4, DBG_EXACT_NAMES = 8;

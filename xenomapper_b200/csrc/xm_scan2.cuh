@@ -51,6 +51,11 @@ struct Scan2Cfg {
 #endif
 using Scan2Big = Scan2Cfg<XM_CLS2_WARPS, XM_SCAN2_SPAN, 1024, 2048>;        /* k_classify2: ~28 primary lines of 440 bytes per span */
 using Scan2Sec = Scan2Cfg<XM_SCAN2_WARPS, XM_SCAN2_SPAN_S, 1024, 2048>;      /* k_scan2: ~30 secondary lines of 378 bytes (one parse batch) */
+/* short reads: a span holds at most 64 lines (two parse batches), so lines of less than ~190 bytes overflow the spans above and
+ * send the whole call to the exact kernels.  Streams whose lines are short on average take spans of half the size: 64 lines of
+ * 80-96 bytes and more still fit. */
+using Scan2BigShort = Scan2Cfg<XM_CLS2_WARPS, 6144, 1024, 2048>;
+using Scan2SecShort = Scan2Cfg<XM_SCAN2_WARPS, 5120, 1024, 2048>;
 
 /* what a warp knows about its span once the masks are built and the line starts are listed */
 struct SpanInfo {
@@ -715,7 +720,10 @@ static cudaError_t launch_classify2_t(ClassifyArgs a, cudaStream_t st)
     k_classify2<C><<<(unsigned)nt, C::WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
-cudaError_t launch_classify2(const ClassifyArgs &a, cudaStream_t st) { return launch_classify2_t<Scan2Big>(a, st); }
+cudaError_t launch_classify2(const ClassifyArgs &a, cudaStream_t st)
+{
+    return a.short_lines ? launch_classify2_t<Scan2BigShort>(a, st) : launch_classify2_t<Scan2Big>(a, st);
+}
 
 template <class C>
 static cudaError_t launch_scan2_t(ScanArgs a, cudaStream_t st)
@@ -727,7 +735,19 @@ static cudaError_t launch_scan2_t(ScanArgs a, cudaStream_t st)
     else k_scan2<C, false, false><<<(unsigned)nt, C::WARPS * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
-cudaError_t launch_scan2(const ScanArgs &a, cudaStream_t st) { return launch_scan2_t<Scan2Sec>(a, st); }
+cudaError_t launch_scan2(const ScanArgs &a, cudaStream_t st)
+{
+    return a.short_lines ? launch_scan2_t<Scan2SecShort>(a, st) : launch_scan2_t<Scan2Sec>(a, st);
+}
 uint32_t scan2_tile_bytes() { return Scan2Sec::TILE; }
+/* the smallest tile any of the span kernels' geometries has: look-back arrays are sized for it */
+uint32_t span_tile_bytes_min()
+{
+    uint32_t t = Scan2Sec::TILE;
+    if (Scan2Big::TILE < t) t = Scan2Big::TILE;
+    if (Scan2BigShort::TILE < t) t = Scan2BigShort::TILE;
+    if (Scan2SecShort::TILE < t) t = Scan2SecShort::TILE;
+    return t;
+}
 
 }  // namespace xm

@@ -71,6 +71,7 @@ struct ShardRows {
     uint64_t cap_tiles = 0;
 };
 struct ShardScratch {
+    int short_lines = 0;             /* the scans take spans of half the size (set when a span overflowed) */
     ShardRows r[2];
     Globals *g = nullptr;
     unsigned long long *tile_tot = nullptr;
@@ -324,7 +325,7 @@ inline int walk_sharded(BE &be, CM &cm, ShardScratch &sc, const ShardBuf in[2], 
     }
     bool declined = false;
     if (!local_rc) {
-        for (int attempt = 0; attempt < 3 && !local_rc; ++attempt) {
+        for (int attempt = 0; attempt < 4 && !local_rc; ++attempt) {
             Globals init;
             memset(&init, 0, sizeof init);
             init.err = NO_ERROR;
@@ -341,6 +342,7 @@ inline int walk_sharded(BE &be, CM &cm, ShardScratch &sc, const ShardBuf in[2], 
                 a.score_src = o.score_src; a.skip = skip ? 1 : 0; a.stream_id = s; a.debug = 0;
                 a.want_same = (s == 0 && paired && !skip) ? 1 : 0;
                 a.start_bias = (uint64_t)((in[s].p + scan_lo[s]) - ebase[s]);
+                a.short_lines = sc.short_lines;
                 const int rc = be.scan2(a);
                 if (rc < 0) { declined = true; break; }
                 if (rc > 0) { fail(XM_ERR_CUDA, "scan kernel launch failed: " + be.last_error()); break; }
@@ -349,7 +351,10 @@ inline int walk_sharded(BE &be, CM &cm, ShardScratch &sc, const ShardBuf in[2], 
             if (local_rc || declined) break;
             if (be.read(&G, sc.g, sizeof G)) { fail(XM_ERR_CUDA, "kernel execution failed: " + be.last_error()); break; }
             res->n_launches += (uint32_t)launched;
-            if (G.pad) { declined = true; break; }
+            if (G.pad) {
+                if (!sc.short_lines) { sc.short_lines = 1; continue; }        /* short reads overflow the spans: half the size, once */
+                declined = true; break;
+            }
             bool grown = false;
             for (int s = 0; s < 2; ++s)
                 if (G.n_stream[s] > sc.r[s].cap) {

@@ -161,6 +161,7 @@ struct Scratch {
     unsigned long long *tile_tot = nullptr;
     uint64_t cap_tot = 0;
     double line_bytes[2] = {0, 0};   /* mean bytes per record of the last walk's streams: sizes the row arrays of the next one */
+    int short_lines[2] = {-1, -1};   /* the span kernels' geometry per stream (primary, secondary): -1 not looked at yet, 1 spans of half the size */
 };
 
 template <class BE>
@@ -224,7 +225,7 @@ inline bool scratch_reserve_rows(BE &be, Scratch &s, uint64_t scp_cap, uint64_t 
 
 /* records a stream of `len` bytes is expected to hold: from the previous walk's density, else from the first 256 KiB */
 template <class BE>
-inline bool estimate_records(BE &be, Scratch &sc, int k, const StreamBuf &B, uint64_t &need)
+inline bool estimate_records(BE &be, Scratch &sc, int k, const StreamBuf &B, uint64_t &need, double *mean_out = nullptr)
 {
     double mean = sc.line_bytes[k];
     if (mean <= 0) {
@@ -236,6 +237,7 @@ inline bool estimate_records(BE &be, Scratch &sc, int k, const StreamBuf &B, uin
         mean = nl ? (double)n / (double)nl : (double)n;
     }
     need = (uint64_t)((double)B.len / mean * 1.05) + 4096;
+    if (mean_out) *mean_out = mean;
     return true;
 }
 
@@ -312,11 +314,23 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
     uint64_t scp_need = 0;
     int code_first = 0;
     unsigned long long err_first = NO_ERROR;
-    for (int attempt = 0; attempt < 6; ++attempt) {
+    for (int attempt = 0; attempt < 8; ++attempt) {
         const uint64_t tile = small ? (uint64_t)CfgSmall::TILE : (uint64_t)CfgBig::TILE;
         const uint64_t nt_s = (S.len + tile - 1) / tile, nt_p = (P.len + tile - 1) / tile;
         if (nt_s > 0xffffffffull || nt_p > 0xffffffffull) { errmsg = "stream too large for one call"; return res->status = XM_ERR_ARG; }
         if (!sc_need && !estimate_records(be, sc, 1, S, sc_need)) { errmsg = "sample read failed"; return res->status = XM_ERR_CUDA; }
+        for (int k = 0; k < 2; ++k)
+            if (sc.short_lines[k] < 0) {
+                /* first walk on this context: mean LINE length of the first 64 KiB decides the span kernels' geometry; a walk
+                 * whose spans overflow switches it (below), and it stays for the walks that follow */
+                const StreamBuf &B = k ? S : P;
+                const size_t n = (size_t)(B.len < (64u << 10) ? B.len : (64u << 10));
+                std::vector<char> smp(n);
+                if (be.read(smp.data(), B.p, n)) { errmsg = "sample read failed"; return res->status = XM_ERR_CUDA; }
+                uint64_t nl = 0;
+                for (size_t q = 0; q < n; q++) nl += smp[q] == '\n';
+                sc.short_lines[k] = (nl && (double)n / (double)nl < 300.0) ? 1 : 0;
+            }
         const uint64_t nt_s2 = small ? 0 : be.scan2_tiles(S.len);               /* the barrier-free scan has its own tiling */
         const uint64_t nt_sc = nt_s > nt_s2 ? nt_s : nt_s2;
         const uint64_t nt_p2 = small ? 0 : be.scan2_tiles(P.len);               /* the row walk scans the primary stream with it too */
@@ -334,7 +348,7 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         init.limit_off = ~0ull;
         be.tick(0);                                  /* the step starts here: scratch init is part of it */
         if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_sc * 8) || be.zero(sc.chain1_p, nt_pc * 8) ||
-            be.zero(sc.chain2, nt_p * 8 * C2_SLOTS)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
+            be.zero(sc.chain2, nt_pc * 8 * C2_SLOTS)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
 
         ScanArgs sa;
         memset(&sa, 0, sizeof sa);
@@ -359,8 +373,9 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
                 if (!scratch_reserve_rows(be, sc, scp_need, (rec_bound + EM_TILE - 1) / EM_TILE + 1)) { errmsg = "out of device memory for scratch"; return res->status = XM_ERR_NOMEM; }
             }
             ScanArgs s2 = sa;
-            s2.sc = sc.sc; s2.sc_cap = sc.sc_cap;
+            s2.sc = sc.sc; s2.sc_cap = sc.sc_cap; s2.short_lines = sc.short_lines[1] > 0 ? 1 : 0;
             ScanArgs p2 = sa;
+            p2.short_lines = sc.short_lines[0] > 0 ? 1 : 0;
             p2.S = P; p2.sc = sc.scp; p2.sc_cap = sc.scp_cap; p2.chain1 = sc.chain1_p; p2.stream_id = 0;
             p2.want_same = (o.mode != MODE_SE && !sa.skip) ? 1 : 0;
             be.tick(3);
@@ -372,7 +387,11 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
                 be.tick(1);
                 if (be.read(&G, sc.g, sizeof G)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
                 res->n_launches += 2;
-                if (G.pad) { no_rows = true; continue; }
+                if (G.pad) {
+                    /* a span overflowed (or the input is not clean): spans of half the size first, then the other walks */
+                    if (!s2.short_lines || !p2.short_lines) { sc.short_lines[0] = sc.short_lines[1] = 1; continue; }
+                    no_rows = true; continue;
+                }
                 if (G.n_stream[1] > sc.sc_cap) { sc_need = G.n_stream[1] + 1; continue; }
                 if (G.n_stream[0] > sc.scp_cap) { scp_need = G.n_stream[0] + 1; continue; }
                 const uint64_t n = G.n_stream[0] < G.n_stream[1] ? G.n_stream[0] : G.n_stream[1];
@@ -411,22 +430,22 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         /* clean inputs take the barrier-free scan (xm_scan2.cuh); it says so when a span needs the exact kernel */
         bool scanned = false, have_gs = false;
         Globals Gs;
-        if (!small && !(debug & DBG_FORCE_GENERIC) && !no_scan2) {
+        for (int geom = 0; geom < 2 && !scanned && !small && !(debug & DBG_FORCE_GENERIC) && !no_scan2; ++geom) {
             ScanArgs s2 = sa;
             s2.ntiles = (uint32_t)be.scan2_tiles(S.len);
+            s2.short_lines = sc.short_lines[1] > 0 ? 1 : 0;
             const int r2 = s2.ntiles ? be.scan2(s2) : -1;
             if (r2 > 0) { errmsg = "scan kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
-            if (r2 == 0) {
-                Globals G2;
-                if (be.read(&G2, sc.g, sizeof G2)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
-                res->n_launches += 1;
-                if (!G2.pad) { scanned = true; Gs = G2; have_gs = true; sc.last_kernels |= 1u; }
-                else {
-                    no_scan2 = true;            /* and for the re-runs of this call */
-                    if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_sc * 8)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
-                    be.tick(3);
-                }
-            }
+            if (r2 < 0) break;
+            Globals G2;
+            if (be.read(&G2, sc.g, sizeof G2)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            res->n_launches += 1;
+            if (!G2.pad) { scanned = true; Gs = G2; have_gs = true; sc.last_kernels |= 1u; break; }
+            /* declined: once more with spans of half the size (a stretch of short lines overflows the 64 lines a span holds),
+             * then the exact kernel -- for the re-runs of this call too */
+            if (s2.short_lines) no_scan2 = true; else sc.short_lines[1] = 1;
+            if (be.write(sc.g, &init, sizeof init) || be.zero(sc.chain1_s, nt_sc * 8)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
+            be.tick(3);
         }
         if (!scanned) {
             sc.last_kernels |= 4u;
@@ -436,23 +455,21 @@ inline int walk_resident(BE &be, Scratch &sc, const StreamBuf &P, const StreamBu
         be.tick(1);
         /* and the barrier-free classify (k_classify2) when nothing but clean, error-free input has been seen so far */
         bool classified = false;
-        if (!small && !(debug & DBG_FORCE_GENERIC) && !no_cls2 && limit == ~0ull) {
-            if (!have_gs && be.read(&Gs, sc.g, sizeof Gs)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+        for (int geom = 0; geom < 2 && !classified && !small && !(debug & DBG_FORCE_GENERIC) && !no_cls2 && limit == ~0ull; ++geom) {
+            if (!have_gs) { if (be.read(&Gs, sc.g, sizeof Gs)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; } have_gs = true; }
+            ca.short_lines = sc.short_lines[0] > 0 ? 1 : 0;
             const int r3 = be.classify2(ca);
             if (r3 > 0) { errmsg = "classify kernel launch failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
-            if (r3 == 0) {
-                be.tick(2);
-                if (be.read(&G, sc.g, sizeof G)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
-                res->n_launches += 1;
-                if (!G.pad) { classified = true; sc.last_kernels |= 2u; }
-                else {
-                    /* back to the state the scan left, and the exact kernel */
-                    no_cls2 = true;
-                    Gs.pad = 0;
-                    if (be.write(sc.g, &Gs, sizeof Gs) || be.zero(sc.chain1_p, nt_p * 8) || be.zero(sc.chain2, nt_p * 8 * C2_SLOTS)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
-                    be.tick(1);
-                }
-            }
+            if (r3 < 0) break;
+            be.tick(2);
+            if (be.read(&G, sc.g, sizeof G)) { errmsg = "kernel execution failed: " + be.last_error(); return res->status = XM_ERR_CUDA; }
+            res->n_launches += 1;
+            if (!G.pad) { classified = true; sc.last_kernels |= 2u; break; }
+            /* back to the state the scan left; spans of half the size, then the exact kernel */
+            if (ca.short_lines) no_cls2 = true; else sc.short_lines[0] = 1;
+            Gs.pad = 0;
+            if (be.write(sc.g, &Gs, sizeof Gs) || be.zero(sc.chain1_p, nt_pc * 8) || be.zero(sc.chain2, nt_pc * 8 * C2_SLOTS)) { errmsg = "scratch init failed"; return res->status = XM_ERR_CUDA; }
+            be.tick(1);
         }
         if (!classified) {
             sc.last_kernels |= 8u;
