@@ -79,7 +79,7 @@ struct Globals {
     unsigned long long end_off[2];    /* byte offset just past the last counted record of each stream */
     unsigned long long limit_off;     /* byte offset of primary record `limit` (error re-run: locates the failing line) */
     unsigned int overflow;            /* a tile held more lines than the geometry allows: relaunch smaller */
-    unsigned int ticket[2];
+    unsigned int reserved_[2];        /* (was a tile ticket: tiles are blockIdx.x, see DESIGN section 3 on dispatch order) */
     unsigned int pad;
     unsigned long long phase[48];     /* XM_PHASE_TIMING builds: thread-0 clock cycles per tile phase, summed over tiles */
 };
@@ -98,7 +98,7 @@ struct ScanArgs {
     Globals *g;
     uint32_t ntiles;
     int32_t score_src, skip;
-    int32_t stream_id;                /* which n_stream / ticket slot this scan owns */
+    int32_t stream_id;                /* which n_stream slot this scan owns */
     uint32_t debug;
     int32_t want_same;                /* mark rows whose QNAME repeats the previous line's (META_SAME): paired walks over rows */
     int32_t count_only;               /* record counts and row offsets only: the score tokens are not parsed */
