@@ -267,10 +267,12 @@ int xm_classify_sharded_host(xm_ctx *ctx, const void *prim, uint64_t prim_len, c
 
 /* Replaces the two `samtools view` pipes of xm.py:48-64 (get_bam_header,
  * bam_lines) and getBamReadPairs (xm.py:66-93).  The BGZF blocks are inflated
- * on the host (zlib, a pool of threads), the GPU renders the alignment records
- * as the SAM text lines `samtools view` prints, in device memory, and the
- * walk runs on them; the six bins come back as with xm_classify_host.
- * Float aux values (types f, B:f) are refused with XM_ERR_UNSUPPORTED. */
+ * on the GPU (one warp per block; XM_BAM_INFLATE=host: zlib on a pool of host
+ * threads), the record chain is followed and the alignment records are rendered
+ * as the SAM text lines `samtools view` prints, in device memory, a window of
+ * the file at a time, and the walk runs on them; the six bins come back as with
+ * xm_classify_host.
+ * Float aux values (types f, B:f) print with "%g", as samtools prints them. */
 int xm_classify_bam_host(xm_ctx *ctx, const void *prim_bam, uint64_t prim_len,
                          const void *sec_bam, uint64_t sec_len, const xm_opts *opts, xm_result *res);
 /* The same with the bins appended to six descriptors as the walk goes (-1: bin disabled), plain or as BGZF members

@@ -71,14 +71,21 @@ def test_gpu_renders_synthetic_bam_back_to_its_sam(ctx, style, block):
 
 
 @pytest.mark.gpu
-def test_float_aux_is_refused_not_misprinted(ctx):
+def test_float_aux_prints_like_the_c_library(ctx):
+    """f and B:f values through the renderer against Python's "%g" of the same single-precision value (the C library's
+    conversion; tests/test_fmtg.py checks the formatter itself on a million bit patterns, scripts/check_fmtg_all.sh on all)"""
+    import random
     import struct
-    from xenomapper_b200 import _lib, synth
+    import numpy as np
+    rnd = random.Random(8)
     rec = _bamwriter.record("r1\t4\t*\t0\t0\t*\t*\t0\t0\tAC\tII", {})
-    body = rec[4:] + b"XFf" + struct.pack("<f", 1.5)
+    patterns = [rnd.getrandbits(32) for _ in range(400)] + [0x3f800000, 0x7f800000, 0xff800000, 0x00000001, 0x80000001, 0x7f7fffff, 0x49742400, 0x49742408, 0x3a83126f]
+    vals = [np.frombuffer(struct.pack("<I", b), dtype=np.float32)[0] for b in patterns]
+    vals = [v for v in vals if v == v]                      # "nan" carries a sign in some C libraries
+    body = rec[4:] + b"XFf" + struct.pack("<f", vals[0]) + b"XGBf" + struct.pack("<I", len(vals)) + b"".join(struct.pack("<f", v) for v in vals)
     raw = b"BAM\1" + struct.pack("<i", 0) + struct.pack("<i", 0) + struct.pack("<i", len(body)) + body
-    with pytest.raises(_lib.UnsupportedInput):
-        ctx.bam_render_host(_bamwriter.bgzf(raw))
+    want = "r1\t4\t*\t0\t0\t*\t*\t0\t0\tAC\tII\tXF:f:%g\tXG:B:f,%s\n" % (float(vals[0]), ",".join("%g" % float(v) for v in vals))
+    assert ctx.bam_render_host(_bamwriter.bgzf(raw)).decode() == want
 
 
 # every reference name the synthetic generator uses (its own header lists two)
@@ -171,6 +178,16 @@ AUX_VECTORS = [
     (bytes.fromhex("584f 42 69 02000000 ffffffff00000080"), "XO:B:i,-1,-2147483648"),   # B:i
     (bytes.fromhex("5850 42 49 01000000 ffffffff"), "XP:B:I,4294967295"),       # B:I
     (bytes.fromhex("5851 42 43 00000000"), "XQ:B:C"),                           # an empty array
+    # floats print as samtools prints them, "%g" (htslib sam_format1): IEEE-754 single precision, little endian
+    (bytes.fromhex("5852 66 0000c03f"), "XR:f:1.5"),                            # f  1.5
+    (bytes.fromhex("5853 66 cdcccc3d"), "XS:f:0.1"),                            #    0.1f is 0.100000001490116: six digits
+    (bytes.fromhex("5854 66 00247449"), "XT:f:1e+06"),                          #    1000000 takes the exponent form
+    (bytes.fromhex("5855 66 17b7d1b8"), "XU:f:-0.0001"),                        #    -1e-4f: the last fixed-notation exponent
+    (bytes.fromhex("5856 66 acc52737"), "XV:f:1e-05"),                          #    1e-5f
+    (bytes.fromhex("5857 66 ffff7f7f"), "XW:f:3.40282e+38"),                    #    FLT_MAX
+    (bytes.fromhex("5858 66 01000000"), "XX:f:1.4013e-45"),                     #    the smallest denormal
+    (bytes.fromhex("5859 66 00000080"), "XY:f:-0"),                             #    minus zero
+    (bytes.fromhex("585a 42 66 03000000 0000803f 0000807f 79e9f642"), "XZ:B:f,1,inf,123.456"),      # B:f
 ]
 
 

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libxenomapper_b200.so")
 SOURCES = ["xm_kernels.cu", "xm_api.cu"]
-HEADERS = ["xm_common.h", "xm_parse.h", "xm_tile.h", "xm_walk.h", "xm_launch.h", "xm_stream.h", "xm_bam.h", "xm_scan2.cuh", "xm_emit.cuh", "xm_shard.h", "xm_nccl.h", "xm_headers.h", "xm_bgzf.h", "xm_inflate.h", "xm_bamchain.h", "xm_deflate.h"]
+HEADERS = ["xm_common.h", "xm_parse.h", "xm_tile.h", "xm_walk.h", "xm_launch.h", "xm_stream.h", "xm_bam.h", "xm_scan2.cuh", "xm_emit.cuh", "xm_shard.h", "xm_nccl.h", "xm_headers.h", "xm_bgzf.h", "xm_inflate.h", "xm_bamchain.h", "xm_deflate.h", "xm_fmtg.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-lz", "-ldl"]
 

@@ -18,14 +18,16 @@
  *
  * Text rendering follows the SAM/BAM specification (sections 1.4, 4.2): the
  * aux integer types c C s S i I all print as `i`, B arrays as
- * `B:<type>,v,v...`.  Float aux values (`f`, `B:f`) are refused
- * (XM_ERR_UNSUPPORTED): printing them needs the C library's %g.
+ * `B:<type>,v,v...`, float aux values (`f`, `B:f`) with the C library's "%g"
+ * (xm_fmtg.h reproduces it digit for digit for every 32-bit float).
  */
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
 #include <zlib.h>
+
+#include "xm_fmtg.h"
 
 #include <atomic>
 #include <string>
@@ -204,6 +206,18 @@ __device__ void put_ref(S &s, const BamDev &B, int32_t id)
     for (uint32_t k = B.ref_off[id]; k < B.ref_off[id + 1]; ++k) s.ch(B.ref_names[k]);
 }
 
+/* a float aux value as samtools prints it: "%g" (xm_fmtg.h) */
+template <class S>
+__device__ void put_float(S &s, const uint8_t *p)
+{
+    const uint32_t bits = ld_u32(p);
+    float f;
+    memcpy(&f, &bits, 4);
+    char tmp[16];
+    const int n = fmt_g(f, tmp);
+    for (int k = 0; k < n; ++k) s.ch((uint8_t)tmp[k]);
+}
+
 /* size in bytes of an integer aux value of type t (0: not an integer type) */
 __device__ __forceinline__ int aux_size(uint8_t t)
 {
@@ -286,13 +300,16 @@ __device__ int bam_line(S &s, const BamDev &B, const uint8_t *r, uint32_t &l_qna
             const uint8_t st = p[0];
             const uint32_t cnt = ld_u32(p + 1);
             p += 5;
-            if (st == 'f') return BAM_E_FLOAT;
             s.ch('B'); s.ch(':'); s.ch(st);
-            const int sz = aux_size(st);
+            const int sz = st == 'f' ? 4 : aux_size(st);
             if (!sz || (unsigned long long)(end - p) < (unsigned long long)sz * cnt) return BAM_E_CORRUPT;
-            for (uint32_t k = 0; k < cnt; ++k) { s.ch(','); put_int(s, aux_int(st, p)); p += sz; }
-        } else if (t == 'f') return BAM_E_FLOAT;
-        else {
+            if (st == 'f') for (uint32_t k = 0; k < cnt; ++k) { s.ch(','); put_float(s, p); p += 4; }
+            else for (uint32_t k = 0; k < cnt; ++k) { s.ch(','); put_int(s, aux_int(st, p)); p += sz; }
+        } else if (t == 'f') {
+            if (p + 4 > end) return BAM_E_CORRUPT;
+            s.ch('f'); s.ch(':'); put_float(s, p);
+            p += 4;
+        } else {
             const int sz = aux_size(t);
             if (!sz || p + sz > end) return BAM_E_CORRUPT;
             s.ch('i'); s.ch(':'); put_int(s, aux_int(t, p));
