@@ -305,3 +305,89 @@ def test_sharded_cli_on_bam_inputs_equals_single_process_cli(tmp_path, flags):
     assert two == one
     assert summary1[summary1.index("Read Count"):].strip() in summary2
     assert sum(len(x) for x in one) > len(bytes(p)) // 2
+
+
+# ---- the ranks' BAM record chains joined (sharded._settle_entries), without a GPU ---------------------------------------------
+class _FakeChainCtx:
+    """what xm_bam_shard_open / xm_bam_shard_chain do, on a list of record offsets: a rank's part is [lo, hi) of the inflated
+    stream; its exit is the first record start at or behind hi; chained from an entry at or behind hi it answers with the entry"""
+    NONE64 = (1 << 64) - 1
+
+    def __init__(self, starts, total, lo, hi, guess):
+        self.starts, self.total, self.lo, self.hi, self.guess = starts, total, lo, hi, guess
+        self.calls = 0
+
+    def _exit(self):
+        nxt = [s for s in self.starts if s >= self.hi]
+        return nxt[0] if nxt else self.total
+
+    def open(self):
+        return (self.guess, self._exit()) if self.guess != self.NONE64 else (self.NONE64, self.NONE64)
+
+    def bam_shard_chain(self, stream, entry):
+        self.calls += 1
+        self.entry = entry
+        return entry if entry >= self.hi else self._exit()
+
+
+@pytest.mark.parametrize("world", [2, 3, 5, 8])
+@pytest.mark.parametrize("scenario", ["all right", "one wrong", "all wrong", "nothing seen", "header parts", "long record"])
+def test_bam_chain_settles_between_ranks(tmp_path, world, scenario):
+    """every rank follows its part from the exit of the ranks before it, whatever it guessed at first"""
+    import random
+    import threading
+    from xenomapper_b200 import sharded
+    rnd = random.Random(world * 7 + len(scenario))
+    total = 100000
+    first_record = 20000 if scenario == "header parts" else 137
+    starts, p = [], first_record
+    while p < total:
+        starts.append(p)
+        p += 60000 if (scenario == "long record" and len(starts) == 3) else rnd.randrange(40, 900)
+    bounds = [total * r // world for r in range(world + 1)]
+    true_entry = []
+    for r in range(world):
+        nxt = [s for s in starts if s >= bounds[r]]
+        true_entry.append(nxt[0] if nxt else total)
+    ctxs = []
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        own = [s for s in starts if lo <= s < hi]
+        if not own:
+            guess = _FakeChainCtx.NONE64                                         # nothing that looks like a record start
+        elif r == 0 or scenario == "all right" or (scenario in ("header parts", "long record", "nothing seen")):
+            guess = own[0]
+        elif scenario == "one wrong":
+            guess = own[0] if r != world // 2 else own[min(1, len(own) - 1)] + 1
+        else:
+            guess = own[min(1, len(own) - 1)] + 3                                # a false positive further in
+        if scenario == "nothing seen" and r == world - 1 and own:
+            guess = _FakeChainCtx.NONE64                                         # the guesser found nothing although records start there
+        if r == 0 and own:
+            guess = own[0]                                                       # rank 0 knows where the records start
+        ctxs.append(_FakeChainCtx(starts, total, lo, hi, guess))
+    errors = []
+
+    def run(r):
+        try:
+            rv = sharded.Rendezvous(r, world, directory=str(tmp_path / "rv"), timeout=30)
+            g, e = ctxs[r].open()
+            sharded._settle_entries(ctxs[r], r, world, rv, 0, g, e, "t")
+        except Exception as ex:                                                  # noqa: BLE001
+            errors.append((r, repr(ex)))
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join(60) for t in th]
+    assert not errors, errors
+    for r in range(world):
+        c = ctxs[r]
+        used = getattr(c, "entry", c.guess)
+        own = [s for s in starts if bounds[r] <= s < bounds[r + 1]]
+        if used == c.NONE64:
+            # a part that passes the chain on: fine only while no rank before it holds records (header) -- or it holds none itself
+            assert not own or all(not [s for s in starts if bounds[q] <= s < bounds[q + 1]] for q in range(r)) and not own
+        elif own:
+            assert used == true_entry[r], (r, used, true_entry[r])
+        else:
+            assert used >= bounds[r + 1] or used == total                        # the chain jumps over the part
