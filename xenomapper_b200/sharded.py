@@ -182,7 +182,9 @@ def sharded_bam_walk(ctx, rank, world, rv, prim_bam, sec_bam, mode=_lib.MODE_SE,
     (dp, np_), (ds, ns_) = shards
     opts = ctx.opts(mode, score_src, skip, float(min_score), enabled_bins)
     slack = 2 * room + 4096
-    caps = [np_ + slack, ns_ + slack, np_ + slack, ns_ + slack, np_ + slack, np_ + ns_ + slack]      # PS SS PM SM UA UR
+    mul = 1 if mode == _lib.MODE_SE else 2             # overlapping pair units can emit a line twice (the library's own bound)
+    pb, sb = (np_ + slack) * mul, (ns_ + slack) * mul
+    caps = [pb, sb, pb, sb, pb, pb + sb]               # PS SS PM SM UA UR
     caps = [c if (enabled_bins >> b) & 1 else 16 for b, c in enumerate(caps)]
     d_out = [ctx.dev_alloc(c) for c in caps]
     try:
